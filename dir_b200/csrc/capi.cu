@@ -1,0 +1,376 @@
+// extern "C" boundary (include/dirb200.h). No exceptions cross it; errors are codes + last_error().
+#include <dlfcn.h>
+
+#include <cstring>
+#include <new>
+
+#include "engine.h"
+
+using namespace dirb200;
+
+struct dirb200_handle {
+  Engine e;
+};
+
+static thread_local std::string g_create_err;
+
+#define H_CHECK(h)              \
+  if (!(h)) return DIRB200_E_INVALID; \
+  Engine& e = (h)->e;           \
+  e.err.clear();
+
+static int fail(Engine& e, int code, const std::string& msg) {
+  e.err = msg;
+  return code;
+}
+
+extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
+  if (!cfg || !out) {
+    g_create_err = "null argument";
+    return DIRB200_E_INVALID;
+  }
+  if (cfg->precision != DIRB200_PRECISION_FP32 && cfg->precision != DIRB200_PRECISION_BF16) {
+    g_create_err = "unknown precision";
+    return DIRB200_E_INVALID;
+  }
+  if (cfg->max_batch <= 0) {
+    g_create_err = "max_batch must be positive";
+    return DIRB200_E_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
+    g_create_err = ce != cudaSuccess ? std::string("no CUDA device: ") + cudaGetErrorString(ce)
+                                     : "device ordinal out of range";
+    return DIRB200_E_CUDA;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major != 10) {
+    g_create_err = "dirb200 is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) +
+                   std::to_string(prop.minor);
+    return DIRB200_E_CUDA;
+  }
+  dirb200_handle* h = new (std::nothrow) dirb200_handle();
+  if (!h) {
+    g_create_err = "out of host memory";
+    return DIRB200_E_INVALID;
+  }
+  h->e.cfg = *cfg;
+  // required-key inventory (no GPU work)
+  h->e.dry = true;
+  h->e.build(nullptr);
+  h->e.dry = false;
+  h->e.err.clear();
+  *out = h;
+  return DIRB200_OK;
+}
+
+extern "C" void dirb200_destroy(dirb200_handle* h) { delete h; }
+
+extern "C" const char* dirb200_last_error(const dirb200_handle* h) { return h ? h->e.err.c_str() : g_create_err.c_str(); }
+
+extern "C" int dirb200_set_weight(dirb200_handle* h, const char* name, const void* dev_ptr, int dtype, int ndim,
+                       const int64_t* shape) {
+  H_CHECK(h);
+  if (!name || !dev_ptr || ndim < 0 || (ndim > 0 && !shape)) return fail(e, DIRB200_E_INVALID, "bad set_weight argument");
+  if (dtype != DIRB200_DTYPE_F32 && dtype != DIRB200_DTYPE_I64) return fail(e, DIRB200_E_INVALID, "bad dtype");
+  RawWeight w;
+  w.p = dev_ptr;
+  w.dtype = dtype;
+  w.shape.assign(shape, shape + ndim);
+  e.raw[name] = w;
+  e.finalized = false;
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_num_required_keys(const dirb200_handle* h) { return h ? (int)h->e.required.size() : 0; }
+
+extern "C" const char* dirb200_required_key(const dirb200_handle* h, int i) {
+  if (!h || i < 0 || i >= (int)h->e.required.size()) return nullptr;
+  return h->e.required[i].c_str();
+}
+
+extern "C" int dirb200_finalize_weights(dirb200_handle* h, void* stream) {
+  H_CHECK(h);
+  cudaSetDevice(e.cfg.device);
+  std::vector<std::string> req = e.required;
+  for (void* p : e.owned) cudaFree(p);
+  e.owned.clear();
+  int rc = e.build(reinterpret_cast<cudaStream_t>(stream));
+  e.required = req;
+  if (rc != DIRB200_OK) return rc;
+  e.finalized = true;
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_workspace_bytes(const dirb200_handle* hc, int batch, size_t* bytes) {
+  dirb200_handle* h = const_cast<dirb200_handle*>(hc);
+  H_CHECK(h);
+  if (!bytes || batch <= 0) return fail(e, DIRB200_E_INVALID, "bad argument");
+  if (!e.finalized) return fail(e, DIRB200_E_STATE, "finalize_weights first");
+  Arena ar;
+  int rc = e.bf16() ? e.forward<__nv_bfloat16>(nullptr, batch, ar, nullptr, nullptr)
+                    : e.forward<float>(nullptr, batch, ar, nullptr, nullptr);
+  if (rc) return rc;
+  // the seam entry points stage NCHW<->NHWC copies in the same workspace: leave generous head-room
+  *bytes = ar.off + (size_t)batch * 4 * (2560 * 1024 + 3 * 256 * 256) + (1 << 20);
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_forward(dirb200_handle* h, const float* img, int batch, void* workspace, size_t workspace_bytes,
+                    const dirb200_outputs* out, void* stream) {
+  H_CHECK(h);
+  if (!img || !workspace || !out || !out->record || !out->mano_para || batch <= 0)
+    return fail(e, DIRB200_E_INVALID, "bad forward argument");
+  if (batch > e.cfg.max_batch) return fail(e, DIRB200_E_INVALID, "batch exceeds max_batch");
+  if (e.cfg.aux_outputs && (!out->seg || !out->dense || !out->proj_feat))
+    return fail(e, DIRB200_E_INVALID, "aux_outputs=1 needs seg/dense/proj_feat buffers");
+  if (!e.finalized) return fail(e, DIRB200_E_STATE, "finalize_weights first");
+  Arena ar;
+  ar.base = reinterpret_cast<char*>(workspace);
+  ar.size = workspace_bytes;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = e.bf16() ? e.forward<__nv_bfloat16>(img, batch, ar, out, st) : e.forward<float>(img, batch, ar, out, st);
+  if (rc == DIRB200_E_WORKSPACE) e.err = "workspace too small";
+  return rc;
+}
+
+extern "C" int dirb200_forward_launches(const dirb200_handle* h, int) { return h ? h->e.last_forward_launches : 0; }
+
+extern "C" int dirb200_profile_layer(dirb200_handle* h, const char* prefix) {
+  H_CHECK(h);
+  e.prof_on = prefix != nullptr;
+  e.prof_prefix = prefix ? prefix : "";
+  e.prof_used = 0;
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_profile_read(dirb200_handle* h, float* total_ms, int* launches, double* total_flops) {
+  H_CHECK(h);
+  float ms = 0.f;
+  double fl = 0.0;
+  for (size_t i = 0; i < e.prof_used; ++i) {
+    if (cudaEventSynchronize(e.prof[i].b) != cudaSuccess) return fail(e, DIRB200_E_CUDA, "event sync failed");
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, e.prof[i].a, e.prof[i].b) != cudaSuccess)
+      return fail(e, DIRB200_E_CUDA, "event elapsed failed");
+    ms += t;
+    fl += e.prof[i].flops;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = (int)e.prof_used;
+  if (total_flops) *total_flops = fl;
+  e.prof_used = 0;
+  return DIRB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ seams
+template <typename T>
+static int seam_backbone(Engine& e, const float* img, int B, int H, int W, float* c1, float* c2, float* c3, float* c4,
+                         Arena& ar, cudaStream_t st) {
+  T *t1 = nullptr, *t2 = nullptr, *t3 = nullptr, *t4 = nullptr;
+  int rc = e.run_backbone<T>(img, B, H, W, ar, &t1, &t2, &t3, &t4, st);
+  if (rc) return rc;
+  launch_nhwc_to_nchw<T>(t1, c1, B, 256, H / 4, W / 4, st);
+  launch_nhwc_to_nchw<T>(t2, c2, B, 512, H / 8, W / 8, st);
+  launch_nhwc_to_nchw<T>(t3, c3, B, 1024, H / 16, W / 16, st);
+  launch_nhwc_to_nchw<T>(t4, c4, B, 2048, H / 32, W / 32, st);
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_backbone(dirb200_handle* h, const float* img, int batch, int height, int width, float* c1, float* c2,
+                     float* c3, float* c4, void* workspace, size_t workspace_bytes, void* stream) {
+  H_CHECK(h);
+  if (!e.finalized) return fail(e, DIRB200_E_STATE, "finalize_weights first");
+  if (!img || !c1 || !c2 || !c3 || !c4 || batch <= 0 || height % 32 || width % 32)
+    return fail(e, DIRB200_E_INVALID, "bad backbone argument");
+  Arena ar;
+  ar.base = reinterpret_cast<char*>(workspace);
+  ar.size = workspace_bytes;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = e.bf16() ? seam_backbone<__nv_bfloat16>(e, img, batch, height, width, c1, c2, c3, c4, ar, st)
+                    : seam_backbone<float>(e, img, batch, height, width, c1, c2, c3, c4, ar, st);
+  if (rc == DIRB200_E_WORKSPACE) e.err = "workspace too small";
+  return rc;
+}
+
+template <typename T>
+static int seam_residual(Engine& e, const ResidualBlock& r, const float* x, int B, int H, int W, float* y, Arena& ar,
+                         cudaStream_t st) {
+  const int64_t n = (int64_t)B * H * W * r.cin;
+  T* raw = reinterpret_cast<T*>(ar.alloc(n * sizeof(T)));
+  T* act = reinterpret_cast<T*>(ar.alloc(n * sizeof(T)));
+  if (ar.overflow) return DIRB200_E_WORKSPACE;
+  launch_nchw_to_nhwc<T>(x, raw, B, r.cin, H, W, st);
+  launch_concat_preact<T>(raw, r.cin, 0, nullptr, 0, r.bn1s, r.bn1b, nullptr, act, B, H, W, st);
+  T* out = e.run_residual<T>(r, raw, act, B, H, W, ar, st);
+  if (!out) return DIRB200_E_WORKSPACE;
+  launch_nhwc_to_nchw<T>(out, y, B, r.cout, H, W, st);
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_residual(dirb200_handle* h, const char* name, const float* x, int batch, int cin, int height, int width,
+                     float* y, void* workspace, size_t workspace_bytes, void* stream) {
+  H_CHECK(h);
+  if (!e.finalized) return fail(e, DIRB200_E_STATE, "finalize_weights first");
+  auto it = name ? e.res.find(name) : e.res.end();
+  if (it == e.res.end()) return fail(e, DIRB200_E_INVALID, "unknown Residual block name");
+  if (it->second.cin != cin || !x || !y) return fail(e, DIRB200_E_INVALID, "bad residual argument");
+  Arena ar;
+  ar.base = reinterpret_cast<char*>(workspace);
+  ar.size = workspace_bytes;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = e.bf16() ? seam_residual<__nv_bfloat16>(e, it->second, x, batch, height, width, y, ar, st)
+                    : seam_residual<float>(e, it->second, x, batch, height, width, y, ar, st);
+  if (rc == DIRB200_E_WORKSPACE) e.err = "workspace too small";
+  return rc;
+}
+
+template <typename T>
+static int seam_init(Engine& e, const float* c4, int B, float* rec, float* para, Arena& ar, cudaStream_t st) {
+  T* x = reinterpret_cast<T*>(ar.alloc((size_t)B * 64 * 2048 * sizeof(T)));
+  if (ar.overflow) return DIRB200_E_WORKSPACE;
+  launch_nchw_to_nhwc<T>(c4, x, B, 2048, 8, 8, st);
+  return e.run_init<T>(x, B, rec, DIRB200_STAGE_FLOATS, para, 128, ar, st);
+}
+
+extern "C" int dirb200_init_regressor(dirb200_handle* h, const float* c4, int batch, float* stage_record, float* mano_para,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  H_CHECK(h);
+  if (!e.finalized) return fail(e, DIRB200_E_STATE, "finalize_weights first");
+  if (!c4 || !stage_record || !mano_para || batch <= 0) return fail(e, DIRB200_E_INVALID, "bad argument");
+  Arena ar;
+  ar.base = reinterpret_cast<char*>(workspace);
+  ar.size = workspace_bytes;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = e.bf16() ? seam_init<__nv_bfloat16>(e, c4, batch, stage_record, mano_para, ar, st)
+                    : seam_init<float>(e, c4, batch, stage_record, mano_para, ar, st);
+  if (rc == DIRB200_E_WORKSPACE) e.err = "workspace too small";
+  return rc;
+}
+
+extern "C" int dirb200_mano(dirb200_handle* h, int which, const float* para, int batch, float* stage_record, void* stream) {
+  H_CHECK(h);
+  if (!e.finalized) return fail(e, DIRB200_E_STATE, "finalize_weights first");
+  if (which < 0 || which > 2 || !para || !stage_record || batch <= 0) return fail(e, DIRB200_E_INVALID, "bad argument");
+  launch_mano_only(para, e.mano[which], stage_record, DIRB200_STAGE_FLOATS, batch, reinterpret_cast<cudaStream_t>(stream));
+  return DIRB200_OK;
+}
+
+template <typename T>
+static int seam_stage(Engine& e, int s, const float* img_feat, const float* prev_rec, const float* prev_para, int B,
+                      float* rec, float* para, float* img_feat_out, float* joint_feat, float* vis, Arena& ar,
+                      cudaStream_t st) {
+  const int S = e.stage[s].S;
+  T* x = reinterpret_cast<T*>(ar.alloc((size_t)B * S * S * 256 * sizeof(T)));
+  if (ar.overflow) return DIRB200_E_WORKSPACE;
+  launch_nchw_to_nhwc<T>(img_feat, x, B, 256, S, S, st);
+  T* out = nullptr;
+  float* jf = nullptr;
+  int rc = e.run_stage<T>(s, x, prev_rec, DIRB200_STAGE_FLOATS, prev_para, 128, B, rec, DIRB200_STAGE_FLOATS, para, 128,
+                          &out, &jf, vis, ar, st);
+  if (rc) return rc;
+  launch_nhwc_to_nchw<T>(out, img_feat_out, B, 256, S, S, st);
+  if (joint_feat)
+    cudaMemcpyAsync(joint_feat, jf, (size_t)B * 42 * 64 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_joint2bone(dirb200_handle* h, int stage, const float* img_feat, const float* prev_record,
+                       const float* prev_para, int batch, float* stage_record, float* mano_para, float* img_feat_out,
+                       float* joint_feat, float* vis_img_feat, void* workspace, size_t workspace_bytes, void* stream) {
+  H_CHECK(h);
+  if (!e.finalized) return fail(e, DIRB200_E_STATE, "finalize_weights first");
+  if (stage < 1 || stage > 2 || !img_feat || !prev_record || !prev_para || !stage_record || !mano_para ||
+      !img_feat_out || batch <= 0)
+    return fail(e, DIRB200_E_INVALID, "bad argument");
+  Arena ar;
+  ar.base = reinterpret_cast<char*>(workspace);
+  ar.size = workspace_bytes;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = e.bf16() ? seam_stage<__nv_bfloat16>(e, stage - 1, img_feat, prev_record, prev_para, batch, stage_record,
+                                                mano_para, img_feat_out, joint_feat, vis_img_feat, ar, st)
+                    : seam_stage<float>(e, stage - 1, img_feat, prev_record, prev_para, batch, stage_record, mano_para,
+                                        img_feat_out, joint_feat, vis_img_feat, ar, st);
+  if (rc == DIRB200_E_WORKSPACE) e.err = "workspace too small";
+  return rc;
+}
+
+extern "C" int dirb200_bone_proj(dirb200_handle* h, const float* uv, const float* feat, int batch, int size, float distance,
+                      float* out, void* stream) {
+  H_CHECK(h);
+  if (!uv || !feat || !out || batch <= 0 || size <= 0) return fail(e, DIRB200_E_INVALID, "bad argument");
+  launch_bone_vis_nchw(uv, nullptr, 42, feat, nullptr, 21 * 64, out, batch, size, distance, 0,
+                       reinterpret_cast<cudaStream_t>(stream));
+  return DIRB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ NCCL (run-time bound)
+namespace {
+struct NcclId {
+  char internal[128];
+};
+typedef int (*fn_get_id)(NcclId*);
+typedef int (*fn_init_rank)(void**, int, NcclId, int);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*fn_destroy)(void*);
+struct NcclApi {
+  void* lib = nullptr;
+  fn_get_id get_id = nullptr;
+  fn_init_rank init_rank = nullptr;
+  fn_allgather allgather = nullptr;
+  fn_destroy destroy = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+      err = std::string("cannot load libnccl.so.2: ") + dlerror();
+      return false;
+    }
+    get_id = (fn_get_id)dlsym(lib, "ncclGetUniqueId");
+    init_rank = (fn_init_rank)dlsym(lib, "ncclCommInitRank");
+    allgather = (fn_allgather)dlsym(lib, "ncclAllGather");
+    destroy = (fn_destroy)dlsym(lib, "ncclCommDestroy");
+    if (!get_id || !init_rank || !allgather || !destroy) {
+      err = "libnccl.so.2 lacks an expected symbol";
+      return false;
+    }
+    return true;
+  }
+} g_nccl;
+}  // namespace
+
+extern "C" int dirb200_nccl_unique_id(dirb200_handle* h, char id_out[128]) {
+  H_CHECK(h);
+  if (!id_out) return fail(e, DIRB200_E_INVALID, "null id buffer");
+  if (!g_nccl.load(e.err)) return DIRB200_E_STATE;
+  NcclId id;
+  if (g_nccl.get_id(&id) != 0) return fail(e, DIRB200_E_CUDA, "ncclGetUniqueId failed");
+  memcpy(id_out, id.internal, 128);
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_nccl_init(dirb200_handle* h, const char id[128], int rank, int world) {
+  H_CHECK(h);
+  if (!id || rank < 0 || rank >= world) return fail(e, DIRB200_E_INVALID, "bad nccl_init argument");
+  if (!g_nccl.load(e.err)) return DIRB200_E_STATE;
+  cudaSetDevice(e.cfg.device);
+  NcclId nid;
+  memcpy(nid.internal, id, 128);
+  void* comm = nullptr;
+  if (g_nccl.init_rank(&comm, world, nid, rank) != 0) return fail(e, DIRB200_E_CUDA, "ncclCommInitRank failed");
+  e.nccl_comm = comm;
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_allgather_records(dirb200_handle* h, const float* send, float* recv, int batch_local, void* stream) {
+  H_CHECK(h);
+  if (!e.nccl_comm) return fail(e, DIRB200_E_STATE, "nccl_init first");
+  if (!send || !recv || batch_local <= 0) return fail(e, DIRB200_E_INVALID, "bad allgather argument");
+  const size_t count = (size_t)batch_local * DIRB200_RECORD_FLOATS;
+  if (g_nccl.allgather(send, recv, count, /*ncclFloat32=*/7, e.nccl_comm, reinterpret_cast<cudaStream_t>(stream)) != 0)
+    return fail(e, DIRB200_E_CUDA, "ncclAllGather failed");
+  return DIRB200_OK;
+}
+

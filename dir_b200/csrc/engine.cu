@@ -1,0 +1,673 @@
+// Engine implementation: weight packing (finalize) and kernel sequencing of DIR's eval forward
+// (models/dir.py:513-540 -> backbone :516, init_regressor :517, decoder :518 / :437-483).
+#include "engine.h"
+
+#include <cstdio>
+#include <cstring>
+
+namespace dirb200 {
+
+#define CK(expr)                                                                 \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess) {                                                     \
+      err = std::string(#expr) + ": " + cudaGetErrorString(_e);                  \
+      return DIRB200_E_CUDA;                                                     \
+    }                                                                            \
+  } while (0)
+
+Engine::~Engine() {
+  for (void* p : owned) cudaFree(p);
+  for (auto& r : prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ finalize helpers
+static const float* kDummy = reinterpret_cast<const float*>(0x100);
+
+const float* Engine::W(const std::string& name, std::vector<int64_t> shape) {
+  if (dry) {
+    required.push_back(name);
+    return kDummy;
+  }
+  auto it = raw.find(name);
+  if (it == raw.end()) {
+    if (err.empty()) err = "missing state_dict key: " + name;
+    return nullptr;
+  }
+  if (it->second.dtype != DIRB200_DTYPE_F32) {
+    if (err.empty()) err = "key is not fp32: " + name;
+    return nullptr;
+  }
+  if (!shape.empty() && it->second.shape != shape) {
+    if (err.empty()) err = "shape mismatch for " + name;
+    return nullptr;
+  }
+  return reinterpret_cast<const float*>(it->second.p);
+}
+
+float* Engine::dalloc(size_t nfloats) {
+  if (dry) return nullptr;
+  void* p = nullptr;
+  if (cudaMalloc(&p, nfloats * sizeof(float)) != cudaSuccess) {
+    if (err.empty()) err = "cudaMalloc failed in finalize";
+    return nullptr;
+  }
+  owned.push_back(p);
+  return reinterpret_cast<float*>(p);
+}
+
+float* Engine::copy_of(const std::string& name) {
+  const float* src = W(name);
+  if (dry || !src) return nullptr;
+  int64_t n = raw[name].numel();
+  float* d = dalloc(n);
+  if (d) cudaMemcpyAsync(d, src, n * sizeof(float), cudaMemcpyDeviceToDevice, fin_stream);
+  return d;
+}
+
+// src is (rows, cols) row-major -> returns (cols, rows)
+float* Engine::transposed(const std::string& name, int rows, int cols) {
+  const float* src = W(name);
+  if (dry || !src) return nullptr;
+  if (raw[name].numel() != (int64_t)rows * cols) {
+    if (err.empty()) err = "unexpected size for " + name;
+    return nullptr;
+  }
+  float* d = dalloc((size_t)rows * cols);
+  if (d) launch_transpose2d(src, d, rows, cols, fin_stream);
+  return d;
+}
+
+// scale/shift = eval-BN folded with an optional preceding conv bias. Writes n values at offset `off` of
+// buffers of `total` (allocated on first use when *scale == nullptr).
+void Engine::fold(const std::string& conv_bias, const std::string& bn, float** scale, float** shift, int n, int off,
+                  int total) {
+  const float* cb = conv_bias.empty() ? nullptr : W(conv_bias);
+  const float *g = nullptr, *be = nullptr, *mu = nullptr, *var = nullptr;
+  if (!bn.empty()) {
+    g = W(bn + "weight");
+    be = W(bn + "bias");
+    mu = W(bn + "running_mean");
+    var = W(bn + "running_var");
+  }
+  if (dry || !err.empty() || n <= 0) return;
+  if (total == 0) total = n;
+  if (!*scale) {
+    *scale = dalloc(total);
+    *shift = dalloc(total);
+  }
+  if (!*scale || !*shift || !err.empty()) return;
+  launch_fold_affine(cb, g, be, mu, var, *scale + off, *shift + off, n, fin_stream);
+}
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+ConvLayer Engine::make_conv(const std::string& wname, const std::string& bias, const std::string& bn, int stride,
+                            int pad, int relu) {
+  ConvLayer L;
+  L.name = wname;
+  const float* w = W(wname);
+  L.stride = stride;
+  L.pad = pad;
+  L.relu = relu;
+  if (dry) {
+    fold(bias, bn, &L.scale, &L.shift, 0);
+    return L;
+  }
+  if (!w) return L;
+  const auto& sh = raw[wname].shape;
+  if (sh.size() != 4) {
+    if (err.empty()) err = "conv weight must be 4-D: " + wname;
+    return L;
+  }
+  L.Cout = (int)sh[0];
+  L.Cin = (int)sh[1];
+  L.kh = (int)sh[2];
+  L.kw = (int)sh[3];
+  L.K = L.kh * L.kw * L.Cin;
+  L.Kpad = round_up(L.K, 16);
+  L.w32 = dalloc((size_t)L.Cout * L.Kpad);
+  if (bf16()) L.w16 = reinterpret_cast<__nv_bfloat16*>(dalloc(((size_t)L.Cout * L.Kpad + 1) / 2));
+  if (L.w32) launch_pack_conv_weight(w, L.w32, L.w16, L.Cout, L.Cin, L.kh, L.kw, L.Kpad, fin_stream);
+  fold(bias, bn, &L.scale, &L.shift, L.Cout);
+  if (bf16() && L.w16 && err.empty()) conv_tc_prepare_weights(L);
+  return L;
+}
+
+PointMlp Engine::make_mlp(const std::string& p, int cin, int cmid, int cout) {
+  PointMlp m{};
+  m.w1t = transposed(p + "0.weight", cmid, cin);
+  float *s = nullptr, *b = nullptr;
+  fold(p + "0.bias", p + "1.", &s, &b, cmid);
+  m.s1 = s;
+  m.b1 = b;
+  m.w2t = transposed(p + "3.weight", cout, cmid);
+  m.b2 = copy_of(p + "3.bias");
+  return m;
+}
+
+ResidualBlock Engine::make_residual(const std::string& p) {
+  ResidualBlock r;
+  r.c1 = make_conv(p + "conv1.conv.weight", p + "conv1.conv.bias", p + "bn2.", 1, 0, 1);
+  r.c2 = make_conv(p + "conv2.conv.weight", p + "conv2.conv.bias", p + "bn3.", 1, 1, 1);
+  r.c3 = make_conv(p + "conv3.conv.weight", p + "conv3.conv.bias", "", 1, 0, 0);
+  r.skip = make_conv(p + "skip_layer.conv.weight", p + "skip_layer.conv.bias", "", 1, 0, 0);
+  r.cin = r.c1.Cin;
+  r.cout = r.c3.Cout;
+  r.need_skip = r.cin != r.cout;  // hourglass.py:49-52
+  fold("", p + "bn1.", &r.bn1s, &r.bn1b, r.cin);  // pre-activation BN, applied by concat_preact
+  return r;
+}
+
+ManoWeights Engine::make_mano(const std::string& p, bool left) {
+  ManoWeights m{};
+  m.comps = copy_of(p + "th_selected_comps");
+  m.mean = copy_of(p + "th_hands_mean");
+  m.shapedirs_t = transposed(p + "th_shapedirs", 2334, 10);
+  m.posedirs_t = transposed(p + "th_posedirs", 2334, 135);
+  m.v_template = copy_of(p + "th_v_template");
+  m.jreg = copy_of(p + "th_J_regressor");
+  m.skin_w = copy_of(p + "th_weights");
+  m.tip2 = left ? 445 : 444;  // manolayer.py:249-252
+  return m;
+}
+
+void Engine::build_stage(int s, const std::string& p) {
+  StageWeights& st = stage[s];
+  st.S = s == 0 ? 16 : 32;           // models/dir.py:395,401
+  st.distance = s == 0 ? 1.f : 2.f;
+  const char* sides[2] = {"left", "right"};
+  for (int h = 0; h < 2; ++h) {
+    std::string sd = sides[h];
+    st.filters[h] = make_mlp(p + "img2joint_" + sd + ".filters.", 256, 128, 128);
+    st.pos[h] = make_mlp(p + "pos_emb_" + sd + ".", 3, 128, 128);
+    for (int l = 0; l < 4; ++l) {
+      std::string q = p + "gcn_" + sd + ".gconv_layers." + std::to_string(l) + ".";
+      st.gcn[l].W[h] = copy_of(q + "gconv.W");
+      const float* e1 = W(q + "gconv.e_1");
+      float* A = dalloc(21 * 21);
+      if (!dry && e1 && A) launch_gcn_adjacency(e1, A, fin_stream);
+      st.gcn[l].A1[h] = A;
+      float *sc = nullptr, *sh = nullptr;
+      fold(q + "gconv.bias", q + "bn.", &sc, &sh, 128);
+      st.gcn[l].scale[h] = sc;
+      st.gcn[l].shift[h] = sh;
+    }
+    st.Wm[h] = copy_of(p + "regressor.mano_" + sd + ".weight");
+    st.bm[h] = copy_of(p + "regressor.mano_" + sd + ".bias");
+    mano[s + 1][h] = make_mano(p + "regressor.mano_layer_" + sd + ".", h == 0);
+  }
+  st.Wo = copy_of(p + "regressor.offset.weight");
+  st.bo = copy_of(p + "regressor.offset.bias");
+  st.gpos = make_mlp(p + "global_pos_emb.", 3, 128, 128);
+  st.proj_feat = make_mlp(p + "proj_feat_emb.", 64, 64, 64);
+  std::string q = p + "interaction.";
+  st.ste.pos = copy_of(q + "spatial_pos_embed");
+  for (int l = 0; l < 3; ++l) {  // blocks 1..3 only (mixSTE.py:197)
+    std::string bq = q + "STEblocks." + std::to_string(l + 1) + ".";
+    auto& B = st.ste.blk[l];
+    B.n1w = copy_of(bq + "norm1.weight");
+    B.n1b = copy_of(bq + "norm1.bias");
+    B.qkv_t = transposed(bq + "attn.qkv.weight", 384, 128);
+    B.qkv_b = copy_of(bq + "attn.qkv.bias");
+    B.proj_t = transposed(bq + "attn.proj.weight", 128, 128);
+    B.proj_b = copy_of(bq + "attn.proj.bias");
+    B.n2w = copy_of(bq + "norm2.weight");
+    B.n2b = copy_of(bq + "norm2.bias");
+    B.fc1_t = transposed(bq + "mlp.fc1.weight", 256, 128);
+    B.fc1_b = copy_of(bq + "mlp.fc1.bias");
+    B.fc2_t = transposed(bq + "mlp.fc2.weight", 128, 256);
+    B.fc2_b = copy_of(bq + "mlp.fc2.bias");
+  }
+  st.ste.snw = copy_of(q + "spatial_norm.weight");
+  st.ste.snb = copy_of(q + "spatial_norm.bias");
+  st.ste.hnw = copy_of(q + "head.0.weight");
+  st.ste.hnb = copy_of(q + "head.0.bias");
+  st.ste.head_t = transposed(q + "head.1.weight", 64, 128);
+  st.ste.head_b = copy_of(q + "head.1.bias");
+  st.fusion0 = make_conv(p + "fusion.0.weight", p + "fusion.0.bias", p + "fusion.1.", 1, 1, 1);
+  st.fusion3 = make_conv(p + "fusion.3.weight", p + "fusion.3.bias", "", 1, 0, 0);
+}
+
+// Two convs sharing their input, concatenated along Cout (attention_left|right, seg|dense first convs).
+static ConvLayer concat_convs(Engine& e, const std::string& w0, const std::string& b0, const std::string& bn0,
+                              const std::string& w1, const std::string& b1, const std::string& bn1, int pad, int relu) {
+  ConvLayer L;
+  L.name = w0;
+  const float* a = e.W(w0);
+  const float* b = e.W(w1);
+  L.stride = 1;
+  L.pad = pad;
+  L.relu = relu;
+  if (e.dry) {
+    e.fold(b0, bn0, &L.scale, &L.shift, 0);
+    e.fold(b1, bn1, &L.scale, &L.shift, 0);
+    return L;
+  }
+  if (!a || !b) return L;
+  const auto& sh = e.raw[w0].shape;
+  int half = (int)sh[0];
+  L.Cout = 2 * half;
+  L.Cin = (int)sh[1];
+  L.kh = (int)sh[2];
+  L.kw = (int)sh[3];
+  L.K = L.kh * L.kw * L.Cin;
+  L.Kpad = round_up(L.K, 16);
+  L.w32 = e.dalloc((size_t)L.Cout * L.Kpad);
+  if (e.bf16()) L.w16 = reinterpret_cast<__nv_bfloat16*>(e.dalloc(((size_t)L.Cout * L.Kpad + 1) / 2));
+  if (!L.w32) return L;
+  size_t hoff = (size_t)half * L.Kpad;
+  launch_pack_conv_weight(a, L.w32, L.w16, half, L.Cin, L.kh, L.kw, L.Kpad, e.fin_stream);
+  launch_pack_conv_weight(b, L.w32 + hoff, L.w16 ? L.w16 + hoff : nullptr, half, L.Cin, L.kh, L.kw, L.Kpad,
+                          e.fin_stream);
+  e.fold(b0, bn0, &L.scale, &L.shift, half, 0, L.Cout);
+  e.fold(b1, bn1, &L.scale, &L.shift, half, half, L.Cout);
+  if (e.bf16() && L.w16 && e.err.empty()) conv_tc_prepare_weights(L);
+  return L;
+}
+
+int Engine::build(cudaStream_t st) {
+  fin_stream = st;
+  required.clear();
+  // ---- backbone (models/backbone/resnet.py)
+  stem = make_conv("backbone.conv1.weight", "", "backbone.bn1.", 2, 3, 1);
+  const int nblocks[4] = {3, 4, 6, 3};
+  for (int l = 0; l < 4; ++l) {
+    layers[l].clear();
+    for (int b = 0; b < nblocks[l]; ++b) {
+      std::string p = "backbone.layer" + std::to_string(l + 1) + "." + std::to_string(b) + ".";
+      Bottleneck bk;
+      int stride = (b == 0 && l > 0) ? 2 : 1;
+      bk.c1 = make_conv(p + "conv1.weight", "", p + "bn1.", 1, 0, 1);
+      bk.c2 = make_conv(p + "conv2.weight", "", p + "bn2.", stride, 1, 1);
+      bk.c3 = make_conv(p + "conv3.weight", "", p + "bn3.", 1, 0, 1);
+      bk.has_ds = (b == 0);
+      if (bk.has_ds) bk.ds = make_conv(p + "downsample.0.weight", "", p + "downsample.1.", stride, 0, 0);
+      layers[l].push_back(bk);
+    }
+  }
+  // ---- init regressor (models/dir.py:218-305)
+  const std::string ir = "init_regressor.";
+  attn_conv = concat_convs(*this, ir + "attention_left.0.weight", ir + "attention_left.0.bias", ir + "attention_left.1.",
+                           ir + "attention_right.0.weight", ir + "attention_right.0.bias", ir + "attention_right.1.", 1,
+                           1);
+  {
+    const float* wl = W(ir + "attention_left.3.weight");
+    const float* wr = W(ir + "attention_right.3.weight");
+    const float* bl = W(ir + "attention_left.3.bias");
+    const float* br = W(ir + "attention_right.3.bias");
+    if (!dry && wl && wr && bl && br) {
+      attn_w = dalloc(2048);
+      attn_b = dalloc(2);
+      if (attn_w && attn_b) {
+        cudaMemcpyAsync(attn_w, wl, 1024 * 4, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(attn_w + 1024, wr, 1024 * 4, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(attn_b, bl, 4, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(attn_b + 1, br, 4, cudaMemcpyDeviceToDevice, st);
+      }
+    }
+  }
+  init_Wm[0] = copy_of(ir + "mano_left.weight");
+  init_bm[0] = copy_of(ir + "mano_left.bias");
+  init_Wm[1] = copy_of(ir + "mano_right.weight");
+  init_bm[1] = copy_of(ir + "mano_right.bias");
+  init_Wo = copy_of(ir + "offset.weight");
+  init_bo = copy_of(ir + "offset.bias");
+  mano[0][0] = make_mano(ir + "mano_layer_left.", true);
+  mano[0][1] = make_mano(ir + "mano_layer_right.", false);
+  // ---- decoder (models/dir.py:389-483)
+  for (const char* n : {"skip_layer4", "fusion_layer4", "enhance_layer4", "skip_layer3", "fusion_layer3",
+                        "enhance_layer3"}) {
+    std::string p = std::string("decoder.") + n + ".";
+    res[p] = make_residual(p);
+  }
+  build_stage(0, "decoder.projecter_4.");
+  build_stage(1, "decoder.projecter_3.");
+  conv_final0 = make_conv("decoder.conv_final.0.weight", "", "decoder.conv_final.1.", 1, 1, 1);
+  conv_final3 = make_conv("decoder.conv_final.3.weight", "decoder.conv_final.3.bias", "", 1, 0, 0);
+  segdense0 = concat_convs(*this, "decoder.seg.0.weight", "decoder.seg.0.bias", "decoder.seg.1.",
+                           "decoder.dense.0.weight", "decoder.dense.0.bias", "decoder.dense.1.", 1, 1);
+  seg3_w = copy_of("decoder.seg.3.weight");
+  seg3_b = copy_of("decoder.seg.3.bias");
+  dense3_w = copy_of("decoder.dense.3.weight");
+  dense3_b = copy_of("decoder.dense.3.bias");
+  if (dry) return DIRB200_OK;
+  if (!err.empty()) return err.rfind("missing", 0) == 0 ? DIRB200_E_MISSING : DIRB200_E_INVALID;
+  CK(cudaGetLastError());
+  return DIRB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ forward pieces
+template <typename T>
+void Engine::conv(const ConvLayer& L, const T* x, T* y, const T* resid, int B, int H, int W_, cudaStream_t st,
+                  bool in_nchw) {
+  const int Ho = (H + 2 * L.pad - L.kh) / L.stride + 1, Wo = (W_ + 2 * L.pad - L.kw) / L.stride + 1;
+  ++launches;
+  Engine::ProfRec* pr = nullptr;
+  if (prof_on && L.name.compare(0, prof_prefix.size(), prof_prefix) == 0) {
+    if (prof_used == prof.size()) {
+      ProfRec r;
+      cudaEventCreate(&r.a);
+      cudaEventCreate(&r.b);
+      r.flops = 0;
+      prof.push_back(r);
+    }
+    pr = &prof[prof_used++];
+    pr->flops = 2.0 * B * Ho * Wo * (double)L.Cout * L.K;
+    cudaEventRecord(pr->a, st);
+  }
+  if (sizeof(T) == 2 && !in_nchw && conv_tc_supported(L, B, H, W_)) {
+    launch_conv_tc(L, reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
+                   reinterpret_cast<const __nv_bfloat16*>(resid), B, H, W_, st);
+    if (pr) cudaEventRecord(pr->b, st);
+    return;
+  }
+  ConvArgs a;
+  a.x = x;
+  a.w32 = L.w32;
+  a.scale = L.scale;
+  a.shift = L.shift;
+  a.res = resid;
+  a.y = y;
+  a.B = B; a.H = H; a.W = W_; a.Cin = L.Cin; a.Ho = Ho; a.Wo = Wo; a.Cout = L.Cout;
+  a.kh = L.kh; a.kw = L.kw; a.stride = L.stride; a.pad = L.pad; a.K = L.K; a.Kpad = L.Kpad;
+  a.relu = L.relu;
+  a.in_nchw = in_nchw ? 1 : 0;
+  launch_conv_simt<T>(a, st);
+  if (pr) cudaEventRecord(pr->b, st);
+}
+
+template <typename T>
+static T* aalloc(Arena& ar, int64_t n) {
+  return reinterpret_cast<T*>(ar.alloc((size_t)n * sizeof(T)));
+}
+
+template <typename T>
+int Engine::run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** c1, T** c2, T** c3, T** c4,
+                         cudaStream_t st) {
+  const int H2 = H / 2, W2 = W_ / 2, H4 = H / 4, W4 = W_ / 4;
+  T* stem_out = aalloc<T>(ar, (int64_t)B * H2 * W2 * 64);
+  T* pool_out = aalloc<T>(ar, (int64_t)B * H4 * W4 * 64);
+  const int64_t rsz = (int64_t)B * H4 * W4 * 256;
+  T* R[5];
+  for (auto& r : R) r = aalloc<T>(ar, rsz);
+  T* keep[4];
+  keep[0] = nullptr;  // c1 lives in a rotating buffer unless requested
+  if (c1) keep[0] = aalloc<T>(ar, rsz);
+  keep[1] = aalloc<T>(ar, (int64_t)B * (H / 8) * (W_ / 8) * 512);
+  keep[2] = aalloc<T>(ar, (int64_t)B * (H / 16) * (W_ / 16) * 1024);
+  keep[3] = aalloc<T>(ar, (int64_t)B * (H / 32) * (W_ / 32) * 2048);
+  if (!ar.base) return DIRB200_OK;
+  if (ar.overflow) return DIRB200_E_WORKSPACE;
+
+  conv<T>(stem, reinterpret_cast<const T*>(img), stem_out, nullptr, B, H, W_, st, /*in_nchw=*/true);
+  launch_maxpool3x3s2<T>(stem_out, pool_out, B, H2, W2, 64, st);
+  ++launches;
+  const T* x = pool_out;
+  int xi = -1;  // index of the rotating buffer holding x (-1: none)
+  int h = H4, w = W4;
+  for (int l = 0; l < 4; ++l) {
+    for (size_t b = 0; b < layers[l].size(); ++b) {
+      const Bottleneck& bk = layers[l][b];
+      int idx[4], n = 0;
+      for (int i = 0; i < 5 && n < 4; ++i)
+        if (i != xi) idx[n++] = i;
+      T *t1 = R[idx[0]], *t2 = R[idx[1]], *dsb = R[idx[2]], *out = R[idx[3]];
+      const bool last = b + 1 == layers[l].size();
+      if (last && keep[l]) out = keep[l];
+      const int ho = h / bk.c2.stride, wo = w / bk.c2.stride;
+      const T* identity = x;
+      if (bk.has_ds) {
+        conv<T>(bk.ds, x, dsb, nullptr, B, h, w, st);
+        identity = dsb;
+      }
+      conv<T>(bk.c1, x, t1, nullptr, B, h, w, st);
+      conv<T>(bk.c2, t1, t2, nullptr, B, h, w, st);
+      conv<T>(bk.c3, t2, out, identity, B, ho, wo, st);
+      x = out;
+      xi = (last && keep[l]) ? -1 : idx[3];
+      h = ho;
+      w = wo;
+    }
+  }
+  if (c1) *c1 = keep[0];
+  *c2 = keep[1];
+  *c3 = keep[2];
+  *c4 = keep[3];
+  return DIRB200_OK;
+}
+
+template <typename T>
+T* Engine::run_residual(const ResidualBlock& r, const T* rawx, const T* act, int B, int H, int W_, Arena& ar,
+                        cudaStream_t st) {
+  const int64_t px = (int64_t)B * H * W_;
+  T* t1 = aalloc<T>(ar, px * r.c1.Cout);
+  T* t2 = aalloc<T>(ar, px * r.c2.Cout);
+  T* sk = r.need_skip ? aalloc<T>(ar, px * r.cout) : nullptr;
+  T* out = aalloc<T>(ar, px * r.cout);
+  if (!ar.base || ar.overflow) return nullptr;
+  conv<T>(r.c1, act, t1, nullptr, B, H, W_, st);
+  conv<T>(r.c2, t1, t2, nullptr, B, H, W_, st);
+  const T* resid = rawx;
+  if (r.need_skip) {
+    conv<T>(r.skip, rawx, sk, nullptr, B, H, W_, st);
+    resid = sk;
+  }
+  conv<T>(r.c3, t2, out, resid, B, H, W_, st);
+  return out;
+}
+
+template <typename T>
+int Engine::run_init(const T* c4, int B, float* stage_rec, int rec_stride, float* para, int para_stride, Arena& ar,
+                     cudaStream_t st) {
+  T* attn_act = aalloc<T>(ar, (int64_t)B * 64 * 2048);
+  float* attn = aalloc<float>(ar, (int64_t)B * 64 * 2);
+  float* pooled = aalloc<float>(ar, (int64_t)B * 3 * 2048);
+  if (!ar.base) return DIRB200_OK;
+  if (ar.overflow) return DIRB200_E_WORKSPACE;
+  conv<T>(attn_conv, c4, attn_act, nullptr, B, 8, 8, st);
+  launch_attn_logits<T>(attn_act, attn_w, attn_b, attn, B, 64, 1024, st);
+  launch_attn_pool<T>(c4, attn, pooled, B, 64, 2048, st);
+  RegressArgs a{};
+  for (int h = 0; h < 2; ++h) {
+    a.in0[h] = VecSeg{pooled + h * 2048, 2048, 3 * 2048};
+    a.in1[h] = VecSeg{nullptr, 0, 0};
+    a.Wm[h] = init_Wm[h];
+    a.bm[h] = init_bm[h];
+    a.mano[h] = mano[0][h];
+  }
+  a.off0 = VecSeg{pooled + 2 * 2048, 2048, 3 * 2048};
+  a.off1 = VecSeg{nullptr, 0, 0};
+  a.Wo = init_Wo;
+  a.bo = init_bo;
+  a.stage_record = stage_rec;
+  a.rec_stride = rec_stride;
+  a.mano_para = para;
+  a.para_stride = para_stride;
+  a.do_proj_feat = 0;
+  a.B = B;
+  launch_regress_mano(a, st);
+  launches += 3;
+  return DIRB200_OK;
+}
+
+template <typename T>
+int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_stride, const float* prev_para,
+                      int prev_para_stride, int B, float* stage_rec, int rec_stride, float* para, int para_stride,
+                      T** img_feat_out, float** joint_feat_out, float* vis_nchw, Arena& ar, cudaStream_t st) {
+  const StageWeights& sw = stage[s];
+  const int S = sw.S;
+  float* jf0 = aalloc<float>(ar, (int64_t)B * 42 * 128);
+  float* jf1 = aalloc<float>(ar, (int64_t)B * 42 * 128);
+  float* tok = aalloc<float>(ar, (int64_t)B * 42 * 64);
+  float* jfeat = aalloc<float>(ar, (int64_t)B * 42 * 64);
+  T* bone = aalloc<T>(ar, (int64_t)B * S * S * 2560);
+  T* fus_mid = aalloc<T>(ar, (int64_t)B * S * S * 256);
+  T* out = aalloc<T>(ar, (int64_t)B * S * S * 256);
+  if (!ar.base) return DIRB200_OK;
+  if (ar.overflow) return DIRB200_E_WORKSPACE;
+
+  EmbedArgs e{};
+  e.feat = img_feat;
+  e.S = S;
+  e.prev_record = prev_rec;
+  e.rec_stride = prev_stride;
+  for (int h = 0; h < 2; ++h) {
+    e.filters[h] = sw.filters[h];
+    e.pos[h] = sw.pos[h];
+  }
+  e.out = jf0;
+  e.B = B;
+  launch_joint_embed<T>(e, st);
+  float *gin = jf0, *gout = jf1;
+  for (int l = 0; l < 4; ++l) {
+    GcnLayerArgs g{};
+    g.x = gin;
+    g.y = gout;
+    for (int h = 0; h < 2; ++h) {
+      g.W[h] = sw.gcn[l].W[h];
+      g.A1[h] = sw.gcn[l].A1[h];
+      g.scale[h] = sw.gcn[l].scale[h];
+      g.shift[h] = sw.gcn[l].shift[h];
+    }
+    g.add_global = (l == 3);
+    g.gpos = sw.gpos;
+    g.prev_record = prev_rec;
+    g.rec_stride = prev_stride;
+    g.B = B;
+    launch_gcn_layer(g, st);
+    std::swap(gin, gout);
+  }
+  launch_ste(gin, tok, sw.ste, B, st);
+  RegressArgs a{};
+  for (int h = 0; h < 2; ++h) {
+    a.in0[h] = VecSeg{tok + h * 1344, 1344, 2688};
+    a.in1[h] = VecSeg{prev_para + h * 64, 64, prev_para_stride};
+    a.Wm[h] = sw.Wm[h];
+    a.bm[h] = sw.bm[h];
+    a.mano[h] = mano[s + 1][h];
+  }
+  a.off0 = VecSeg{tok, 2688, 2688};
+  a.off1 = VecSeg{prev_rec + DIRB200_OFF_OFFSET, 3, prev_stride};
+  a.Wo = sw.Wo;
+  a.bo = sw.bo;
+  a.stage_record = stage_rec;
+  a.rec_stride = rec_stride;
+  a.mano_para = para;
+  a.para_stride = para_stride;
+  a.do_proj_feat = 1;
+  a.proj_feat = sw.proj_feat;
+  a.joint_feat = jfeat;
+  a.B = B;
+  launch_regress_mano(a, st);
+  launch_bone_raster<T>(stage_rec, rec_stride, jfeat, bone, B, S, sw.distance, st);
+  launches += 8;
+  conv<T>(sw.fusion0, bone, fus_mid, nullptr, B, S, S, st);
+  conv<T>(sw.fusion3, fus_mid, out, nullptr, B, S, S, st);
+  if (vis_nchw) {
+    launch_bone_vis_nchw(stage_rec + DIRB200_OFF_UV_L, stage_rec + DIRB200_OFF_UV_R, rec_stride, jfeat, jfeat + 21 * 64,
+                         42 * 64, vis_nchw, B, S, sw.distance, 1, st);
+    ++launches;
+  }
+  *img_feat_out = out;
+  if (joint_feat_out) *joint_feat_out = jfeat;
+  return DIRB200_OK;
+}
+
+template <typename T>
+int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o, cudaStream_t st) {
+  launches = 0;
+  const bool plan = ar.base == nullptr;
+  T *c2 = nullptr, *c3 = nullptr, *c4 = nullptr;
+  int rc = run_backbone<T>(img, B, 256, 256, ar, nullptr, &c2, &c3, &c4, st);
+  if (rc) return rc;
+  float* rec = plan ? nullptr : o->record;
+  float* para = plan ? nullptr : o->mano_para;
+  const int RS = DIRB200_RECORD_FLOATS, PS = 3 * 128;
+  rc = run_init<T>(c4, B, rec, RS, para, PS, ar, st);
+  if (rc) return rc;
+
+  auto concat = [&](const T* s0, int C0, int up, const T* s1, int C1, const ResidualBlock& r, int S, T** rawo,
+                    T** acto) {
+    const int64_t n = (int64_t)B * S * S * (C0 + C1);
+    *rawo = s1 ? aalloc<T>(ar, n) : nullptr;
+    *acto = aalloc<T>(ar, n);
+    if (plan || ar.overflow) return;
+    launch_concat_preact<T>(s0, C0, up, s1, C1, r.bn1s, r.bn1b, *rawo, *acto, B, S, S, st);
+    ++launches;
+  };
+  // ---- stage 1 @16x16 (models/dir.py:442-456)
+  T *raw = nullptr, *act = nullptr;
+  const ResidualBlock& skip4 = res["decoder.skip_layer4."];
+  concat(c3, 1024, 0, nullptr, 0, skip4, 16, &raw, &act);
+  T* c3_skip = run_residual<T>(skip4, c3, act, B, 16, 16, ar, st);
+  const ResidualBlock& fus4 = res["decoder.fusion_layer4."];
+  concat(c4, 2048, 1, c3_skip, 256, fus4, 16, &raw, &act);
+  T* fusion4 = run_residual<T>(fus4, raw, act, B, 16, 16, ar, st);
+  T* img_feat1 = nullptr;
+  rc = run_stage<T>(0, fusion4, rec, RS, para, PS, B, plan ? nullptr : rec + DIRB200_STAGE_FLOATS, RS,
+                    plan ? nullptr : para + 128, PS, &img_feat1, nullptr, nullptr, ar, st);
+  if (rc) return rc;
+  const ResidualBlock& enh4 = res["decoder.enhance_layer4."];
+  concat(fusion4, 256, 0, img_feat1, 256, enh4, 16, &raw, &act);
+  T* enhance4 = run_residual<T>(enh4, raw, act, B, 16, 16, ar, st);
+  // ---- stage 2 @32x32 (models/dir.py:459-471)
+  const ResidualBlock& skip3 = res["decoder.skip_layer3."];
+  concat(c2, 512, 0, nullptr, 0, skip3, 32, &raw, &act);
+  T* c2_skip = run_residual<T>(skip3, c2, act, B, 32, 32, ar, st);
+  const ResidualBlock& fus3 = res["decoder.fusion_layer3."];
+  concat(enhance4, 256, 1, c2_skip, 256, fus3, 32, &raw, &act);
+  T* fusion3 = run_residual<T>(fus3, raw, act, B, 32, 32, ar, st);
+  T* img_feat2 = nullptr;
+  const bool aux = cfg.aux_outputs != 0;
+  rc = run_stage<T>(1, fusion3, plan ? nullptr : rec + DIRB200_STAGE_FLOATS, RS, plan ? nullptr : para + 128, PS, B,
+                    plan ? nullptr : rec + 2 * DIRB200_STAGE_FLOATS, RS, plan ? nullptr : para + 256, PS, &img_feat2,
+                    nullptr, (aux && !plan) ? o->proj_feat : nullptr, ar, st);
+  if (rc) return rc;
+  if (aux) {  // models/dir.py:470-476: only the seg/dense heads consume enhance_layer3
+    const ResidualBlock& enh3 = res["decoder.enhance_layer3."];
+    concat(fusion3, 256, 0, img_feat2, 256, enh3, 32, &raw, &act);
+    T* enhance3 = run_residual<T>(enh3, raw, act, B, 32, 32, ar, st);
+    const int64_t px = (int64_t)B * 32 * 32;
+    T* fmid = aalloc<T>(ar, px * 256);
+    T* feat = aalloc<T>(ar, px * 256);
+    T* sd = aalloc<T>(ar, px * 256);
+    if (!plan && !ar.overflow) {
+      conv<T>(conv_final0, enhance3, fmid, nullptr, B, 32, 32, st);
+      conv<T>(conv_final3, fmid, feat, nullptr, B, 32, 32, st);
+      conv<T>(segdense0, feat, sd, nullptr, B, 32, 32, st);
+      launch_head3<T>(sd, 256, 0, 128, seg3_w, seg3_b, o->seg, B, 1024, st);
+      launch_head3<T>(sd, 256, 128, 128, dense3_w, dense3_b, o->dense, B, 1024, st);
+      launches += 2;
+    }
+  }
+  if (plan) return DIRB200_OK;
+  if (ar.overflow) return DIRB200_E_WORKSPACE;
+  last_forward_launches = launches;
+  CK(cudaPeekAtLastError());
+  return DIRB200_OK;
+}
+
+template int Engine::forward<float>(const float*, int, Arena&, const dirb200_outputs*, cudaStream_t);
+template int Engine::forward<__nv_bfloat16>(const float*, int, Arena&, const dirb200_outputs*, cudaStream_t);
+template int Engine::run_backbone<float>(const float*, int, int, int, Arena&, float**, float**, float**, float**,
+                                         cudaStream_t);
+template int Engine::run_backbone<__nv_bfloat16>(const float*, int, int, int, Arena&, __nv_bfloat16**,
+                                                 __nv_bfloat16**, __nv_bfloat16**, __nv_bfloat16**, cudaStream_t);
+template float* Engine::run_residual<float>(const ResidualBlock&, const float*, const float*, int, int, int, Arena&,
+                                            cudaStream_t);
+template __nv_bfloat16* Engine::run_residual<__nv_bfloat16>(const ResidualBlock&, const __nv_bfloat16*,
+                                                            const __nv_bfloat16*, int, int, int, Arena&, cudaStream_t);
+template int Engine::run_init<float>(const float*, int, float*, int, float*, int, Arena&, cudaStream_t);
+template int Engine::run_init<__nv_bfloat16>(const __nv_bfloat16*, int, float*, int, float*, int, Arena&,
+                                             cudaStream_t);
+template int Engine::run_stage<float>(int, const float*, const float*, int, const float*, int, int, float*, int, float*,
+                                      int, float**, float**, float*, Arena&, cudaStream_t);
+template int Engine::run_stage<__nv_bfloat16>(int, const __nv_bfloat16*, const float*, int, const float*, int, int,
+                                              float*, int, float*, int, __nv_bfloat16**, float**, float*, Arena&,
+                                              cudaStream_t);
+
+}  // namespace dirb200

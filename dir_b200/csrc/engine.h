@@ -1,0 +1,160 @@
+// Engine: owns packed weights and sequences the kernels of DIR's eval forward.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dirb200.h"
+#include "kernels.h"
+
+namespace dirb200 {
+
+struct RawWeight {
+  const void* p;
+  int dtype;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto d : shape) n *= d;
+    return n;
+  }
+};
+
+struct ConvLayer {
+  std::string name;  // state_dict key of the weight (profiling hook / error messages)
+  int Cin = 0, Cout = 0, kh = 1, kw = 1, stride = 1, pad = 0, K = 0, Kpad = 0, relu = 0;
+  float* w32 = nullptr;
+  __nv_bfloat16* w16 = nullptr;
+  float* scale = nullptr;
+  float* shift = nullptr;
+  CUtensorMap wmap;  // bf16 weights [Cout][Kpad], box 64(k) x BN rows, 128B swizzle (tensor-core path)
+  int wmap_bn = 0;   // rows per weight box (0: no tensor map)
+};
+
+struct Bottleneck {
+  ConvLayer c1, c2, c3, ds;
+  bool has_ds = false;
+};
+
+struct ResidualBlock {  // hourglass Residual
+  int cin = 0, cout = 0;
+  bool need_skip = true;
+  float *bn1s = nullptr, *bn1b = nullptr;
+  ConvLayer c1, c2, c3, skip;
+};
+
+struct StageWeights {
+  int S = 16;
+  float distance = 1.f;
+  PointMlp filters[2], pos[2], gpos, proj_feat;
+  struct Gcn {
+    const float* W[2];
+    const float* A1[2];
+    const float* scale[2];
+    const float* shift[2];
+  } gcn[4];
+  SteWeights ste;
+  const float *Wm[2], *bm[2], *Wo, *bo;
+  ConvLayer fusion0, fusion3;
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t size = 0, off = 0;
+  bool overflow = false;
+  void* alloc(size_t bytes) {
+    size_t a = (off + 255) & ~size_t(255);
+    off = a + bytes;
+    if (!base) return nullptr;
+    if (off > size) {
+      overflow = true;
+      return nullptr;
+    }
+    return base + a;
+  }
+};
+
+struct Engine {
+  dirb200_config cfg{};
+  std::string err;
+  std::map<std::string, RawWeight> raw;
+  std::vector<std::string> required;
+  bool finalized = false;
+  bool dry = false;  // enumerate required keys without touching the GPU
+  std::vector<void*> owned;
+  cudaStream_t fin_stream = nullptr;
+  int launches = 0;
+  int last_forward_launches = 0;
+  void* nccl_comm = nullptr;
+  // timing hook (bench.py roofline): CUDA events around every conv launch whose name starts with prof_prefix
+  struct ProfRec {
+    cudaEvent_t a, b;
+    double flops;
+  };
+  bool prof_on = false;
+  std::string prof_prefix;
+  std::vector<ProfRec> prof;
+  size_t prof_used = 0;
+
+  // ---- network
+  ConvLayer stem;
+  std::vector<Bottleneck> layers[4];
+  ConvLayer attn_conv;  // both hands, Cout = 2048
+  float *attn_w = nullptr, *attn_b = nullptr;
+  const float *init_Wm[2] = {nullptr, nullptr}, *init_bm[2] = {nullptr, nullptr}, *init_Wo = nullptr, *init_bo = nullptr;
+  ManoWeights mano[3][2];
+  std::map<std::string, ResidualBlock> res;
+  StageWeights stage[2];
+  ConvLayer conv_final0, conv_final3, segdense0;
+  float *seg3_w = nullptr, *seg3_b = nullptr, *dense3_w = nullptr, *dense3_b = nullptr;
+
+  ~Engine();
+  bool bf16() const { return cfg.precision == DIRB200_PRECISION_BF16; }
+  size_t esize() const { return bf16() ? 2 : 4; }
+
+  // finalize helpers
+  int build(cudaStream_t st);
+  const float* W(const std::string& name, std::vector<int64_t> shape = {});
+  float* dalloc(size_t nfloats);
+  float* copy_of(const std::string& name);
+  float* transposed(const std::string& name, int rows, int cols);
+  void fold(const std::string& conv_bias, const std::string& bn, float** scale, float** shift, int n, int off = 0,
+            int total = 0);
+  ConvLayer make_conv(const std::string& wname, const std::string& bias, const std::string& bn, int stride, int pad,
+                      int relu);
+  void fuse_post_bn(ConvLayer& c, const std::string& conv_bias, const std::string& bn);
+  PointMlp make_mlp(const std::string& prefix, int cin, int cmid, int cout);
+  ResidualBlock make_residual(const std::string& prefix);
+  ManoWeights make_mano(const std::string& prefix, bool left);
+  void build_stage(int s, const std::string& p);
+
+  // forward pieces (T = activation element type)
+  template <typename T>
+  void conv(const ConvLayer& L, const T* x, T* y, const T* res, int B, int H, int W_, cudaStream_t st,
+            bool in_nchw = false);
+  template <typename T>
+  int run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** c1, T** c2, T** c3, T** c4, cudaStream_t st);
+  template <typename T>
+  T* run_residual(const ResidualBlock& r, const T* raw, const T* act, int B, int H, int W_, Arena& ar, cudaStream_t st);
+  template <typename T>
+  int run_init(const T* c4, int B, float* stage_rec, int rec_stride, float* para, int para_stride, Arena& ar,
+               cudaStream_t st);
+  template <typename T>
+  int run_stage(int s, const T* img_feat, const float* prev_rec, int prev_stride, const float* prev_para,
+                int prev_para_stride, int B, float* stage_rec, int rec_stride, float* para, int para_stride,
+                T** img_feat_out, float** joint_feat_out, float* vis_nchw, Arena& ar, cudaStream_t st);
+  template <typename T>
+  int forward(const float* img, int B, Arena& ar, const dirb200_outputs* out, cudaStream_t st);
+};
+
+// tensor-core conv (conv_tc.cu). Returns false if the shape is not supported (caller falls back to CUDA cores).
+bool conv_tc_supported(const ConvLayer& L, int B, int H, int W);
+int conv_tc_prepare_weights(ConvLayer& L);  // builds L.wmap
+int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bfloat16* res, int B,
+                   int H, int W, cudaStream_t st);
+
+}  // namespace dirb200

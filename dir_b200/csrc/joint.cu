@@ -1,0 +1,514 @@
+// Joint-space kernels of one refinement stage (models/dir.py:86-130): everything between the
+// feature map and the fusion conv. All arithmetic fp32; feature maps may be fp32 or bf16 NHWC.
+//   joint_embed : F.grid_sample gather + img2joint filters + pos_emb          (dir.py:94-101,197-200)
+//   gcn_layer   : PGraphConv + BN1d + ReLU (+ global_pos_emb on the last one) (p_graph_conv.py:39-60, p_gcn.py:20-27, dir.py:106-110)
+//   ste         : mixSTE blocks 1..3 + head                                    (mixSTE.py:194-205)
+//   bone_raster : bone_proj rasterisation                                      (dir.py:132-174)
+#include "../../include/dirb200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dirb200 {
+
+namespace {
+
+constexpr int NJ = 21;
+
+// =================================================================== joint_embed
+template <typename T>
+__global__ void __launch_bounds__(128) joint_embed_kernel(EmbedArgs a) {
+  __shared__ __align__(16) float samp[NJ][256];
+  __shared__ __align__(16) float hid[NJ][128];
+  __shared__ float xyz[NJ][3];
+  __shared__ float uv[NJ][2];
+  const int b = blockIdx.x, hand = blockIdx.y, n = threadIdx.x;
+  const float* rec = a.prev_record + (int64_t)b * a.rec_stride;
+  if (n < NJ * 3) xyz[n / 3][n % 3] = rec[DIRB200_OFF_JOINT_L + hand * 63 + n] / 0.15f;
+  if (n < NJ * 2) uv[n / 2][n % 2] = rec[DIRB200_OFF_UV_L + hand * 42 + n];
+  __syncthreads();
+
+  // ---- bilinear gather, zeros padding, align_corners=False
+  const int S = a.S;
+  const T* feat = reinterpret_cast<const T*>(a.feat) + (int64_t)b * S * S * 256;
+  for (int j = 0; j < NJ; ++j) {
+    float ix = ((uv[j][0] + 1.f) * S - 1.f) * 0.5f;
+    float iy = ((uv[j][1] + 1.f) * S - 1.f) * 0.5f;
+    float fx = floorf(ix), fy = floorf(iy);
+    int x0 = (int)fx, y0 = (int)fy;
+    float wx1 = ix - fx, wy1 = iy - fy;
+    float wx0 = (fx + 1.f) - ix, wy0 = (fy + 1.f) - iy;
+    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        int xi = x0 + dx, yi = y0 + dy;
+        if (xi < 0 || xi >= S || yi < 0 || yi >= S) continue;
+        float w = (dx ? wx1 : wx0) * (dy ? wy1 : wy0);
+        const T* p = feat + ((int64_t)yi * S + xi) * 256;
+        v0 = fmaf(ActIO<T>::ld(p + n), w, v0);
+        v1 = fmaf(ActIO<T>::ld(p + n + 128), w, v1);
+      }
+    samp[j][n] = v0;
+    samp[j][n + 128] = v1;
+  }
+  __syncthreads();
+
+  float acc[NJ];
+  float outv[NJ];
+  // ---- filters: 256 -> 128 (BN, ReLU) -> 128
+  {
+    const PointMlp& f = a.filters[hand];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
+    for (int k = 0; k < 256; k += 4) {
+      float w0 = __ldg(f.w1t + (k + 0) * 128 + n), w1 = __ldg(f.w1t + (k + 1) * 128 + n);
+      float w2 = __ldg(f.w1t + (k + 2) * 128 + n), w3 = __ldg(f.w1t + (k + 3) * 128 + n);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        float4 s = *reinterpret_cast<const float4*>(&samp[j][k]);
+        acc[j] = fmaf(s.x, w0, acc[j]);
+        acc[j] = fmaf(s.y, w1, acc[j]);
+        acc[j] = fmaf(s.z, w2, acc[j]);
+        acc[j] = fmaf(s.w, w3, acc[j]);
+      }
+    }
+    float s1 = f.s1[n], b1 = f.b1[n];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) hid[j][n] = fmaxf(fmaf(acc[j], s1, b1), 0.f);
+    __syncthreads();
+    float b2 = f.b2[n];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
+    for (int k = 0; k < 128; k += 4) {
+      float w0 = __ldg(f.w2t + (k + 0) * 128 + n), w1 = __ldg(f.w2t + (k + 1) * 128 + n);
+      float w2 = __ldg(f.w2t + (k + 2) * 128 + n), w3 = __ldg(f.w2t + (k + 3) * 128 + n);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        float4 s = *reinterpret_cast<const float4*>(&hid[j][k]);
+        acc[j] = fmaf(s.x, w0, acc[j]);
+        acc[j] = fmaf(s.y, w1, acc[j]);
+        acc[j] = fmaf(s.z, w2, acc[j]);
+        acc[j] = fmaf(s.w, w3, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) outv[j] = acc[j] + b2;
+    __syncthreads();
+  }
+  // ---- pos_emb: 3 -> 128 (BN, ReLU) -> 128
+  {
+    const PointMlp& f = a.pos[hand];
+    float w0 = f.w1t[n], w1 = f.w1t[128 + n], w2 = f.w1t[256 + n];
+    float s1 = f.s1[n], b1 = f.b1[n];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      float h = fmaf(xyz[j][2], w2, fmaf(xyz[j][1], w1, xyz[j][0] * w0));
+      hid[j][n] = fmaxf(fmaf(h, s1, b1), 0.f);
+    }
+    __syncthreads();
+    float b2 = f.b2[n];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
+    for (int k = 0; k < 128; k += 4) {
+      float q0 = __ldg(f.w2t + (k + 0) * 128 + n), q1 = __ldg(f.w2t + (k + 1) * 128 + n);
+      float q2 = __ldg(f.w2t + (k + 2) * 128 + n), q3 = __ldg(f.w2t + (k + 3) * 128 + n);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        float4 s = *reinterpret_cast<const float4*>(&hid[j][k]);
+        acc[j] = fmaf(s.x, q0, acc[j]);
+        acc[j] = fmaf(s.y, q1, acc[j]);
+        acc[j] = fmaf(s.z, q2, acc[j]);
+        acc[j] = fmaf(s.w, q3, acc[j]);
+      }
+    }
+    float* out = a.out + ((int64_t)(b * 2 + hand) * NJ) * 128 + n;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) out[j * 128] = outv[j] + (acc[j] + b2);
+  }
+}
+
+// =================================================================== gcn_layer
+constexpr int GBT = 32;  // images per CTA
+
+__global__ void __launch_bounds__(128) gcn_layer_kernel(GcnLayerArgs a) {
+  __shared__ __align__(16) float xs[GBT][128];
+  const int i = blockIdx.x, hand = blockIdx.y, b0 = blockIdx.z * GBT, n = threadIdx.x;
+  const int nb = min(GBT, a.B - b0);
+  const float* W = a.W[hand];
+  const float* A1 = a.A1[hand];
+  float tot[GBT];
+#pragma unroll
+  for (int bb = 0; bb < GBT; ++bb) tot[bb] = 0.f;
+
+  // sources: self (W[0][i], weight 1) then neighbours j (W[1][j], weight A1[i][j])
+  for (int src = -1; src < NJ; ++src) {
+    float aw;
+    const float* Wsrc;
+    int j;
+    if (src < 0) {
+      aw = 1.f;
+      j = i;
+      Wsrc = W + (int64_t)i * 128 * 128;
+    } else {
+      aw = A1[i * NJ + src];
+      if (aw == 0.f) continue;
+      j = src;
+      Wsrc = W + (int64_t)(NJ + src) * 128 * 128;
+    }
+    __syncthreads();
+    for (int bb = 0; bb < GBT; ++bb)
+      xs[bb][n] = (bb < nb) ? a.x[((int64_t)((b0 + bb) * 2 + hand) * NJ + j) * 128 + n] : 0.f;
+    __syncthreads();
+    float acc[GBT];
+#pragma unroll
+    for (int bb = 0; bb < GBT; ++bb) acc[bb] = 0.f;
+    for (int k = 0; k < 128; k += 4) {
+      float w0 = __ldg(Wsrc + (k + 0) * 128 + n), w1 = __ldg(Wsrc + (k + 1) * 128 + n);
+      float w2 = __ldg(Wsrc + (k + 2) * 128 + n), w3 = __ldg(Wsrc + (k + 3) * 128 + n);
+#pragma unroll
+      for (int bb = 0; bb < GBT; ++bb) {
+        float4 s = *reinterpret_cast<const float4*>(&xs[bb][k]);
+        acc[bb] = fmaf(s.x, w0, acc[bb]);
+        acc[bb] = fmaf(s.y, w1, acc[bb]);
+        acc[bb] = fmaf(s.z, w2, acc[bb]);
+        acc[bb] = fmaf(s.w, w3, acc[bb]);
+      }
+    }
+#pragma unroll
+    for (int bb = 0; bb < GBT; ++bb) tot[bb] = fmaf(aw, acc[bb], tot[bb]);
+  }
+  const float sc = a.scale[hand][n], sh = a.shift[hand][n];
+#pragma unroll
+  for (int bb = 0; bb < GBT; ++bb) tot[bb] = fmaxf(fmaf(tot[bb], sc, sh), 0.f);
+
+  if (a.add_global) {  // + global_pos_emb(xyz/0.15 -/+ offset/2)   (models/dir.py:106-110)
+    __syncthreads();
+    const PointMlp& g = a.gpos;
+    float w0 = g.w1t[n], w1 = g.w1t[128 + n], w2 = g.w1t[256 + n];
+    float s1 = g.s1[n], b1 = g.b1[n];
+    const float sgn = hand == 0 ? -1.f : 1.f;
+    for (int bb = 0; bb < GBT; ++bb) {
+      float h = 0.f;
+      if (bb < nb) {
+        const float* rec = a.prev_record + (int64_t)(b0 + bb) * a.rec_stride;
+        const float* p = rec + DIRB200_OFF_JOINT_L + hand * 63 + i * 3;
+        const float* off = rec + DIRB200_OFF_OFFSET;
+        float px = p[0] / 0.15f + sgn * (off[0] / 2.f);
+        float py = p[1] / 0.15f + sgn * (off[1] / 2.f);
+        float pz = p[2] / 0.15f + sgn * (off[2] / 2.f);
+        h = fmaxf(fmaf(fmaf(pz, w2, fmaf(py, w1, px * w0)), s1, b1), 0.f);
+      }
+      xs[bb][n] = h;
+    }
+    __syncthreads();
+    float acc[GBT];
+#pragma unroll
+    for (int bb = 0; bb < GBT; ++bb) acc[bb] = 0.f;
+    for (int k = 0; k < 128; k += 4) {
+      float q0 = __ldg(g.w2t + (k + 0) * 128 + n), q1 = __ldg(g.w2t + (k + 1) * 128 + n);
+      float q2 = __ldg(g.w2t + (k + 2) * 128 + n), q3 = __ldg(g.w2t + (k + 3) * 128 + n);
+#pragma unroll
+      for (int bb = 0; bb < GBT; ++bb) {
+        float4 s = *reinterpret_cast<const float4*>(&xs[bb][k]);
+        acc[bb] = fmaf(s.x, q0, acc[bb]);
+        acc[bb] = fmaf(s.y, q1, acc[bb]);
+        acc[bb] = fmaf(s.z, q2, acc[bb]);
+        acc[bb] = fmaf(s.w, q3, acc[bb]);
+      }
+    }
+    const float b2 = g.b2[n];
+#pragma unroll
+    for (int bb = 0; bb < GBT; ++bb) tot[bb] += acc[bb] + b2;
+  }
+#pragma unroll
+  for (int bb = 0; bb < GBT; ++bb)
+    if (bb < nb) a.y[((int64_t)((b0 + bb) * 2 + hand) * NJ + i) * 128 + n] = tot[bb];
+}
+
+// =================================================================== STE
+constexpr int NT = 42;
+constexpr int STE_THREADS = 256;
+constexpr int SC_LD = 44;
+constexpr int STE_SMEM_FLOATS = NT * 128 * 2 + NT * 384 + 4 * NT * SC_LD;
+
+// out[r][n] = sum_k in[r][k] * Wt[k][n] + bias[n]; optional GELU; optional residual accumulate into out.
+// work item = (n, row-half) with 21 rows each.
+template <int MODE>  // 0: store, 1: store GELU, 2: out += result
+__device__ __forceinline__ void ste_linear(const float* __restrict__ in, int ldin, int K, const float* __restrict__ Wt,
+                                           const float* __restrict__ bias, int N, float* __restrict__ out, int ldout) {
+  for (int item = threadIdx.x; item < N * 2; item += STE_THREADS) {
+    const int n = item % N, half = item / N;
+    const float* inr = in + half * 21 * ldin;
+    float acc[21];
+#pragma unroll
+    for (int r = 0; r < 21; ++r) acc[r] = 0.f;
+    for (int k = 0; k < K; k += 4) {
+      float w0 = __ldg(Wt + (int64_t)(k + 0) * N + n), w1 = __ldg(Wt + (int64_t)(k + 1) * N + n);
+      float w2 = __ldg(Wt + (int64_t)(k + 2) * N + n), w3 = __ldg(Wt + (int64_t)(k + 3) * N + n);
+#pragma unroll
+      for (int r = 0; r < 21; ++r) {
+        float4 s = *reinterpret_cast<const float4*>(inr + r * ldin + k);
+        acc[r] = fmaf(s.x, w0, acc[r]);
+        acc[r] = fmaf(s.y, w1, acc[r]);
+        acc[r] = fmaf(s.z, w2, acc[r]);
+        acc[r] = fmaf(s.w, w3, acc[r]);
+      }
+    }
+    const float bb = bias[n];
+    float* o = out + half * 21 * ldout + n;
+#pragma unroll
+    for (int r = 0; r < 21; ++r) {
+      float v = acc[r] + bb;
+      if (MODE == 1) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+      if (MODE == 2)
+        o[r * ldout] += v;
+      else
+        o[r * ldout] = v;
+    }
+  }
+}
+
+// LayerNorm over 128 channels, one warp per row (two-pass like ATen)
+__device__ __forceinline__ void ste_layernorm(const float* __restrict__ in, float* __restrict__ out,
+                                              const float* __restrict__ w, const float* __restrict__ b, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < NT; r += STE_THREADS / 32) {
+    float4 v = *reinterpret_cast<const float4*>(in + r * 128 + lane * 4);
+    float mu = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
+    float dx = v.x - mu, dy = v.y - mu, dz = v.z - mu, dw = v.w - mu;
+    float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.f / 128.f);
+    float rs = rsqrtf(var + eps);
+    float4 g = __ldg(reinterpret_cast<const float4*>(w + lane * 4));
+    float4 be = __ldg(reinterpret_cast<const float4*>(b + lane * 4));
+    float4 o = make_float4(dx * rs * g.x + be.x, dy * rs * g.y + be.y, dz * rs * g.z + be.z, dw * rs * g.w + be.w);
+    *reinterpret_cast<float4*>(out + r * 128 + lane * 4) = o;
+  }
+}
+
+__global__ void __launch_bounds__(STE_THREADS) ste_kernel(const float* __restrict__ xin, float* __restrict__ yout,
+                                                          SteWeights w) {
+  extern __shared__ __align__(16) float sm[];
+  float* x = sm;                   // [42][128] residual stream
+  float* h = x + NT * 128;         // [42][128] LN output / attention output
+  float* big = h + NT * 128;       // [42][384] qkv, later [42][256] MLP hidden
+  float* sc = big + NT * 384;      // [4][42][44] attention probabilities
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < NT * 128; i += STE_THREADS) x[i] = xin[(int64_t)b * NT * 128 + i] + w.pos[i];
+  __syncthreads();
+  for (int l = 0; l < 3; ++l) {
+    const SteWeights::Block& B = w.blk[l];
+    ste_layernorm(x, h, B.n1w, B.n1b, 1e-6f);
+    __syncthreads();
+    ste_linear<0>(h, 128, 128, B.qkv_t, B.qkv_b, 384, big, 384);
+    __syncthreads();
+    // scores = q k^T * 32^-0.5
+    for (int item = tid; item < 4 * NT * NT; item += STE_THREADS) {
+      int j = item % NT, t = item / NT;
+      int i = t % NT, hd = t / NT;
+      const float* q = big + i * 384 + hd * 32;
+      const float* k = big + j * 384 + 128 + hd * 32;
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; d += 4) {
+        float4 a4 = *reinterpret_cast<const float4*>(q + d);
+        float4 b4 = *reinterpret_cast<const float4*>(k + d);
+        s = fmaf(a4.x, b4.x, s); s = fmaf(a4.y, b4.y, s); s = fmaf(a4.z, b4.z, s); s = fmaf(a4.w, b4.w, s);
+      }
+      sc[(hd * NT + i) * SC_LD + j] = s * 0.17677669529663688110f;
+    }
+    __syncthreads();
+    {  // softmax rows
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int r = warp; r < 4 * NT; r += STE_THREADS / 32) {
+        float* row = sc + r * SC_LD;
+        float v0 = row[lane], v1 = (lane + 32 < NT) ? row[lane + 32] : -INFINITY;
+        float mx = warp_max(fmaxf(v0, v1));
+        float e0 = expf(v0 - mx), e1 = (lane + 32 < NT) ? expf(v1 - mx) : 0.f;
+        float inv = 1.f / warp_sum(e0 + e1);
+        row[lane] = e0 * inv;
+        if (lane + 32 < NT) row[lane + 32] = e1 * inv;
+      }
+    }
+    __syncthreads();
+    // o = P v  -> h[i][hd*32+d]
+    for (int item = tid; item < NT * 128; item += STE_THREADS) {
+      int c = item & 127, i = item >> 7;
+      int hd = c >> 5;
+      const float* p = sc + (hd * NT + i) * SC_LD;
+      const float* v = big + 256 + c;
+      float s = 0.f;
+#pragma unroll 6
+      for (int j = 0; j < NT; ++j) s = fmaf(p[j], v[j * 384], s);
+      h[item] = s;
+    }
+    __syncthreads();
+    ste_linear<2>(h, 128, 128, B.proj_t, B.proj_b, 128, x, 128);
+    __syncthreads();
+    ste_layernorm(x, h, B.n2w, B.n2b, 1e-6f);
+    __syncthreads();
+    ste_linear<1>(h, 128, 128, B.fc1_t, B.fc1_b, 256, big, 256);
+    __syncthreads();
+    ste_linear<2>(big, 256, 256, B.fc2_t, B.fc2_b, 128, x, 128);
+    __syncthreads();
+    ste_layernorm(x, x, w.snw, w.snb, 1e-6f);  // shared spatial_norm (mixSTE.py:200), in place (row-local)
+    __syncthreads();
+  }
+  ste_layernorm(x, h, w.hnw, w.hnb, 1e-5f);
+  __syncthreads();
+  ste_linear<0>(h, 128, 128, w.head_t, w.head_b, 64, big, 64);
+  __syncthreads();
+  for (int i = tid; i < NT * 64; i += STE_THREADS) yout[(int64_t)b * NT * 64 + i] = big[i];
+}
+
+// =================================================================== bone rasterisation
+struct BoneGeom {
+  float ax, ay, bx, by, dx, dy;
+};
+
+// Per (pixel, bone): capsule test + endpoint weights, op-for-op as the reference (no FMA contraction in
+// the mask so that boundary pixels agree with the PyTorch eager kernels).
+__device__ __forceinline__ bool bone_weights(const BoneGeom& g, float px, float py, float distance, float& wa,
+                                             float& wb) {
+  float s = __fadd_rn(__fmul_rn(__fsub_rn(g.ax, px), g.dx), __fmul_rn(__fsub_rn(g.ay, py), g.dy));
+  float t = __fadd_rn(__fmul_rn(__fsub_rn(px, g.bx), g.dx), __fmul_rn(__fsub_rn(py, g.by), g.dy));
+  float h = fmaxf(fmaxf(s, t), 0.f);
+  float c = __fsub_rn(__fmul_rn(__fsub_rn(px, g.ax), g.dy), __fmul_rn(__fsub_rn(py, g.ay), g.dx));
+  float dist = hypotf(h, c);
+  if (!(dist < distance)) return false;  // NaN (degenerate bone) -> false
+  float ex = __fadd_rn(__fsub_rn(px, g.ax), 1e-6f), ey = __fadd_rn(__fsub_rn(py, g.ay), 1e-6f);
+  float da = sqrtf(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
+  ex = __fadd_rn(__fsub_rn(px, g.bx), 1e-6f);
+  ey = __fadd_rn(__fsub_rn(py, g.by), 1e-6f);
+  float db = sqrtf(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
+  float sum = __fadd_rn(da, db);
+  wa = 1.f - da / sum;
+  wb = 1.f - db / sum;
+  return true;
+}
+
+__device__ __forceinline__ BoneGeom make_bone(const float* uv /*21x2*/, int bone, int S) {
+  int pa = (bone % 4 == 0) ? 0 : bone;  // parents [0,1,2,3,0,5,6,7,...], child = bone+1
+  int ch = bone + 1;
+  BoneGeom g;
+  g.ax = (uv[pa * 2] + 1.f) / 2.f * S;
+  g.ay = (uv[pa * 2 + 1] + 1.f) / 2.f * S;
+  g.bx = (uv[ch * 2] + 1.f) / 2.f * S;
+  g.by = (uv[ch * 2 + 1] + 1.f) / 2.f * S;
+  float ex = g.bx - g.ax, ey = g.by - g.ay;
+  float len = hypotf(ex, ey);
+  g.dx = ex / len;
+  g.dy = ey / len;
+  return g;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bone_raster_kernel(const float* __restrict__ rec, int rec_stride,
+                                                          const float* __restrict__ jf, T* __restrict__ out, int S,
+                                                          float distance) {
+  __shared__ BoneGeom geo[40];
+  __shared__ float uv[84];
+  __shared__ __align__(16) float feat[2 * NJ * 64];
+  const int b = blockIdx.x, y = blockIdx.y, tid = threadIdx.x;
+  if (tid < 84) uv[tid] = rec[(int64_t)b * rec_stride + DIRB200_OFF_UV_L + tid];
+  for (int i = tid; i < 2 * NJ * 64; i += 256) feat[i] = jf[(int64_t)b * 2 * NJ * 64 + i];
+  __syncthreads();
+  if (tid < 40) geo[tid] = make_bone(uv + (tid / 20) * 42, tid % 20, S);
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const float py = y + 0.5f;
+  T* orow = out + ((int64_t)b * S + y) * S * 2560;
+  for (int item = warp; item < S * 40; item += 8) {
+    int x = item / 40, hb = item % 40;
+    float wa, wb;
+    float2 v = make_float2(0.f, 0.f);
+    if (bone_weights(geo[hb], x + 0.5f, py, distance, wa, wb)) {
+      int hand = hb / 20, bone = hb % 20;
+      int pa = (bone % 4 == 0) ? 0 : bone, ch = bone + 1;
+      float2 fa = *reinterpret_cast<const float2*>(&feat[(hand * NJ + pa) * 64 + lane * 2]);
+      float2 fb = *reinterpret_cast<const float2*>(&feat[(hand * NJ + ch) * 64 + lane * 2]);
+      v.x = __fadd_rn(__fmul_rn(fa.x, wa), __fmul_rn(fb.x, wb));
+      v.y = __fadd_rn(__fmul_rn(fa.y, wa), __fmul_rn(fb.y, wb));
+    }
+    T* o = orow + (int64_t)x * 2560 + hb * 64 + lane * 2;
+    if (sizeof(T) == 4) {
+      *reinterpret_cast<float2*>(o) = v;
+    } else {
+      *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(v.x, v.y);
+    }
+  }
+}
+
+// vis = left (+ right), NCHW fp32: out[b][bone*64+c][y][x]
+__global__ void __launch_bounds__(256) bone_vis_kernel(const float* __restrict__ uv_l, const float* __restrict__ uv_r,
+                                                       int uv_stride, const float* __restrict__ f_l,
+                                                       const float* __restrict__ f_r, int f_stride,
+                                                       float* __restrict__ out, int S, float distance, int add_right) {
+  __shared__ float uv[2][42];
+  __shared__ float fe[2][2][64];  // [hand][a/b][c]
+  __shared__ BoneGeom geo[2];
+  const int b = blockIdx.x, bone = blockIdx.y, tid = threadIdx.x;
+  const int pa = (bone % 4 == 0) ? 0 : bone, ch = bone + 1;
+  if (tid < 42) uv[0][tid] = uv_l[(int64_t)b * uv_stride + tid];
+  if (tid >= 64 && tid < 106 && add_right) uv[1][tid - 64] = uv_r[(int64_t)b * uv_stride + tid - 64];
+  if (tid >= 128) {
+    int c = (tid - 128) & 63, ab = (tid - 128) >> 6;
+    fe[0][ab][c] = f_l[(int64_t)b * f_stride + (ab ? ch : pa) * 64 + c];
+    fe[1][ab][c] = add_right ? f_r[(int64_t)b * f_stride + (ab ? ch : pa) * 64 + c] : 0.f;
+  }
+  __syncthreads();
+  if (tid == 0) geo[0] = make_bone(uv[0], bone, S);
+  if (tid == 32 && add_right) geo[1] = make_bone(uv[1], bone, S);
+  __syncthreads();
+  float* ob = out + ((int64_t)b * 1280 + bone * 64) * S * S;
+  for (int p = tid; p < S * S; p += 256) {
+    int y = p / S, x = p % S;
+    float wal = 0.f, wbl = 0.f, war = 0.f, wbr = 0.f;
+    bool ml = bone_weights(geo[0], x + 0.5f, y + 0.5f, distance, wal, wbl);
+    bool mr = add_right ? bone_weights(geo[1], x + 0.5f, y + 0.5f, distance, war, wbr) : false;
+    for (int c = 0; c < 64; ++c) {
+      float vl = ml ? __fadd_rn(__fmul_rn(fe[0][0][c], wal), __fmul_rn(fe[0][1][c], wbl)) : 0.f;
+      float vr = mr ? __fadd_rn(__fmul_rn(fe[1][0][c], war), __fmul_rn(fe[1][1][c], wbr)) : 0.f;
+      ob[(int64_t)c * S * S + p] = vl + vr;
+    }
+  }
+}
+
+}  // namespace
+
+template <typename T>
+void launch_joint_embed(const EmbedArgs& a, cudaStream_t st) {
+  joint_embed_kernel<T><<<dim3(a.B, 2), 128, 0, st>>>(a);
+}
+template void launch_joint_embed<float>(const EmbedArgs&, cudaStream_t);
+template void launch_joint_embed<__nv_bfloat16>(const EmbedArgs&, cudaStream_t);
+
+void launch_gcn_layer(const GcnLayerArgs& a, cudaStream_t st) {
+  gcn_layer_kernel<<<dim3(NJ, 2, ceil_div(a.B, GBT)), 128, 0, st>>>(a);
+}
+
+void launch_ste(const float* x, float* y, const SteWeights& w, int B, cudaStream_t st) {
+  static bool attr_set = false;
+  const int smem = STE_SMEM_FLOATS * (int)sizeof(float);
+  if (!attr_set) {
+    cudaFuncSetAttribute(ste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_set = true;
+  }
+  ste_kernel<<<B, STE_THREADS, smem, st>>>(x, y, w);
+}
+
+template <typename T>
+void launch_bone_raster(const float* rec, int rec_stride, const float* jf, T* out, int B, int S, float distance,
+                        cudaStream_t st) {
+  bone_raster_kernel<T><<<dim3(B, S), 256, 0, st>>>(rec, rec_stride, jf, out, S, distance);
+}
+template void launch_bone_raster<float>(const float*, int, const float*, float*, int, int, float, cudaStream_t);
+template void launch_bone_raster<__nv_bfloat16>(const float*, int, const float*, __nv_bfloat16*, int, int, float,
+                                                cudaStream_t);
+
+void launch_bone_vis_nchw(const float* uv_l, const float* uv_r, int uv_stride, const float* f_l, const float* f_r,
+                          int f_stride, float* out, int B, int S, float distance, int add_right, cudaStream_t st) {
+  bone_vis_kernel<<<dim3(B, 20), 256, 0, st>>>(uv_l, uv_r, uv_stride, f_l, f_r, f_stride, out, S, distance, add_right);
+}
+
+}  // namespace dirb200

@@ -1,0 +1,275 @@
+"""Drop-in host module: same constructor, forward signature and state_dict keys as the reference's
+`DIR` (models/dir.py:486-596), with the eval forward executed by the sm_100a kernels behind the
+C ABI (include/dirb200.h). `apps/eval.py:104-111,168` works unchanged with
+`from dir_b200 import DIR`.
+
+    network = DIR(21, './misc/mano').cuda()
+    network.load_state_dict(state, strict=False); network.eval()
+    result, _ = network({'img': imgTensors}, None, None)
+
+Host code is PyTorch only for plumbing (device memory, streams, state_dict); no torch op touches
+the data path. The training branch (models/dir.py:542-594) is out of scope and raises.
+"""
+import ctypes as C
+import json
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_KEYS_JSON = os.path.join(_HERE, "state_dict_keys.json")
+
+STAGE_KEYS = [  # (key in outs_list[i], offset name, trailing shape) — models/dir.py:521-535
+    ("pd_joint_uv_left", "uv_l", (21, 2)), ("pd_joint_uv_right", "uv_r", (21, 2)),
+    ("pd_mesh_xyz_left", "mesh_l", (778, 3)), ("pd_mesh_xyz_right", "mesh_r", (778, 3)),
+    ("pd_joint_xyz_left", "joint_l", (21, 3)), ("pd_joint_xyz_right", "joint_r", (21, 3)),
+    ("pd_proj_left", "proj_l", (3,)), ("pd_proj_right", "proj_r", (3,)), ("pd_offset", "offset", (3,)),
+]
+
+
+class _Node(nn.Module):
+    """Anonymous container; the tree only exists to reproduce the reference's state_dict key names."""
+
+
+def _is_buffer(name):
+    leaf = name.rsplit(".", 1)[-1]
+    return leaf in ("running_mean", "running_var", "num_batches_tracked", "img_gird") or "mano_layer_" in name \
+        or name == "seg_loss.weight"
+
+
+def _default_init(name, shape):
+    leaf = name.rsplit(".", 1)[-1]
+    if leaf == "num_batches_tracked":
+        return torch.zeros((), dtype=torch.long)
+    if leaf == "th_faces":
+        return torch.zeros(shape, dtype=torch.long)
+    if leaf == "running_var" or leaf in ("e_0", "e_1"):
+        return torch.ones(shape)
+    if leaf == "weight" and len(shape) == 1:
+        return torch.ones(shape)
+    if leaf in ("weight", "W") and len(shape) >= 2:
+        fan_in = 1
+        for d in shape[1:]:
+            fan_in *= d
+        return torch.randn(shape) * math.sqrt(2.0 / fan_in)
+    if leaf == "img_gird":
+        s = int(round(math.sqrt(shape[0])))
+        r = torch.arange(s, dtype=torch.float32) + 0.5
+        gx, gy = torch.meshgrid(r, r, indexing="ij")
+        return torch.stack((gy, gx), dim=-1).reshape(s * s, 2).contiguous()
+    return torch.zeros(shape)
+
+
+def reference_key_shapes():
+    with open(_KEYS_JSON) as f:
+        return json.load(f)
+
+
+class DIR(nn.Module):
+    """B200-native DIR. Extra keyword arguments (all optional, defaults keep the reference call valid):
+    precision 'bf16' | 'fp32'; aux_outputs: also return seg/dense/proj_feat (outs_list[3]);
+    max_batch: larger batches are processed in chunks; use_cuda_graph: capture one graph per batch size."""
+
+    def __init__(self, joint_num, mano_path, root_joint=0, precision="bf16", aux_outputs=True, max_batch=128,
+                 use_cuda_graph=False):
+        super().__init__()
+        if joint_num != 21:
+            raise ValueError("DIR is defined for the 21-joint hand skeleton (models/dir.py:25-26)")
+        if root_joint != 0:
+            raise ValueError("only root_joint=0 (wrist) is built; the reference default (config.py:10)")
+        self.joint_num = joint_num
+        self.mano_path = mano_path
+        self.precision = precision
+        self.aux_outputs = bool(aux_outputs)
+        self.max_batch = int(max_batch)
+        self.use_cuda_graph = bool(use_cuda_graph)
+        for name, shape in reference_key_shapes().items():
+            parts = name.split(".")
+            m = self
+            for p in parts[:-1]:
+                if p not in m._modules:
+                    m.add_module(p, _Node())
+                m = m._modules[p]
+            t = _default_init(name, tuple(shape))
+            if _is_buffer(name):
+                m.register_buffer(parts[-1], t)
+            else:
+                m.register_parameter(parts[-1], nn.Parameter(t, requires_grad=False))
+        self._handle = None
+        self._loaded_keys = None
+        self._packed = False
+        self._workspace = {}
+        self._graphs = {}
+        self.eval()
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict, strict=True, allow_missing=False, **kw):
+        """Same call as the reference (apps/eval.py:107-108 uses strict=False). Unlike nn.Module we do
+        not let strict=False hide a key the kernels need: that raises unless allow_missing=True."""
+        res = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._loaded_keys = None if allow_missing else set(state_dict.keys())
+        self._packed = False
+        self._graphs.clear()
+        return res
+
+    def _apply(self, fn, *a, **k):
+        self._packed = False
+        self._graphs = {}
+        return super()._apply(fn, *a, **k)
+
+    def _device(self):
+        return self.backbone.conv1.weight.device
+
+    def _ensure_handle(self):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise capi.DirB200Error("DIR runs on an sm_100a CUDA device only (call .cuda()); there is no CPU fallback")
+        if self._handle is None:
+            self._handle = capi.Handle(self.precision, self.max_batch, self.aux_outputs, dev.index or 0)
+        return self._handle
+
+    def required_keys(self):
+        return self._ensure_handle().required_keys()
+
+    def _pack(self):
+        h = self._ensure_handle()
+        if self._loaded_keys is not None:  # coverage check that strict=False would have hidden
+            missing = sorted(k for k in h.required_keys() if k not in self._loaded_keys)
+            if missing:
+                raise KeyError(f"the loaded state_dict lacks {len(missing)} keys the DIR forward needs, "
+                               f"e.g. {missing[:4]} (pass allow_missing=True to load_state_dict to override)")
+        keep = []
+        with torch.cuda.device(self._device()):
+            for name, t in self.state_dict().items():
+                if t.dtype == torch.int64:
+                    dtype = capi.DTYPE_I64
+                else:
+                    t = t.detach().to(torch.float32)
+                    dtype = capi.DTYPE_F32
+                t = t.contiguous()
+                keep.append(t)
+                h.set_weight(name, t.data_ptr(), dtype, list(t.shape))
+            stream = torch.cuda.current_stream()
+            h.finalize(stream.cuda_stream)
+            stream.synchronize()
+        del keep
+        self._packed = True
+        self._workspace.clear()
+
+    # ------------------------------------------------------------------ forward
+    def _workspace_for(self, B):
+        if B not in self._workspace:
+            n = self._handle.workspace_bytes(B)
+            self._workspace[B] = torch.empty(n, dtype=torch.uint8, device=self._device())
+        return self._workspace[B]
+
+    def _alloc_outputs(self, B):
+        dev = self._device()
+        o = {"record": torch.empty(B, capi.RECORD_FLOATS, device=dev),
+             "mano_para": torch.empty(B, 3, 2, 64, device=dev)}
+        if self.aux_outputs:
+            o["seg"] = torch.empty(B, 3, 32, 32, device=dev)
+            o["dense"] = torch.empty(B, 3, 32, 32, device=dev)
+            o["proj_feat"] = torch.empty(B, 1280, 32, 32, device=dev)
+        return o
+
+    def _enqueue(self, x, o):
+        h = self._handle
+        B = x.shape[0]
+        ws = self._workspace_for(B)
+        outs = capi.Outputs(o["record"].data_ptr(), o["mano_para"].data_ptr(),
+                            o["seg"].data_ptr() if self.aux_outputs else None,
+                            o["dense"].data_ptr() if self.aux_outputs else None,
+                            o["proj_feat"].data_ptr() if self.aux_outputs else None)
+        rc = h.lib.dirb200_forward(h.h, C.c_void_p(x.data_ptr()), B, C.c_void_p(ws.data_ptr()), ws.numel(),
+                                   C.byref(outs), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        h.check(rc, "dirb200_forward")
+
+    def _run_chunk(self, x):
+        B = x.shape[0]
+        if not self.use_cuda_graph:
+            o = self._alloc_outputs(B)
+            self._enqueue(x, o)
+            return o
+        if B not in self._graphs:
+            sx = torch.empty_like(x)
+            so = self._alloc_outputs(B)
+            sx.copy_(x)
+            self._enqueue(sx, so)  # warm-up outside capture (sets function attributes)
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue(sx, so)
+            self._graphs[B] = (g, sx, so)
+        g, sx, so = self._graphs[B]
+        sx.copy_(x)
+        g.replay()
+        return {k: v.clone() for k, v in so.items()}
+
+    def run_raw(self, img):
+        """img (B,3,256,256) on the module's device -> dict of packed output buffers (record, mano_para, ...)."""
+        self._ensure_handle()
+        if not self._packed:
+            self._pack()
+        x = img.to(device=self._device(), dtype=torch.float32).contiguous()
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, 256, 256):
+            raise ValueError(f"expected (B,3,256,256) images, got {tuple(x.shape)}")
+        with torch.cuda.device(self._device()):
+            if x.shape[0] <= self.max_batch:
+                return self._run_chunk(x)
+            parts = [self._run_chunk(x[i:i + self.max_batch]) for i in range(0, x.shape[0], self.max_batch)]
+            return {k: torch.cat([p[k] for p in parts], 0) for k in parts[0]}
+
+    @staticmethod
+    def unpack_record(record, aux=None):
+        """(B, 3*4887) packed record -> the reference's outs_list (views, no copies)."""
+        B = record.shape[0]
+        outs = []
+        for i in range(3):
+            d = {}
+            for key, off, shp in STAGE_KEYS:
+                a = i * capi.STAGE_FLOATS + capi.OFF[off]
+                n = 1
+                for s in shp:
+                    n *= s
+                d[key] = record[:, a:a + n].unflatten(1, shp) if len(shp) > 1 else record[:, a:a + n]
+            d["pd_rel_joint"] = None
+            outs.append(d)
+        if aux is not None:
+            outs.append(aux)
+        return outs
+
+    def forward(self, input, target=None, meta_info=None):
+        if self.training:
+            raise NotImplementedError("only the eval branch of DIR.forward (models/dir.py:513-540) is built; "
+                                      "call .eval()")
+        o = self.run_raw(input["img"])
+        aux = {"dense": o["dense"], "seg": o["seg"], "proj_feat": o["proj_feat"]} if self.aux_outputs else \
+              {"dense": None, "seg": None, "proj_feat": None}
+        return self.unpack_record(o["record"], aux), {}
+
+    # ------------------------------------------------------------------ multi-GPU (batch sharding + one all-gather)
+    def init_nccl(self, rank, world, broadcast_bytes):
+        """Create the library's NCCL communicator. `broadcast_bytes(b: bytes|None) -> bytes` must return rank 0's
+        128-byte id on every rank (e.g. via torch.distributed.broadcast_object_list)."""
+        h = self._ensure_handle()
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            h.check(h.lib.dirb200_nccl_unique_id(h.h, buf), "nccl_unique_id")
+        uid = broadcast_bytes(bytes(buf.raw) if rank == 0 else None)
+        with torch.cuda.device(self._device()):
+            h.check(h.lib.dirb200_nccl_init(h.h, uid, rank, world), "nccl_init")
+        self._world = world
+
+    def allgather_records(self, record):
+        h = self._handle
+        B = record.shape[0]
+        out = torch.empty(self._world * B, capi.RECORD_FLOATS, device=record.device)
+        rc = h.lib.dirb200_allgather_records(h.h, C.c_void_p(record.data_ptr()), C.c_void_p(out.data_ptr()), B,
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        h.check(rc, "allgather_records")
+        return out

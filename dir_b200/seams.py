@@ -1,0 +1,136 @@
+"""Per-seam entry points of the C ABI, mirroring the reference sub-modules' call
+signatures so the parity tests read like calls into the reference:
+
+    ResNet.forward, Residual.forward, InitRegressor.forward, ManoLayer.forward (+projection),
+    Joint2BoneFeature.forward, Joint2BoneFeature.bone_proj
+
+All tensors are fp32 CUDA tensors in the reference's own layouts (NCHW feature maps).
+"""
+import ctypes as C
+
+import torch
+
+from . import capi
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _prep(model, B):
+    model._ensure_handle()
+    if not model._packed:
+        model._pack()
+    ws = model._workspace_for(max(B, 1))
+    return model._handle, ws
+
+
+def _f32(t):
+    return t.detach().to(dtype=torch.float32).contiguous()
+
+
+def stage_dict(rec, para=None):
+    """(B,4887) stage slice -> dict with the reference's result keys."""
+    out = {}
+    for key, off, shp in __import__("dir_b200.module", fromlist=["STAGE_KEYS"]).STAGE_KEYS:
+        a = capi.OFF[off]
+        n = 1
+        for s in shp:
+            n *= s
+        out[key] = rec[:, a:a + n].reshape(rec.shape[0], *shp)
+    if para is not None:
+        out["pd_mano_para_left"] = para[:, 0]
+        out["pd_mano_para_right"] = para[:, 1]
+    return out
+
+
+def pack_prev(prev, device):
+    """Build the (B,4887) record slice + (B,2,64) para a stage consumes from a dict with the reference's keys
+    (pd_joint_xyz_*, pd_joint_uv_*, pd_mano_para_*, pd_offset) — models/dir.py:446-454."""
+    B = prev["pd_offset"].shape[0]
+    rec = torch.zeros(B, capi.STAGE_FLOATS, device=device)
+    rec[:, capi.OFF["joint_l"]:capi.OFF["joint_l"] + 63] = prev["pd_joint_xyz_left"].reshape(B, -1)
+    rec[:, capi.OFF["joint_r"]:capi.OFF["joint_r"] + 63] = prev["pd_joint_xyz_right"].reshape(B, -1)
+    rec[:, capi.OFF["uv_l"]:capi.OFF["uv_l"] + 42] = prev["pd_joint_uv_left"].reshape(B, -1)
+    rec[:, capi.OFF["uv_r"]:capi.OFF["uv_r"] + 42] = prev["pd_joint_uv_right"].reshape(B, -1)
+    rec[:, capi.OFF["offset"]:capi.OFF["offset"] + 3] = prev["pd_offset"].reshape(B, 3)
+    para = torch.stack((prev["pd_mano_para_left"], prev["pd_mano_para_right"]), 1).to(device).contiguous()
+    return rec, para
+
+
+def backbone(model, img):
+    img = _f32(img)
+    B, _, H, W = img.shape
+    h, ws = _prep(model, B)
+    dev = img.device
+    c1 = torch.empty(B, 256, H // 4, W // 4, device=dev)
+    c2 = torch.empty(B, 512, H // 8, W // 8, device=dev)
+    c3 = torch.empty(B, 1024, H // 16, W // 16, device=dev)
+    c4 = torch.empty(B, 2048, H // 32, W // 32, device=dev)
+    h.check(h.lib.dirb200_backbone(h.h, _ptr(img), B, H, W, _ptr(c1), _ptr(c2), _ptr(c3), _ptr(c4), _ptr(ws),
+                                   ws.numel(), _stream()), "backbone")
+    return [c1, c2, c3, c4]
+
+
+def residual(model, name, x):
+    x = _f32(x)
+    B, Cin, H, W = x.shape
+    h, ws = _prep(model, B)
+    cout = model.state_dict()[name + "conv3.conv.weight"].shape[0]
+    y = torch.empty(B, cout, H, W, device=x.device)
+    h.check(h.lib.dirb200_residual(h.h, name.encode(), _ptr(x), B, Cin, H, W, _ptr(y), _ptr(ws), ws.numel(),
+                                   _stream()), "residual")
+    return y
+
+
+def init_regressor(model, c4):
+    c4 = _f32(c4)
+    B = c4.shape[0]
+    h, ws = _prep(model, B)
+    rec = torch.zeros(B, capi.STAGE_FLOATS, device=c4.device)
+    para = torch.zeros(B, 2, 64, device=c4.device)
+    h.check(h.lib.dirb200_init_regressor(h.h, _ptr(c4), B, _ptr(rec), _ptr(para), _ptr(ws), ws.numel(), _stream()),
+            "init_regressor")
+    return stage_dict(rec, para)
+
+
+def mano(model, which, para):
+    """para (B,2,64) -> stage dict (verts/joints/uv for both hands)."""
+    para = _f32(para)
+    B = para.shape[0]
+    h, _ = _prep(model, B)
+    rec = torch.zeros(B, capi.STAGE_FLOATS, device=para.device)
+    h.check(h.lib.dirb200_mano(h.h, which, _ptr(para), B, _ptr(rec), _stream()), "mano")
+    return stage_dict(rec)
+
+
+def joint2bone(model, stage, img_feat, prev, want_vis=False):
+    img_feat = _f32(img_feat)
+    B, _, S, _ = img_feat.shape
+    h, ws = _prep(model, B)
+    dev = img_feat.device
+    prev_rec, prev_para = pack_prev(prev, dev)
+    rec = torch.zeros(B, capi.STAGE_FLOATS, device=dev)
+    para = torch.zeros(B, 2, 64, device=dev)
+    out_feat = torch.empty(B, 256, S, S, device=dev)
+    jf = torch.empty(B, 2, 21, 64, device=dev)
+    vis = torch.empty(B, 1280, S, S, device=dev) if want_vis else None
+    h.check(h.lib.dirb200_joint2bone(h.h, stage, _ptr(img_feat), _ptr(prev_rec), _ptr(prev_para), B, _ptr(rec),
+                                     _ptr(para), _ptr(out_feat), _ptr(jf), _ptr(vis), _ptr(ws), ws.numel(),
+                                     _stream()), "joint2bone")
+    feats = {"img_feat": out_feat, "joint_feat_left": jf[:, 0], "joint_feat_right": jf[:, 1], "vis_img_feat": vis}
+    return stage_dict(rec, para), feats
+
+
+def bone_proj(model, uv, feat, size, distance):
+    uv, feat = _f32(uv), _f32(feat)
+    B = uv.shape[0]
+    h, _ = _prep(model, B)
+    out = torch.empty(B, 1280, size, size, device=uv.device)
+    h.check(h.lib.dirb200_bone_proj(h.h, _ptr(uv), _ptr(feat), B, size, float(distance), _ptr(out), _stream()),
+            "bone_proj")
+    return out

@@ -1,0 +1,144 @@
+/*
+ * dirb200.h — C ABI of the B200-native DIR inference hot path.
+ *
+ * The reference (PengfeiRen96/DIR) has no FFI/plugin layer: its only seam is the
+ * nn.Module interface `DIR.forward(input, target, meta_info)` (models/dir.py:513-540)
+ * plus its state_dict key set. This header is the boundary a host binds instead of
+ * that module's PyTorch ops (the Python host in dir_b200/module.py binds it with
+ * ctypes; INTEGRATION.md shows the stub). Each entry point cites what it replaces.
+ *
+ * Conventions: every function returns 0 on success or a negative DIRB200_E_* code and
+ * never throws; dirb200_last_error() gives the message. All device buffers (weights in,
+ * image in, workspace, outputs) are allocated and owned by the CALLER; the library only
+ * allocates its own packed-weight copies inside dirb200_finalize_weights(). Every
+ * compute call is asynchronous on the given CUDA stream, performs no host sync and is
+ * CUDA-graph capturable. One handle per device; a handle is not thread-safe.
+ * `stream` is a cudaStream_t passed as void*.
+ */
+#ifndef DIRB200_H_
+#define DIRB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIRB200_OK 0
+#define DIRB200_E_INVALID (-1)   /* bad argument / unknown name / shape mismatch */
+#define DIRB200_E_STATE (-2)     /* call order violated (e.g. forward before finalize) */
+#define DIRB200_E_CUDA (-3)      /* a CUDA runtime/driver call failed */
+#define DIRB200_E_MISSING (-4)   /* finalize: a required state_dict key was never set */
+#define DIRB200_E_WORKSPACE (-5) /* workspace too small */
+
+#define DIRB200_PRECISION_FP32 0 /* fp32 activations + fp32 CUDA-core contractions (parity config) */
+#define DIRB200_PRECISION_BF16 1 /* bf16 feature maps, tcgen05 bf16 MMA with fp32 accumulate; joint space fp32 */
+
+#define DIRB200_DTYPE_F32 0
+#define DIRB200_DTYPE_I64 1
+
+/* floats per image in the packed output record: 3 stages x 4887 */
+#define DIRB200_STAGE_FLOATS 4887
+#define DIRB200_RECORD_FLOATS (3 * DIRB200_STAGE_FLOATS)
+/* offsets inside one stage of the record */
+#define DIRB200_OFF_MESH_L 0
+#define DIRB200_OFF_MESH_R 2334
+#define DIRB200_OFF_JOINT_L 4668
+#define DIRB200_OFF_JOINT_R 4731
+#define DIRB200_OFF_UV_L 4794
+#define DIRB200_OFF_UV_R 4836
+#define DIRB200_OFF_PROJ_L 4878
+#define DIRB200_OFF_PROJ_R 4881
+#define DIRB200_OFF_OFFSET 4884
+
+typedef struct dirb200_handle dirb200_handle;
+
+typedef struct dirb200_config {
+  int precision;   /* DIRB200_PRECISION_* */
+  int max_batch;   /* largest per-call batch the handle will be asked for */
+  int aux_outputs; /* 1: also compute seg/dense/proj_feat (models/dir.py:474-482,536-540) */
+  int device;      /* CUDA device ordinal */
+} dirb200_config;
+
+/* Caller-owned output buffers of one forward (device pointers). */
+typedef struct dirb200_outputs {
+  float* record;    /* (B, DIRB200_RECORD_FLOATS): per image, 3 stages x [mesh_l mesh_r joint_l joint_r uv_l uv_r
+                       proj_l proj_r offset] == the 9 tensors per stage of outs_list[0..2] (models/dir.py:521-535) */
+  float* mano_para; /* (B, 3, 2, 64): pd_mano_para_{left,right} per stage (models/dir.py:291-292,370-371) */
+  float* seg;       /* (B,3,32,32) NCHW or NULL when aux_outputs=0 */
+  float* dense;     /* (B,3,32,32) NCHW or NULL */
+  float* proj_feat; /* (B,1280,32,32) NCHW or NULL */
+} dirb200_outputs;
+
+/* Lifetime. Replaces DIR.__init__ (models/dir.py:487-511) minus weight creation. */
+int dirb200_create(const dirb200_config* cfg, dirb200_handle** out);
+void dirb200_destroy(dirb200_handle* h);
+const char* dirb200_last_error(const dirb200_handle* h); /* h may be NULL: last create() error */
+
+/* Weights. Replaces nn.Module.load_state_dict (apps/eval.py:107-108): call set_weight once per
+ * state_dict key (reference key names, fp32 or int64 device tensors, contiguous, PyTorch layout),
+ * then finalize_weights, which folds BN, repacks to kernel layouts, precomputes the SemGCN softmax
+ * adjacency and verifies key coverage (strict). Source tensors may be freed after finalize returns
+ * and the stream is synchronised by the caller. */
+int dirb200_set_weight(dirb200_handle* h, const char* name, const void* dev_ptr, int dtype, int ndim,
+                       const int64_t* shape);
+int dirb200_finalize_weights(dirb200_handle* h, void* stream);
+int dirb200_num_required_keys(const dirb200_handle* h);
+const char* dirb200_required_key(const dirb200_handle* h, int i);
+
+/* Whole forward. Replaces DIR.forward's eval branch (models/dir.py:513-540).
+ * img: (B,3,256,256) fp32 NCHW, ImageNet-normalised, device memory. */
+int dirb200_workspace_bytes(const dirb200_handle* h, int batch, size_t* bytes);
+int dirb200_forward(dirb200_handle* h, const float* img, int batch, void* workspace, size_t workspace_bytes,
+                    const dirb200_outputs* out, void* stream);
+/* number of kernels one dirb200_forward(batch) enqueues (for launch accounting) */
+int dirb200_forward_launches(const dirb200_handle* h, int batch);
+
+/* Kernel timing hook (bench.py's roofline line): CUDA events are recorded on the launch stream around every
+ * conv launch whose weight key starts with `prefix` (e.g. "decoder.projecter_3.fusion.0"; "" = all convs;
+ * NULL disables). profile_read synchronises those events, returns their summed duration, the number of launches
+ * and their algorithmic FLOPs (2*M*N*K) since the last read, and resets. Not usable under graph capture. */
+int dirb200_profile_layer(dirb200_handle* h, const char* prefix);
+int dirb200_profile_read(dirb200_handle* h, float* total_ms, int* launches, double* total_flops);
+
+/* Per-seam entry points; used by the parity tests. All tensors fp32 device memory,
+ * feature maps NCHW exactly as the reference module sees them; conversion to the internal NHWC /
+ * bf16 layout happens inside, in `workspace`. */
+/* ResNet.forward (models/backbone/resnet.py:243-255): img (B,3,H,W) -> c1..c4 NCHW fp32 */
+int dirb200_backbone(dirb200_handle* h, const float* img, int batch, int height, int width, float* c1, float* c2,
+                     float* c3, float* c4, void* workspace, size_t workspace_bytes, void* stream);
+/* Residual.forward (models/backbone/hourglass.py:55-70); name = "decoder.enhance_layer4." etc. */
+int dirb200_residual(dirb200_handle* h, const char* name, const float* x, int batch, int cin, int height, int width,
+                     float* y, void* workspace, size_t workspace_bytes, void* stream);
+/* InitRegressor.forward (models/dir.py:260-305): c4 (B,2048,8,8) -> stage-0 slice of record + mano_para */
+int dirb200_init_regressor(dirb200_handle* h, const float* c4, int batch, float* stage_record /*(B,4887)*/,
+                           float* mano_para /*(B,2,64)*/, void* workspace, size_t workspace_bytes, void* stream);
+/* manopth ManoLayer.forward + projection_batch_xy (manopth/manopth/manolayer.py:110-270, utils/utils.py:47-63):
+ * para (B,2,64) = [pose51|beta10|proj3] per hand -> stage slice of the record. `which` = 0 init_regressor,
+ * 1 projecter_4.regressor, 2 projecter_3.regressor (six buffer copies live in the state_dict). */
+int dirb200_mano(dirb200_handle* h, int which, const float* para, int batch, float* stage_record, void* stream);
+/* Joint2BoneFeature.forward (models/dir.py:86-130); stage = 1 (projecter_4, S=16) or 2 (projecter_3, S=32).
+ * img_feat (B,256,S,S); prev_record (B,4887) and prev_para (B,2,64) from the previous stage.
+ * Outputs: stage_record (B,4887), mano_para (B,2,64), img_feat_out (B,256,S,S), joint_feat (B,2,21,64),
+ * vis_img_feat (B,1280,S,S) or NULL. */
+int dirb200_joint2bone(dirb200_handle* h, int stage, const float* img_feat, const float* prev_record,
+                       const float* prev_para, int batch, float* stage_record, float* mano_para, float* img_feat_out,
+                       float* joint_feat, float* vis_img_feat, void* workspace, size_t workspace_bytes, void* stream);
+/* Joint2BoneFeature.bone_proj (models/dir.py:146-174): uv (B,21,2), feat (B,21,64) -> (B,1280,S,S) */
+int dirb200_bone_proj(dirb200_handle* h, const float* uv, const float* feat, int batch, int size, float distance,
+                      float* out, void* stream);
+
+/* Multi-GPU: images shard over ranks with no exchange inside the forward; the only
+ * collective is one all-gather of the per-image records over NVLink (the reference has no distributed
+ * code at all). The library resolves NCCL at run time (dlopen of the libnccl the host process already
+ * loaded); rank 0 creates the id, the host broadcasts the 128 bytes, every rank calls nccl_init.
+ * send (B_local, RECORD) -> recv (world*B_local, RECORD), rank-major. */
+int dirb200_nccl_unique_id(dirb200_handle* h, char id_out[128]);
+int dirb200_nccl_init(dirb200_handle* h, const char id[128], int rank, int world);
+int dirb200_allgather_records(dirb200_handle* h, const float* send, float* recv, int batch_local, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIRB200_H_ */

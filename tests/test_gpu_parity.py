@@ -1,0 +1,343 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): every call goes through the C ABI
+(dir_b200/libdirb200.so) and is compared with the CPU oracle (oracle/dir_oracle.py) on the same
+seeded inputs, with the committed golden outputs of the unmodified reference (tests/golden/), and
+— at the benchmark's full batch — through size-independent properties.
+
+Tolerances (relative = max|a-b| / max|b| per tensor):
+  fp32 configuration : 1e-4   (north_star's bar; measured ~1e-6..1e-5)
+  bf16 configuration : stated per test, measured values are printed (bf16 feature maps cannot meet 1e-4;
+                       SURVEY.md H1 measured 0.2 mm drift for the reference's own bf16 autocast).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-4
+
+
+def rel(a, b):
+    a = a.detach().float().cpu()
+    b = torch.as_tensor(b).float().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def X():
+    from oracle.gen_golden import seam_inputs
+
+    return seam_inputs()
+
+
+def _make(synth_sd, precision, **kw):
+    import dir_b200
+
+    m = dir_b200.DIR(21, "./misc/mano", precision=precision, **kw).cuda()
+    m.load_state_dict(synth_sd, strict=False)
+    m.eval()
+    return m
+
+
+@pytest.fixture(scope="module")
+def m32(synth_sd):
+    return _make(synth_sd, "fp32", max_batch=128)
+
+
+@pytest.fixture(scope="module")
+def m16(synth_sd):
+    return _make(synth_sd, "bf16", max_batch=128)
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+# ------------------------------------------------------------------------------------------ library / boundary
+def test_native_library_is_loaded_and_strict(m32):
+    from dir_b200 import capi
+
+    assert os.path.exists(capi.LIB_PATH)
+    req = m32.required_keys()
+    assert len(req) > 600 and len(set(req)) == len(req)
+    sd_keys = set(m32.state_dict().keys())
+    assert set(req) <= sd_keys
+    # keys the forward never touches
+    assert not any(k.startswith("backbone.fc.") or ".STEblocks.0." in k or k.endswith(".e_0") for k in req)
+
+
+def test_missing_required_key_is_an_error(synth_sd):
+    import dir_b200
+
+    sd = {k: v for k, v in synth_sd.items() if k != "decoder.projecter_3.fusion.0.weight"}
+    m = dir_b200.DIR(21, "./misc/mano", precision="fp32").cuda()
+    m.load_state_dict(sd, strict=False)
+    with pytest.raises(KeyError):
+        m({"img": torch.zeros(1, 3, 256, 256)}, None, None)
+
+
+def test_training_branch_and_cpu_are_refused(synth_sd):
+    import dir_b200
+
+    m = dir_b200.DIR(21, "./misc/mano", precision="fp32")
+    with pytest.raises(dir_b200.DirB200Error):
+        m({"img": torch.zeros(1, 3, 256, 256)}, None, None)  # module still on CPU: no fallback
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m({"img": torch.zeros(1, 3, 256, 256)}, None, None)
+
+
+# ------------------------------------------------------------------------------------------ seams, fp32
+@pytest.mark.parametrize("side", ["left", "right"])
+def test_mano_layer_vs_golden(m32, golden_dir, X, side):
+    from dir_b200 import seams
+
+    g = load(golden_dir, f"mano_{side}.npz")
+    B = X["mano_pose"].shape[0]
+    para = torch.zeros(B, 2, 64)
+    hand = 0 if side == "left" else 1
+    para[:, hand, :51] = X["mano_pose"]
+    para[:, hand, 51:61] = X["mano_beta"]
+    para[:, :, 61] = 1.0
+    out = seams.mano(m32, 0, para.cuda())
+    assert rel(out[f"pd_mesh_xyz_{side}"], g["verts"]) < TOL32
+    assert rel(out[f"pd_joint_xyz_{side}"], g["joints"]) < TOL32
+    assert float(out[f"pd_joint_xyz_{side}"][:, 0].abs().max()) == 0.0  # centred on the wrist
+    # scale 1, zero translation: uv == xy
+    assert rel(out[f"pd_joint_uv_{side}"], g["joints"][..., :2]) < TOL32
+
+
+def test_mano_all_six_copies_and_projection(m32, synth_sd):
+    from dir_b200 import seams
+    from oracle import dir_oracle as O
+
+    gen = torch.Generator().manual_seed(5)
+    para = torch.randn(7, 2, 64, generator=gen) * 0.4
+    para[:, :, 61] = 2.5
+    prefixes = ["init_regressor.", "decoder.projecter_4.regressor.", "decoder.projecter_3.regressor."]
+    for which, p in enumerate(prefixes):
+        out = seams.mano(m32, which, para.cuda())
+        for hand, side in enumerate(("left", "right")):
+            v, j = O.mano_layer(synth_sd, f"{p}mano_layer_{side}.", para[:, hand, :51], para[:, hand, 51:61], side)
+            assert rel(out[f"pd_mesh_xyz_{side}"], v) < TOL32
+            assert rel(out[f"pd_joint_xyz_{side}"], j) < TOL32
+            assert rel(out[f"pd_joint_uv_{side}"], O.projection_xy(para[:, hand, 61:64], j)) < TOL32
+
+
+def test_backbone_vs_golden_and_oracle(m32, synth_sd, golden_dir, X):
+    from dir_b200 import seams
+    from oracle import dir_oracle as O
+
+    g = load(golden_dir, "resnet50.npz")
+    feats = seams.backbone(m32, X["bb_img"].cuda())
+    for f, k in zip(feats, ("c1", "c2", "c3", "c4")):
+        assert rel(f, g[k]) < TOL32, k
+    img = X["img"][:1]
+    want = O.resnet50(synth_sd, img)
+    got = seams.backbone(m32, img.cuda())
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert rel(a, b) < TOL32, i
+
+
+@pytest.mark.parametrize("name,cin,S", [("decoder.skip_layer4.", 1024, 16), ("decoder.fusion_layer4.", 2304, 16),
+                                        ("decoder.enhance_layer4.", 512, 8), ("decoder.skip_layer3.", 512, 32),
+                                        ("decoder.fusion_layer3.", 512, 32), ("decoder.enhance_layer3.", 512, 32)])
+def test_residual_blocks(m32, synth_sd, golden_dir, X, name, cin, S):
+    from dir_b200 import seams
+    from oracle import dir_oracle as O
+
+    if name == "decoder.enhance_layer4.":
+        x = X["res_x"]
+        assert rel(seams.residual(m32, name, x.cuda()), load(golden_dir, "residual.npz")["y"]) < TOL32
+    else:
+        x = torch.randn(3, cin, S, S, generator=torch.Generator().manual_seed(cin + S))
+    assert rel(seams.residual(m32, name, x.cuda()), O.residual(synth_sd, name, x)) < TOL32
+
+
+def test_init_regressor(m32, synth_sd, golden_dir, X):
+    from dir_b200 import seams
+
+    g = load(golden_dir, "init_regressor.npz")
+    out = seams.init_regressor(m32, X["c4"].cuda())
+    for k in g.files:
+        if k in out:
+            assert rel(out[k], g[k]) < TOL32, k
+
+
+def _prev(X):
+    return {"pd_joint_xyz_left": X["j2b_xyz_l"], "pd_joint_xyz_right": X["j2b_xyz_r"],
+            "pd_joint_uv_left": X["j2b_uv_l"], "pd_joint_uv_right": X["j2b_uv_r"],
+            "pd_mano_para_left": X["j2b_para_l"], "pd_mano_para_right": X["j2b_para_r"], "pd_offset": X["j2b_off"]}
+
+
+def test_joint2bone_stage1_vs_golden(m32, golden_dir, X):
+    from dir_b200 import seams
+
+    g = load(golden_dir, "joint2bone.npz")
+    res, feats = seams.joint2bone(m32, 1, X["j2b_feat"].cuda(), {k: v.cuda() for k, v in _prev(X).items()})
+    for k in g.files:
+        got = feats[k] if k in feats else res[k]
+        assert rel(got, g[k]) < TOL32, k
+
+
+@pytest.mark.parametrize("stage,S,uv_range", [(1, 16, 0.8), (2, 32, 0.8), (2, 32, 3.0), (1, 16, 0.0)])
+def test_joint2bone_vs_oracle(m32, synth_sd, stage, S, uv_range):
+    """uv_range 3.0 exercises grid_sample zero padding / off-map bones; 0.0 collapses every bone (a==b -> zeros)."""
+    from dir_b200 import seams
+    from oracle import dir_oracle as O
+
+    gen = torch.Generator().manual_seed(100 + stage + int(uv_range * 10))
+    B = 3
+    prev = {"pd_joint_xyz_left": torch.randn(B, 21, 3, generator=gen) * 0.05,
+            "pd_joint_xyz_right": torch.randn(B, 21, 3, generator=gen) * 0.05,
+            "pd_joint_uv_left": (torch.rand(B, 21, 2, generator=gen) * 2 - 1) * uv_range,
+            "pd_joint_uv_right": (torch.rand(B, 21, 2, generator=gen) * 2 - 1) * uv_range,
+            "pd_mano_para_left": torch.randn(B, 64, generator=gen) * 0.3,
+            "pd_mano_para_right": torch.randn(B, 64, generator=gen) * 0.3,
+            "pd_offset": torch.randn(B, 3, generator=gen) * 0.5}
+    feat = torch.randn(B, 256, S, S, generator=gen)
+    p = "decoder.projecter_4." if stage == 1 else "decoder.projecter_3."
+    want, wfeats = O.joint2bone(synth_sd, p, feat, prev, S, 1 if stage == 1 else 2)
+    res, feats = seams.joint2bone(m32, stage, feat.cuda(), {k: v.cuda() for k, v in prev.items()}, want_vis=True)
+    for k in ("pd_offset", "pd_mano_para_left", "pd_mano_para_right", "pd_joint_uv_left", "pd_joint_uv_right",
+              "pd_mesh_xyz_left", "pd_mesh_xyz_right", "pd_joint_xyz_left", "pd_joint_xyz_right"):
+        assert rel(res[k], want[k]) < TOL32, k
+    assert rel(feats["joint_feat_left"], wfeats["joint_feat_left"]) < TOL32
+    assert rel(feats["joint_feat_right"], wfeats["joint_feat_right"]) < TOL32
+    # rasterisation is discontinuous in uv: compare away from flipped boundary pixels
+    wv, gv = wfeats["vis_img_feat"], feats["vis_img_feat"].cpu()
+    flipped = ((wv != 0) != (gv != 0)).float().mean()
+    assert float(flipped) < 2e-3
+    same = (wv != 0) == (gv != 0)
+    assert float(((wv - gv).abs() * same).max()) < TOL32 * float(wv.abs().max() + 1e-9) + 1e-6
+    assert float(((wfeats["img_feat"] - feats["img_feat"].cpu()).abs() > 1e-3 * wfeats["img_feat"].abs().max()).float().mean()) < 5e-3
+
+
+def test_bone_proj_vs_golden(m32, golden_dir, X):
+    from dir_b200 import seams
+
+    g = load(golden_dir, "bone_proj.npz")
+    y16 = seams.bone_proj(m32, X["bp_uv16"].cuda(), X["bp_feat"].cuda(), 16, 1.0).cpu()
+    y32 = seams.bone_proj(m32, X["bp_uv32"].cuda(), X["bp_feat"][:1].cuda(), 32, 2.0).cpu()
+    for got, want in ((y16, torch.as_tensor(g["y16"])), (y32, torch.as_tensor(g["y32"]))):
+        assert bool(((got != 0) == (want != 0)).all())  # identical capsule masks
+        assert rel(got, want) < 1e-5
+
+
+def test_bone_proj_degenerate(m32):
+    from dir_b200 import seams
+
+    y = seams.bone_proj(m32, torch.zeros(2, 21, 2).cuda(), torch.ones(2, 21, 64).cuda(), 16, 1.0)
+    assert float(y.abs().sum()) == 0.0 and not bool(torch.isnan(y).any())
+
+
+# ------------------------------------------------------------------------------------------ whole forward
+def _check_forward(outs, g, tol):
+    from oracle import dir_oracle as O
+
+    worst = 0.0
+    for i in range(3):
+        for k in O.OUT_KEYS:
+            r = rel(outs[i][k], g[f"s{i}_{k}"])
+            worst = max(worst, r)
+            assert r < tol, (i, k, r)
+    return worst
+
+
+def test_forward_fp32_vs_golden(m32, golden_dir, X):
+    g = load(golden_dir, "forward_b2.npz")
+    outs, loss = m32({"img": X["img"]}, None, None)  # CPU tensor in, like apps/eval.py would after .cuda()
+    assert loss == {} and len(outs) == 4 and outs[0]["pd_rel_joint"] is None
+    worst = _check_forward(outs, g, TOL32)
+    assert rel(outs[3]["seg"], g["seg"]) < TOL32 and rel(outs[3]["dense"], g["dense"]) < TOL32
+    pf = outs[3]["proj_feat"]
+    assert tuple(pf.shape) == (2, 1280, 32, 32)
+    assert abs(int((pf != 0).sum()) - int(g["proj_feat_nnz"])) <= 64 * 8
+    assert abs(float(pf.abs().double().sum()) / float(g["proj_feat_abs_sum"]) - 1) < 1e-3
+    print(f"fp32 whole-forward worst relative error vs reference: {worst:.2e}")
+
+
+def test_forward_mpjpe_delta_fp32(m32, golden_dir, X):
+    """|MPJPE/MPVPE(new) - (ref)| < 0.01 mm for any fixed GT (apps/eval.py:151-193 metric core: wrist-aligned L2, mm)."""
+    g = load(golden_dir, "forward_b2.npz")
+    outs, _ = m32({"img": X["img"]}, None, None)
+    gen = torch.Generator().manual_seed(3)
+    for side in ("left", "right"):
+        ref_v = torch.as_tensor(g[f"s2_pd_mesh_xyz_{side}"])
+        ref_j = torch.as_tensor(g[f"s2_pd_joint_xyz_{side}"])
+        gt_v = ref_v + torch.randn(ref_v.shape, generator=gen) * 0.01
+        gt_j = ref_j + torch.randn(ref_j.shape, generator=gen) * 0.01
+        new_v, new_j = outs[2][f"pd_mesh_xyz_{side}"].cpu(), outs[2][f"pd_joint_xyz_{side}"].cpu()
+        mpvpe = lambda v: float((v - gt_v).norm(dim=-1).mean() * 1000)
+        mpjpe = lambda j: float((j - gt_j).norm(dim=-1).mean() * 1000)
+        assert abs(mpvpe(new_v) - mpvpe(ref_v)) < 0.01 and abs(mpjpe(new_j) - mpjpe(ref_j)) < 0.01
+        assert float((new_v - ref_v).norm(dim=-1).max() * 1000) < 0.01  # stricter: per-vertex, mm
+
+
+def test_forward_fp32_odd_batch_vs_oracle(m32, synth_sd):
+    from oracle import dir_oracle as O
+
+    img = torch.randn(5, 3, 256, 256, generator=torch.Generator().manual_seed(77))
+    want = O.dir_forward(synth_sd, img)
+    outs, _ = m32({"img": img.cuda()}, None, None)
+    for i in range(3):
+        for k in O.OUT_KEYS:
+            assert rel(outs[i][k], want[i][k]) < TOL32, (i, k)
+    assert rel(outs[3]["seg"], want[3]["seg"]) < TOL32
+
+
+def test_forward_bf16_vs_golden(m16, golden_dir, X):
+    """bf16 feature maps: report the drift; bound chosen from measurement (precision)."""
+    g = load(golden_dir, "forward_b2.npz")
+    outs, _ = m16({"img": X["img"].cuda()}, None, None)
+    worst = _check_forward(outs, g, 0.15)
+    ref_v = torch.as_tensor(g["s2_pd_mesh_xyz_left"])
+    d_mm = float((outs[2]["pd_mesh_xyz_left"].cpu() - ref_v).norm(dim=-1).mean() * 1000)
+    print(f"bf16 whole-forward worst relative error {worst:.2e}; mean per-vertex drift {d_mm:.3f} mm")
+    assert d_mm < 5.0
+
+
+@pytest.mark.parametrize("which", ["m32", "m16"])
+def test_full_batch_properties(which, request):
+    """B=128 (BASELINE.json's batch): no oracle run; size-independent properties instead.
+    (1) per-image independence: an image's outputs do not depend on its batch or position — bit-exact;
+    (2) MANO invariants: wrist joint is the origin; uv == s*xy + t;  (3) everything finite."""
+    m = request.getfixturevalue(which)
+    gen = torch.Generator().manual_seed(1234)
+    img = torch.randn(128, 3, 256, 256, generator=gen).cuda()
+    big = m.run_raw(img)
+    rec = big["record"]
+    assert bool(torch.isfinite(rec).all())
+    pick = [5, 77, 127]
+    small = m.run_raw(img[pick])
+    assert torch.equal(small["record"], rec[pick])
+    assert torch.equal(small["seg"], big["seg"][pick])
+    outs = m.unpack_record(rec)
+    for o in outs[:3]:
+        for side in ("left", "right"):
+            j, uv, pr = o[f"pd_joint_xyz_{side}"], o[f"pd_joint_uv_{side}"], o[f"pd_proj_{side}"]
+            assert float(j[:, 0].abs().max()) == 0.0
+            want = pr[:, None, 0:1] * j[..., :2] + pr[:, None, 1:3]
+            assert float((uv - want).abs().max()) < 1e-5 * (1 + float(want.abs().max()))
+
+
+def test_chunking_over_max_batch(synth_sd):
+    m = _make(synth_sd, "fp32", max_batch=4, aux_outputs=False)
+    img = torch.randn(9, 3, 256, 256, generator=torch.Generator().manual_seed(9)).cuda()
+    a = m.run_raw(img)["record"]
+    b = torch.cat([m.run_raw(img[i:i + 3])["record"] for i in range(0, 9, 3)])
+    assert torch.equal(a, b)
+    outs, _ = m({"img": img}, None, None)
+    assert outs[3]["seg"] is None
+
+
+def test_cuda_graph_replay_matches_eager(synth_sd, X):
+    m = _make(synth_sd, "fp32", max_batch=8, use_cuda_graph=True)
+    e = _make(synth_sd, "fp32", max_batch=8)
+    img = X["img"].cuda()
+    want = e.run_raw(img)
+    for _ in range(2):
+        got = m.run_raw(img)
+        assert torch.equal(got["record"], want["record"]) and torch.equal(got["proj_feat"], want["proj_feat"])
