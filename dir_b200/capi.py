@@ -22,7 +22,7 @@ EXPORTS = [
     "dirb200_num_required_keys", "dirb200_required_key", "dirb200_workspace_bytes", "dirb200_forward",
     "dirb200_forward_launches", "dirb200_backbone", "dirb200_residual", "dirb200_init_regressor", "dirb200_mano",
     "dirb200_joint2bone", "dirb200_bone_proj", "dirb200_nccl_unique_id", "dirb200_nccl_init",
-    "dirb200_allgather_records", "dirb200_profile_layer", "dirb200_profile_read",
+    "dirb200_allgather_records", "dirb200_profile_layer", "dirb200_profile_read", "dirb200_conv_layer",
 ]
 
 
@@ -74,6 +74,7 @@ def load_library():
     lib.dirb200_nccl_unique_id.argtypes = [vp, C.c_char_p]
     lib.dirb200_nccl_init.argtypes = [vp, C.c_char_p, ip, ip]
     lib.dirb200_allgather_records.argtypes = [vp, vp, vp, ip, vp]
+    lib.dirb200_conv_layer.argtypes = [vp, C.c_char_p, vp, vp, ip, ip, ip, vp, C.POINTER(C.c_int), vp, C.c_size_t, vp]
     lib.dirb200_profile_layer.argtypes = [vp, C.c_char_p]
     lib.dirb200_profile_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)]
     for name in EXPORTS:

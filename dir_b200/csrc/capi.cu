@@ -1,6 +1,7 @@
 // extern "C" boundary (include/dirb200.h). No exceptions cross it; errors are codes + last_error().
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -57,6 +58,10 @@ extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
     return DIRB200_E_INVALID;
   }
   h->e.cfg = *cfg;
+  {
+    const char* dis = getenv("DIRB200_DISABLE_TC");
+    h->e.disable_tc = dis && dis[0] == '1';
+  }
   // required-key inventory (no GPU work)
   h->e.dry = true;
   h->e.build(nullptr);
@@ -304,6 +309,43 @@ extern "C" int dirb200_bone_proj(dirb200_handle* h, const float* uv, const float
   launch_bone_vis_nchw(uv, nullptr, 42, feat, nullptr, 21 * 64, out, batch, size, distance, 0,
                        reinterpret_cast<cudaStream_t>(stream));
   return DIRB200_OK;
+}
+
+template <typename T>
+static int seam_conv(Engine& e, const ConvLayer& L, const float* x, const float* res, int B, int H, int W, float* y,
+                     Arena& ar, cudaStream_t st) {
+  const int Ho = (H + 2 * L.pad - L.kh) / L.stride + 1, Wo = (W + 2 * L.pad - L.kw) / L.stride + 1;
+  T* xi = reinterpret_cast<T*>(ar.alloc((size_t)B * H * W * L.Cin * sizeof(T)));
+  T* yo = reinterpret_cast<T*>(ar.alloc((size_t)B * Ho * Wo * L.Cout * sizeof(T)));
+  T* ri = res ? reinterpret_cast<T*>(ar.alloc((size_t)B * Ho * Wo * L.Cout * sizeof(T))) : nullptr;
+  if (ar.overflow) return DIRB200_E_WORKSPACE;
+  launch_nchw_to_nhwc<T>(x, xi, B, L.Cin, H, W, st);
+  if (res) launch_nchw_to_nhwc<T>(res, ri, B, L.Cout, Ho, Wo, st);
+  e.sticky_rc = 0;
+  e.tc_launches = 0;
+  e.conv<T>(L, xi, yo, ri, B, H, W, st);
+  if (e.sticky_rc) return e.sticky_rc;
+  launch_nhwc_to_nchw<T>(yo, y, B, L.Cout, Ho, Wo, st);
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_conv_layer(dirb200_handle* h, const char* weight_key, const float* x, const float* res,
+                                  int batch, int height, int width, float* y, int* used_tensor_cores, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  H_CHECK(h);
+  if (!e.finalized) return fail(e, DIRB200_E_STATE, "finalize_weights first");
+  const ConvLayer* L = weight_key ? e.find_conv(weight_key) : nullptr;
+  if (!L) return fail(e, DIRB200_E_INVALID, "unknown conv weight key");
+  if (!x || !y || batch <= 0 || L->Cin % 4 != 0) return fail(e, DIRB200_E_INVALID, "bad conv_layer argument");
+  Arena ar;
+  ar.base = reinterpret_cast<char*>(workspace);
+  ar.size = workspace_bytes;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = e.bf16() ? seam_conv<__nv_bfloat16>(e, *L, x, res, batch, height, width, y, ar, st)
+                    : seam_conv<float>(e, *L, x, res, batch, height, width, y, ar, st);
+  if (used_tensor_cores) *used_tensor_cores = e.tc_launches;
+  if (rc == DIRB200_E_WORKSPACE) e.err = "workspace too small";
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ NCCL (run-time bound)

@@ -1,13 +1,383 @@
-// tcgen05 / TMA implicit-GEMM convolution (bf16 operands, fp32 accumulate in TMEM).
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a: bf16 operands, fp32 accumulation in TMEM,
+// fused affine (+residual) (+ReLU) epilogue. NHWC activations, weights [Cout][(ky,kx,ci)].
+//
+//   D[m, n] = sum_k A[m, k] * W[n, k],  m = (b, ho, wo) (128 consecutive output pixels per CTA),
+//                                        k = (ky, kx, ci) walked in blocks of 64 channels of one tap.
+//
+// A operand: one 4-D TMA box per (tap, 64-channel block): {64 ch, wbox*stride, hbox*stride, nbox}
+//   of the NHWC input with elementStrides {1, stride, stride, 1}; the tap offset (ky-pad, kx-pad) is just a
+//   coordinate shift and TMA zero-fills out-of-bounds pixels, i.e. im2col + padding cost no instructions.
+// B operand: 2-D TMA box {64 k, BN rows} of the packed weights. Both land K-major with 128B swizzle,
+//   which is exactly the canonical UMMA SWIZZLE_128B K-major layout (SBO = 1024 B).
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one elected thread issues
+//   tcgen05.mma 128xBNx16), warps 2..5 = epilogue (tcgen05.ld 32x32b -> registers -> global).
+#include <cuda.h>
+
+#include <cstdio>
+#include <map>
+#include <tuple>
+
+#include "common.cuh"
 #include "engine.h"
 
 namespace dirb200 {
 
-bool conv_tc_supported(const ConvLayer&, int, int, int) { return false; }
-int conv_tc_prepare_weights(ConvLayer&) { return 0; }
-int launch_conv_tc(const ConvLayer&, const __nv_bfloat16*, __nv_bfloat16*, const __nv_bfloat16*, int, int, int,
-                   cudaStream_t) {
-  return DIRB200_E_STATE;
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int NUM_THREADS = 192;
+
+struct TcArgs {
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* y;
+  int M, Cout, Ho, Wo;
+  int stride, pad, kw;
+  int taps, cblocks;  // K loop = taps * cblocks blocks of 64
+  int relu;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major): 1
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+template <int BN>
+struct TcCfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * BN * 4 + 256;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N=BN, M=128
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  float* s_scale = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float* s_shift = s_scale + BN;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + BN);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = a.Cout / BN;
+  const int n_tile = blockIdx.x % n_tiles;
+  const int m_tile = blockIdx.x / n_tiles;
+  const int m0 = m_tile * BM, n0 = n_tile * BN;
+  const int nkb = a.taps * a.cblocks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation: BN fp32 columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {  // stage the epilogue vectors
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      s_scale[i] = a.scale[n0 + i];
+      s_shift[i] = a.shift[n0 + i];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer
+      const int wo0 = m0 % a.Wo;
+      const int ho0 = (m0 / a.Wo) % a.Ho;
+      const int b0 = m0 / (a.Wo * a.Ho);
+      const int cin = a.cblocks * BK;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
+        const int ky = tap / a.kw, kx = tap - ky * a.kw;
+        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        tma_load_4d(&tmA, &full_bar[s], sA + s * A_STAGE_BYTES, cb * BK, wo0 * a.stride + kx - a.pad,
+                    ho0 * a.stride + ky - a.pad, b0);
+        tma_load_2d(&tmB, &full_bar[s], sB + s * Cfg::B_STAGE_BYTES, tap * cin + cb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t da = umma_desc(smem_u32(sA + s * A_STAGE_BYTES));
+        const uint64_t db = umma_desc(smem_u32(sB + s * Cfg::B_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle atom
+          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int lane_base = (warp & 3) * 32;
+    const int m = m0 + lane_base + lane;
+    const bool valid = m < a.M;
+    __nv_bfloat16* yrow = a.y + (int64_t)m * a.Cout + n0;
+    const __nv_bfloat16* rrow = a.res ? a.res + (int64_t)m * a.Cout + n0 : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + c * 32, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (valid) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), s_scale[c * 32 + j], s_shift[c * 32 + j]);
+        if (rrow) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u = __ldg(reinterpret_cast<const uint4*>(rrow + c * 32 + q * 8));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __bfloat1622float2(h[e]);
+              v[q * 8 + e * 2] += f.x;
+              v[q * 8 + e * 2 + 1] += f.y;
+            }
+          }
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
+          *reinterpret_cast<uint4*>(yrow + c * 32 + q * 8) = u;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int pick_bn(int Cout) { return Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64); }
+
+struct Boxes {
+  int wbox, hbox, nbox;
+};
+Boxes pick_boxes(int Ho, int Wo) {
+  Boxes b;
+  b.wbox = Wo < BM ? Wo : BM;
+  b.hbox = Ho < BM / b.wbox ? Ho : BM / b.wbox;
+  b.nbox = BM / (b.wbox * b.hbox);
+  return b;
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES) !=
+        cudaSuccess)
+      return DIRB200_E_CUDA;
+    attr = true;
+  }
+  const int m_tiles = (a.M + BM - 1) / BM;
+  conv_tc_kernel<BN><<<m_tiles * (a.Cout / BN), NUM_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, a);
+  return DIRB200_OK;
+}
+
+}  // namespace
+
+bool conv_tc_supported(const ConvLayer& L, int B, int H, int W) {
+  if (!L.w16 || L.wmap_bn == 0 || !get_encode()) return false;
+  if (L.Cin % 64 != 0 || L.Cout % 64 != 0 || L.K != L.Kpad) return false;
+  if (L.stride != 1 && L.stride != 2) return false;
+  const int Ho = (H + 2 * L.pad - L.kh) / L.stride + 1, Wo = (W + 2 * L.pad - L.kw) / L.stride + 1;
+  if (!is_pow2(Ho) || !is_pow2(Wo)) return false;
+  if (Wo > BM && Wo % BM != 0) return false;
+  return true;
+}
+
+int conv_tc_prepare_weights(ConvLayer& L) {
+  L.wmap_bn = 0;
+  EncodeTiledFn enc = get_encode();
+  if (!enc || L.Cin % 64 != 0 || L.Cout % 64 != 0 || L.K != L.Kpad) return 0;
+  const int bn = pick_bn(L.Cout);
+  cuuint64_t dims[2] = {(cuuint64_t)L.Kpad, (cuuint64_t)L.Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)L.Kpad * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(&L.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, L.w16, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return DIRB200_E_CUDA;
+  L.wmap_bn = bn;
+  return DIRB200_OK;
+}
+
+int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bfloat16* res, int B,
+                   int H, int W, cudaStream_t st) {
+  const int Ho = (H + 2 * L.pad - L.kh) / L.stride + 1, Wo = (W + 2 * L.pad - L.kw) / L.stride + 1;
+  const Boxes bx = pick_boxes(Ho, Wo);
+  // activation tensor map, cached per (pointer, geometry): encoding is host-only work
+  typedef std::tuple<const void*, int, int, int, int, int, int, int, int> Key;
+  static thread_local std::map<Key, CUtensorMap> cache;
+  Key key(x, B, H, W, L.Cin, L.stride, bx.wbox, bx.hbox, bx.nbox);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    CUtensorMap tm;
+    cuuint64_t dims[4] = {(cuuint64_t)L.Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)L.Cin * 2, (cuuint64_t)W * L.Cin * 2, (cuuint64_t)H * W * L.Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(bx.wbox * L.stride), (cuuint32_t)(bx.hbox * L.stride),
+                         (cuuint32_t)bx.nbox};
+    cuuint32_t es[4] = {1, (cuuint32_t)L.stride, (cuuint32_t)L.stride, 1};
+    CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x), dims, strides,
+                              box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      fprintf(stderr, "dirb200: cuTensorMapEncodeTiled(A) failed: %d (layer %s)\n", (int)r, L.name.c_str());
+      return DIRB200_E_CUDA;
+    }
+    if (cache.size() > 4096) cache.clear();
+    it = cache.emplace(key, tm).first;
+  }
+  TcArgs a;
+  a.scale = L.scale;
+  a.shift = L.shift;
+  a.res = res;
+  a.y = y;
+  a.M = B * Ho * Wo;
+  a.Cout = L.Cout;
+  a.Ho = Ho;
+  a.Wo = Wo;
+  a.stride = L.stride;
+  a.pad = L.pad;
+  a.kw = L.kw;
+  a.taps = L.kh * L.kw;
+  a.cblocks = L.Cin / BK;
+  a.relu = L.relu;
+  switch (L.wmap_bn) {
+    case 256: return launch_tc<256>(it->second, L.wmap, a, st);
+    case 128: return launch_tc<128>(it->second, L.wmap, a, st);
+    default: return launch_tc<64>(it->second, L.wmap, a, st);
+  }
 }
 
 }  // namespace dirb200

@@ -340,6 +340,30 @@ int Engine::build(cudaStream_t st) {
   return DIRB200_OK;
 }
 
+const ConvLayer* Engine::find_conv(const std::string& k) const {
+  std::vector<const ConvLayer*> all = {&stem, &attn_conv, &conv_final0, &conv_final3, &segdense0};
+  for (int l = 0; l < 4; ++l)
+    for (const auto& b : layers[l]) {
+      all.push_back(&b.c1);
+      all.push_back(&b.c2);
+      all.push_back(&b.c3);
+      if (b.has_ds) all.push_back(&b.ds);
+    }
+  for (const auto& kv : res) {
+    all.push_back(&kv.second.c1);
+    all.push_back(&kv.second.c2);
+    all.push_back(&kv.second.c3);
+    all.push_back(&kv.second.skip);
+  }
+  for (int s = 0; s < 2; ++s) {
+    all.push_back(&stage[s].fusion0);
+    all.push_back(&stage[s].fusion3);
+  }
+  for (const ConvLayer* c : all)
+    if (c->name == k) return c;
+  return nullptr;
+}
+
 // ------------------------------------------------------------------------------------------------ forward pieces
 template <typename T>
 void Engine::conv(const ConvLayer& L, const T* x, T* y, const T* resid, int B, int H, int W_, cudaStream_t st,
@@ -359,9 +383,14 @@ void Engine::conv(const ConvLayer& L, const T* x, T* y, const T* resid, int B, i
     pr->flops = 2.0 * B * Ho * Wo * (double)L.Cout * L.K;
     cudaEventRecord(pr->a, st);
   }
-  if (sizeof(T) == 2 && !in_nchw && conv_tc_supported(L, B, H, W_)) {
-    launch_conv_tc(L, reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
-                   reinterpret_cast<const __nv_bfloat16*>(resid), B, H, W_, st);
+  if (sizeof(T) == 2 && !in_nchw && !disable_tc && conv_tc_supported(L, B, H, W_)) {
+    int rc = launch_conv_tc(L, reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
+                            reinterpret_cast<const __nv_bfloat16*>(resid), B, H, W_, st);
+    if (rc && !sticky_rc) {
+      sticky_rc = rc;
+      err = "tcgen05 conv launch failed for " + L.name;
+    }
+    ++tc_launches;
     if (pr) cudaEventRecord(pr->b, st);
     return;
   }
@@ -580,6 +609,8 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
 template <typename T>
 int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o, cudaStream_t st) {
   launches = 0;
+  tc_launches = 0;
+  sticky_rc = 0;
   const bool plan = ar.base == nullptr;
   T *c2 = nullptr, *c3 = nullptr, *c4 = nullptr;
   int rc = run_backbone<T>(img, B, 256, 256, ar, nullptr, &c2, &c3, &c4, st);
@@ -647,10 +678,15 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   if (plan) return DIRB200_OK;
   if (ar.overflow) return DIRB200_E_WORKSPACE;
   last_forward_launches = launches;
+  if (sticky_rc) return sticky_rc;
   CK(cudaPeekAtLastError());
   return DIRB200_OK;
 }
 
+template void Engine::conv<float>(const ConvLayer&, const float*, float*, const float*, int, int, int, cudaStream_t,
+                                  bool);
+template void Engine::conv<__nv_bfloat16>(const ConvLayer&, const __nv_bfloat16*, __nv_bfloat16*,
+                                          const __nv_bfloat16*, int, int, int, cudaStream_t, bool);
 template int Engine::forward<float>(const float*, int, Arena&, const dirb200_outputs*, cudaStream_t);
 template int Engine::forward<__nv_bfloat16>(const float*, int, Arena&, const dirb200_outputs*, cudaStream_t);
 template int Engine::run_backbone<float>(const float*, int, int, int, Arena&, float**, float**, float**, float**,

@@ -89,6 +89,10 @@ struct Engine {
   cudaStream_t fin_stream = nullptr;
   int launches = 0;
   int last_forward_launches = 0;
+  int tc_launches = 0;      // convs that went to the tcgen05 kernel since the last forward() start
+  int sticky_rc = 0;        // first launch error inside a forward
+  bool disable_tc = false;  // DIRB200_DISABLE_TC=1: force the CUDA-core conv in bf16 mode (debug A/B)
+  const ConvLayer* find_conv(const std::string& weight_key) const;
   void* nccl_comm = nullptr;
   // timing hook (bench.py roofline): CUDA events around every conv launch whose name starts with prof_prefix
   struct ProfRec {

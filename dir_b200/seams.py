@@ -134,3 +134,29 @@ def bone_proj(model, uv, feat, size, distance):
     h.check(h.lib.dirb200_bone_proj(h.h, _ptr(uv), _ptr(feat), B, size, float(distance), _ptr(out), _stream()),
             "bone_proj")
     return out
+
+
+def conv_layer(model, weight_key, x, res=None):
+    """One conv with its fused epilogue, addressed by the reference state_dict key of its weight.
+    Returns (y NCHW fp32, used_tensor_cores)."""
+    x = _f32(x)
+    B, _, H, W = x.shape
+    h, ws = _prep(model, B)
+    w = model.state_dict()[weight_key]
+    cout, _, kh, kw = w.shape
+    parts = weight_key.split(".")
+    stride, pad = 1, (kh - 1) // 2
+    if weight_key == "backbone.conv1.weight":
+        stride = 2
+    elif parts[0] == "backbone" and parts[2] == "0" and parts[1] != "layer1" and (parts[3] in ("conv2", "downsample")):
+        stride = 2  # resnet.py:111,227 (v1.5: stride on the 3x3 and on the downsample 1x1)
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    if weight_key.startswith(("init_regressor.attention_left.0", "decoder.seg.0")):
+        cout *= 2  # packed together with its right/dense twin
+    y = torch.empty(B, cout, Ho, Wo, device=x.device)
+    if res is not None:
+        res = _f32(res)
+    used = C.c_int(0)
+    h.check(h.lib.dirb200_conv_layer(h.h, weight_key.encode(), _ptr(x), _ptr(res), B, H, W, _ptr(y), C.byref(used),
+                                     _ptr(ws), ws.numel(), _stream()), "conv_layer")
+    return y, used.value

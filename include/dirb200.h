@@ -129,6 +129,14 @@ int dirb200_joint2bone(dirb200_handle* h, int stage, const float* img_feat, cons
 int dirb200_bone_proj(dirb200_handle* h, const float* uv, const float* feat, int batch, int size, float distance,
                       float* out, void* stream);
 
+/* One nn.Conv2d (+ its folded eval BatchNorm / bias, optional residual add, ReLU exactly as fused in the
+ * forward) by the state_dict key of its weight, e.g. "backbone.layer2.0.conv2.weight"
+ * (models/backbone/resnet.py:120-140). x (B,Cin,H,W), res/y (B,Cout,Ho,Wo) NCHW fp32. *used_tensor_cores is
+ * set to 1 when the tcgen05 kernel ran (bf16 handles, tensor-core shaped layers), 0 for the CUDA-core kernel. */
+int dirb200_conv_layer(dirb200_handle* h, const char* weight_key, const float* x, const float* res, int batch,
+                       int height, int width, float* y, int* used_tensor_cores, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Multi-GPU: images shard over ranks with no exchange inside the forward; the only
  * collective is one all-gather of the per-image records over NVLink (the reference has no distributed
  * code at all). The library resolves NCCL at run time (dlopen of the libnccl the host process already

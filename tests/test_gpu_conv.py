@@ -1,0 +1,149 @@
+"""GPU: every distinct conv shape of the path, one layer at a time, through dirb200_conv_layer.
+
+fp32 handle  -> CUDA-core implicit GEMM, compared with torch conv2d in fp32 (1e-4).
+bf16 handle  -> tcgen05/TMA kernel (asserted via used_tensor_cores), compared with an fp32 conv2d on the
+                bf16-ROUNDED inputs and weights, i.e. the exact arithmetic the tensor cores do (products of bf16
+                are exact in fp32, accumulation fp32); the only remaining differences are accumulation order and
+                the final bf16 rounding of the output (2^-9 relative), hence tol 6e-3 of the tensor's max.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BN_EPS = 1e-5
+
+# (weight key, B, H, W, with_residual)
+CASES = [
+    ("backbone.layer1.0.conv1.weight", 2, 64, 64, False),       # 1x1 64->64   (BN=64 tile)
+    ("backbone.layer1.0.conv2.weight", 2, 64, 64, False),       # 3x3 64->64
+    ("backbone.layer1.0.conv3.weight", 2, 64, 64, True),        # 1x1 64->256 + residual + relu
+    ("backbone.layer1.0.downsample.0.weight", 1, 64, 64, False),
+    ("backbone.layer2.0.conv2.weight", 2, 64, 64, False),       # 3x3 stride 2 (TMA elementStrides)
+    ("backbone.layer2.0.downsample.0.weight", 2, 64, 64, False),  # 1x1 stride 2
+    ("backbone.layer3.0.conv2.weight", 3, 32, 32, False),       # stride 2 -> 16x16
+    ("backbone.layer3.0.conv2.weight", 5, 8, 8, False),         # tiny map 4x4: tile spans 8 images, ragged M
+    ("backbone.layer4.0.conv2.weight", 3, 16, 16, False),       # stride 2 -> 8x8, odd batch (partial tile)
+    ("backbone.layer4.2.conv3.weight", 3, 8, 8, True),          # 1x1 512->2048 + residual
+    ("backbone.layer4.2.conv1.weight", 1, 2, 2, False),         # 2x2 map (64x64 image case)
+    ("init_regressor.attention_left.0.weight", 2, 8, 8, False),  # 3x3 2048->2x1024, K=18432
+    ("decoder.fusion_layer4.conv1.conv.weight", 2, 16, 16, False),  # 1x1 2304->128
+    ("decoder.fusion_layer4.conv2.conv.weight", 2, 16, 16, False),  # 3x3 128->128
+    ("decoder.fusion_layer4.conv3.conv.weight", 2, 16, 16, True),   # 1x1 + residual, no relu
+    ("decoder.fusion_layer4.skip_layer.conv.weight", 1, 16, 16, False),
+    ("decoder.projecter_4.fusion.0.weight", 2, 16, 16, False),  # 3x3 2560->256
+    ("decoder.projecter_3.fusion.0.weight", 1, 32, 32, False),  # the largest op, K=23040
+    ("decoder.projecter_3.fusion.3.weight", 2, 32, 32, False),
+    ("decoder.conv_final.0.weight", 2, 32, 32, False),
+    ("decoder.seg.0.weight", 2, 32, 32, False),                 # packed seg|dense
+]
+
+
+def epilogue_spec(key):
+    """-> list of (weight_key, bias_key|None, bn_prefix|None) per packed part, relu, stride, pad."""
+    p = key[: -len("weight")]
+    parts = key.split(".")
+    if key.startswith("backbone.layer"):
+        blk = ".".join(parts[:3]) + "."
+        if parts[3] == "downsample":
+            stride = 1 if parts[1] == "layer1" else 2
+            return [(key, None, blk + "downsample.1.")], False, stride, 0
+        n = parts[3][-1]
+        stride = 2 if (n == "2" and parts[2] == "0" and parts[1] != "layer1") else 1
+        return [(key, None, f"{blk}bn{n}.")], True, stride, 1 if n == "2" else 0
+    if ".conv1.conv." in key:
+        return [(key, p + "bias", key.split("conv1.conv.")[0] + "bn2.")], True, 1, 0
+    if ".conv2.conv." in key:
+        return [(key, p + "bias", key.split("conv2.conv.")[0] + "bn3.")], True, 1, 1
+    if ".conv3.conv." in key or ".skip_layer.conv." in key:
+        return [(key, p + "bias", None)], False, 1, 0
+    if key.startswith("init_regressor.attention_left.0"):
+        return [(key, p + "bias", "init_regressor.attention_left.1."),
+                (key.replace("left", "right"), p.replace("left", "right") + "bias",
+                 "init_regressor.attention_right.1.")], True, 1, 1
+    if key.endswith("fusion.0.weight"):
+        return [(key, p + "bias", key.replace("fusion.0.weight", "fusion.1."))], True, 1, 1
+    if key.endswith("fusion.3.weight"):
+        return [(key, p + "bias", None)], False, 1, 0
+    if key == "decoder.conv_final.0.weight":
+        return [(key, None, "decoder.conv_final.1.")], True, 1, 1
+    if key == "decoder.seg.0.weight":
+        return [(key, "decoder.seg.0.bias", "decoder.seg.1."),
+                ("decoder.dense.0.weight", "decoder.dense.0.bias", "decoder.dense.1.")], True, 1, 1
+    raise KeyError(key)
+
+
+def expected(sd, key, x, res, round_bf16):
+    spec, relu, stride, pad = epilogue_spec(key)
+    rb = (lambda t: t.bfloat16().float()) if round_bf16 else (lambda t: t)
+    outs = []
+    for wk, bk, bn in spec:
+        y = F.conv2d(rb(x), rb(sd[wk]), None, stride=stride, padding=pad)
+        scale = torch.ones(y.shape[1])
+        shift = torch.zeros(y.shape[1])
+        if bn:
+            scale = sd[bn + "weight"] / torch.sqrt(sd[bn + "running_var"] + BN_EPS)
+            shift = sd[bn + "bias"] - sd[bn + "running_mean"] * scale
+        if bk:
+            shift = shift + sd[bk] * scale
+        outs.append(y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    y = torch.cat(outs, 1)
+    if res is not None:
+        y = y + rb(res)
+    return F.relu(y) if relu else y
+
+
+def _model(synth_sd, precision):
+    import dir_b200
+
+    m = dir_b200.DIR(21, "./misc/mano", precision=precision, max_batch=8).cuda()
+    m.load_state_dict(synth_sd, strict=False)
+    return m
+
+
+@pytest.fixture(scope="module")
+def m32(synth_sd):
+    return _model(synth_sd, "fp32")
+
+
+@pytest.fixture(scope="module")
+def m16(synth_sd):
+    return _model(synth_sd, "bf16")
+
+
+def _inputs(synth_sd, key, B, H, W, with_res):
+    spec, relu, stride, pad = epilogue_spec(key)
+    w = synth_sd[key]
+    g = torch.Generator().manual_seed(H * 131 + W * 7 + B + w.shape[0])
+    x = torch.relu(torch.randn(B, w.shape[1], H, W, generator=g)) * 1.5
+    kh = w.shape[2]
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kh) // stride + 1
+    cout = sum(synth_sd[s[0]].shape[0] for s in spec)
+    res = torch.randn(B, cout, Ho, Wo, generator=g) if with_res else None
+    return x, res
+
+
+@pytest.mark.parametrize("key,B,H,W,with_res", CASES)
+def test_conv_fp32_cuda_core(m32, synth_sd, key, B, H, W, with_res):
+    from dir_b200 import seams
+
+    x, res = _inputs(synth_sd, key, B, H, W, with_res)
+    want = expected(synth_sd, key, x, res, round_bf16=False)
+    got, used = seams.conv_layer(m32, key, x.cuda(), None if res is None else res.cuda())
+    assert used == 0
+    err = float((got.cpu() - want).abs().max() / want.abs().max())
+    assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("key,B,H,W,with_res", CASES)
+def test_conv_bf16_tcgen05(m16, synth_sd, key, B, H, W, with_res):
+    from dir_b200 import seams
+
+    x, res = _inputs(synth_sd, key, B, H, W, with_res)
+    want = expected(synth_sd, key, x, res, round_bf16=True)
+    got, used = seams.conv_layer(m16, key, x.cuda(), None if res is None else res.cuda())
+    torch.cuda.synchronize()
+    assert used == 1, "layer did not run on the tcgen05 kernel"
+    err = float((got.cpu() - want).abs().max() / want.abs().max())
+    assert err < 6e-3, err
