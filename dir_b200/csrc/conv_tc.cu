@@ -1,16 +1,23 @@
 // tcgen05 / TMA implicit-GEMM convolution for sm_100a: bf16 operands, fp32 accumulation in TMEM,
-// fused affine (+residual) (+ReLU) epilogue. NHWC activations, weights [Cout][(ky,kx,ci)].
+// fused affine (+residual) (+ReLU) epilogue, persistent CTAs. NHWC activations, weights [Cout][(ky,kx,ci)].
 //
-//   D[m, n] = sum_k A[m, k] * W[n, k],  m = (b, ho, wo) (128 consecutive output pixels per CTA),
+//   D[m, n] = sum_k A[m, k] * W[n, k],  m = (b, ho, wo) (128 consecutive output pixels per tile),
 //                                        k = (ky, kx, ci) walked in blocks of 64 channels of one tap.
 //
-// A operand: one 4-D TMA box per (tap, 64-channel block): {64 ch, wbox*stride, hbox*stride, nbox}
-//   of the NHWC input with elementStrides {1, stride, stride, 1}; the tap offset (ky-pad, kx-pad) is just a
-//   coordinate shift and TMA zero-fills out-of-bounds pixels, i.e. im2col + padding cost no instructions.
-// B operand: 2-D TMA box {64 k, BN rows} of the packed weights. Both land K-major with 128B swizzle,
-//   which is exactly the canonical UMMA SWIZZLE_128B K-major layout (SBO = 1024 B).
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one elected thread issues
-//   tcgen05.mma 128xBNx16), warps 2..5 = epilogue (tcgen05.ld 32x32b -> registers -> global).
+// A operand: one 4-D TMA box per (tap, 64-channel block): {64 ch, wbox*stride, hbox*stride, nbox} of the NHWC
+//   input with elementStrides {1, stride, stride, 1}; the tap offset (ky-pad, kx-pad) is a coordinate shift and
+//   TMA zero-fills out-of-bounds pixels, so im2col and padding cost no instructions.
+// B operand: 2-D TMA box {64 k, BN rows} of the packed weights. Both land K-major with 128B swizzle, i.e. the
+//   canonical UMMA SWIZZLE_128B K-major layout (8-row groups 1024 B apart).
+// Stem variant (7x7 stride 2, Cin=3; models/backbone/resnet.py:176): the image is first repacked to a
+//   zero-padded NHWC4 bf16 buffer; a k-block is one kernel row (8 px x 4 ch = 32 elements = 64 B, SWIZZLE_64B)
+//   and the A box is taken from an OVERLAPPING-stride view of that buffer (consecutive wo are 2 px = 16 B apart),
+//   so the 7x7 window gather is again pure TMA.
+// Persistent schedule (grid = min(tiles, SMs)), roles per CTA (192 threads):
+//   warp 0   : TMA producer over a `stages`-deep smem ring (runs ahead across tiles)
+//   warp 1   : TMEM alloc (2 accumulator buffers of BN fp32 columns) + single-thread tcgen05.mma issue
+//   warps 2-5: epilogue of tile i overlapped with the main loop of tile i+1: tcgen05.ld -> affine/residual/ReLU ->
+//              bf16 -> 128B-swizzled smem staging -> TMA store (coalesced, asynchronous); residual tiles arrive by TMA.
 #include <cuda.h>
 
 #include <cstdio>
@@ -25,19 +32,18 @@ namespace dirb200 {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 64;
-constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr int CHUNK_BYTES = BM * 128;  // one 64-column bf16 epilogue box: 16 KB
 
 struct TcArgs {
   const float* scale;
   const float* shift;
-  const __nv_bfloat16* res;
-  __nv_bfloat16* y;
   int M, Cout, Ho, Wo;
   int stride, pad, kw;
-  int taps, cblocks;  // K loop = taps * cblocks blocks of 64
-  int relu;
+  int taps, cblocks;  // K loop = taps * cblocks k-blocks
+  int relu, has_res, stem;
+  int m_tiles, n_tiles, stages;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -47,6 +53,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -74,14 +83,22 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// UMMA shared-memory descriptor, K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// UMMA shared-memory descriptor, K-major, rows of SW bytes (SW = 128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B),
+// 8-row groups 8*SW bytes apart (cute::UMMA::SmemDescriptor / make_umma_desc<Major::K>).
+template <int SW>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
-  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major): 1
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: 8 rows * 128 B
-  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);         // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major): 1
+  d |= (uint64_t)((8 * SW) >> 4) << 32;             // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+  d |= (uint64_t)(SW == 128 ? 2 : 4) << 61;         // layout type: SWIZZLE_128B = 2, SWIZZLE_64B = 4
   return d;
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
@@ -107,61 +124,67 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BN>
+template <int BN, int SW>
 struct TcCfg {
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * BN * 4 + 256;
+  static constexpr int A_STAGE = BM * SW;
+  static constexpr int B_STAGE = BN * SW;
+  static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
+  static constexpr int KSTEPS = SW / 32;  // tcgen05.mma K=16 bf16 = 32 B per step
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N=BN, M=128
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+  static constexpr int NCH = BN / 64;
+  static int smem_bytes(int stages, int has_res) {
+    return 1024 + stages * STAGE_BYTES + 2 * CHUNK_BYTES + (has_res ? 2 * CHUNK_BYTES : 0) + 256;
+  }
 };
 
-template <int BN>
+template <int BN, int SW>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-  using Cfg = TcCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const TcArgs a) {
+  using Cfg = TcCfg<BN, SW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stages = a.stages;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  float* s_scale = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-  float* s_shift = s_scale + BN;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + BN);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint8_t* sB = sA + stages * Cfg::A_STAGE;
+  uint8_t* sOut = sB + stages * Cfg::B_STAGE;             // 2 x 16 KB output staging (128B-swizzled boxes)
+  uint8_t* sRes = sOut + 2 * CHUNK_BYTES;                 // 2 x 16 KB residual staging (only if has_res)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRes + (a.has_res ? 2 * CHUNK_BYTES : 0));
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* tmem_full = bars + 2 * MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* res_full = tmem_empty + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = a.Cout / BN;
-  const int n_tile = blockIdx.x % n_tiles;
-  const int m_tile = blockIdx.x / n_tiles;
-  const int m0 = m_tile * BM, n0 = n_tile * BN;
+  const int total_tiles = a.m_tiles * a.n_tiles;
   const int nkb = a.taps * a.cblocks;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    for (int s = 0; s < STAGES; ++s) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
+    for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&res_full[i], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM allocation: BN fp32 columns x 128 lanes
+  if (warp == 1) {  // TMEM: two accumulator buffers of BN fp32 columns x 128 lanes
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"((uint32_t)BN)
+                 "r"(Cfg::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (warp >= 2) {  // stage the epilogue vectors
-    for (int i = threadIdx.x - 64; i < BN; i += 128) {
-      s_scale[i] = a.scale[n0 + i];
-      s_shift[i] = a.shift[n0 + i];
-    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -169,90 +192,216 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {  // ===== TMA producer
-      const int wo0 = m0 % a.Wo;
-      const int ho0 = (m0 / a.Wo) % a.Ho;
-      const int b0 = m0 / (a.Wo * a.Ho);
-      const int cin = a.cblocks * BK;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
-        const int ky = tap / a.kw, kx = tap - ky * a.kw;
-        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        tma_load_4d(&tmA, &full_bar[s], sA + s * A_STAGE_BYTES, cb * BK, wo0 * a.stride + kx - a.pad,
-                    ho0 * a.stride + ky - a.pad, b0);
-        tma_load_2d(&tmB, &full_bar[s], sB + s * Cfg::B_STAGE_BYTES, tap * cin + cb * BK, n0);
+    if (lane == 0) {  // ===================== TMA producer
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / a.n_tiles) * BM, n0 = (tile % a.n_tiles) * BN;
+        const int wo0 = m0 % a.Wo;
+        const int ho0 = (m0 / a.Wo) % a.Ho;
+        const int b0 = m0 / (a.Wo * a.Ho);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          if (a.stem) {  // k-block = kernel row ky; overlapped view: {32 elems, wo (16 B apart), h, n}
+            tma_load_4d(&tmA, &full_bar[s], sA + s * Cfg::A_STAGE, 0, wo0, ho0 * 2 + kb - 3, b0);
+            tma_load_2d(&tmB, &full_bar[s], sB + s * Cfg::B_STAGE, kb * 32, n0);
+          } else {
+            const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
+            const int ky = tap / a.kw, kx = tap - ky * a.kw;
+            tma_load_4d(&tmA, &full_bar[s], sA + s * Cfg::A_STAGE, cb * 64, wo0 * a.stride + kx - a.pad,
+                        ho0 * a.stride + ky - a.pad, b0);
+            tma_load_2d(&tmB, &full_bar[s], sB + s * Cfg::B_STAGE, kb * 64, n0);
+          }
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+    if (lane == 0) {  // ===================== MMA issuer
+      int s = 0;
+      uint32_t ph = 0;
+      int i = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
+        const int buf = i & 1;
+        mbar_wait(&tmem_empty[buf], ((i >> 1) & 1) ^ 1);  // epilogue drained this accumulator buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t da = umma_desc(smem_u32(sA + s * A_STAGE_BYTES));
-        const uint64_t db = umma_desc(smem_u32(sB + s * Cfg::B_STAGE_BYTES));
+        const uint32_t d = tmem_base + buf * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = umma_desc<SW>(smem_u32(sA + s * Cfg::A_STAGE));
+          const uint64_t db = umma_desc<SW>(smem_u32(sB + s * Cfg::B_STAGE));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle atom
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) ? 1u : 0u);
-        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
-      }
-      umma_commit(tmem_full_bar);  // accumulator complete
-    }
-  } else {
-    // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int lane_base = (warp & 3) * 32;
-    const int m = m0 + lane_base + lane;
-    const bool valid = m < a.M;
-    __nv_bfloat16* yrow = a.y + (int64_t)m * a.Cout + n0;
-    const __nv_bfloat16* rrow = a.res ? a.res + (int64_t)m * a.Cout + n0 : nullptr;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + c * 32, r);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (valid) {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), s_scale[c * 32 + j], s_shift[c * 32 + j]);
-        if (rrow) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u = __ldg(reinterpret_cast<const uint4*>(rrow + c * 32 + q * 8));
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 f = __bfloat1622float2(h[e]);
-              v[q * 8 + e * 2] += f.x;
-              v[q * 8 + e * 2 + 1] += f.y;
-            }
+          for (int k = 0; k < Cfg::KSTEPS; ++k)  // +32 B per K=16 step inside the swizzle atom
+            umma_bf16(d, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have consumed it
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
           }
         }
-        if (a.relu) {
+        umma_commit(&tmem_full[buf]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue (128 threads); warp w may touch TMEM lanes 32*(w%4) .. +31
+    const int et = threadIdx.x - 64;
+    const int lane_base = (warp & 3) * 32;
+    const int row = lane_base + lane;
+    const uint32_t swz = (uint32_t)(row & 7);
+    uint32_t chunk_it = 0;  // running 64-column chunk counter (staging buffer / parity selection)
+    int i = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
+      const int m0 = (tile / a.n_tiles) * BM, n0 = (tile % a.n_tiles) * BN;
+      const int buf = i & 1;
+      if (a.has_res && et == 0) {  // residual chunks 0,1 of this tile (buffers are free: see barrier (d) below)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        for (int c = 0; c < (Cfg::NCH < 2 ? Cfg::NCH : 2); ++c) {
+          const uint32_t rb = (chunk_it + c) & 1;
+          mbar_expect_tx(&res_full[rb], CHUNK_BYTES);
+          tma_load_2d(&tmR, &res_full[rb], sRes + rb * CHUNK_BYTES, n0 + c * 64, m0);
         }
+      }
+      mbar_wait(&tmem_full[buf], (i >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c = 0; c < Cfg::NCH; ++c, ++chunk_it) {
+        uint32_t r[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + buf * BN + c * 64;
+        tmem_ld32(taddr, r);
+        tmem_ld32(taddr + 32, r + 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == Cfg::NCH - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&tmem_empty[buf]);
+        }
+        const float* sc = a.scale + n0 + c * 64;
+        const float* sh = a.shift + n0 + c * 64;
+        const uint32_t ob = chunk_it & 1;
+        uint4 packed[8];
+        if (a.has_res) {
+          mbar_wait(&res_full[ob], (chunk_it >> 1) & 1);
+          const uint8_t* rrow = sRes + ob * CHUNK_BYTES + row * 128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+          for (int q = 0; q < 8; ++q) {
+            const uint4 u = *reinterpret_cast<const uint4*>(rrow + ((q ^ swz) << 4));
+            const __nv_bfloat162* hres = reinterpret_cast<const __nv_bfloat162*>(&u);
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + q * 8));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + q * 8 + 4));
+            const float4 h0 = __ldg(reinterpret_cast<const float4*>(sh + q * 8));
+            const float4 h1 = __ldg(reinterpret_cast<const float4*>(sh + q * 8 + 4));
+            float v[8];
+            v[0] = fmaf(__uint_as_float(r[q * 8 + 0]), s0.x, h0.x);
+            v[1] = fmaf(__uint_as_float(r[q * 8 + 1]), s0.y, h0.y);
+            v[2] = fmaf(__uint_as_float(r[q * 8 + 2]), s0.z, h0.z);
+            v[3] = fmaf(__uint_as_float(r[q * 8 + 3]), s0.w, h0.w);
+            v[4] = fmaf(__uint_as_float(r[q * 8 + 4]), s1.x, h1.x);
+            v[5] = fmaf(__uint_as_float(r[q * 8 + 5]), s1.y, h1.y);
+            v[6] = fmaf(__uint_as_float(r[q * 8 + 6]), s1.z, h1.z);
+            v[7] = fmaf(__uint_as_float(r[q * 8 + 7]), s1.w, h1.w);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
-          *reinterpret_cast<uint4*>(yrow + c * 32 + q * 8) = u;
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(hres[e]);
+              v[2 * e] += f.x;
+              v[2 * e + 1] += f.y;
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&packed[q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hp[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + q * 8));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + q * 8 + 4));
+            const float4 h0 = __ldg(reinterpret_cast<const float4*>(sh + q * 8));
+            const float4 h1 = __ldg(reinterpret_cast<const float4*>(sh + q * 8 + 4));
+            float v[8];
+            v[0] = fmaf(__uint_as_float(r[q * 8 + 0]), s0.x, h0.x);
+            v[1] = fmaf(__uint_as_float(r[q * 8 + 1]), s0.y, h0.y);
+            v[2] = fmaf(__uint_as_float(r[q * 8 + 2]), s0.z, h0.z);
+            v[3] = fmaf(__uint_as_float(r[q * 8 + 3]), s0.w, h0.w);
+            v[4] = fmaf(__uint_as_float(r[q * 8 + 4]), s1.x, h1.x);
+            v[5] = fmaf(__uint_as_float(r[q * 8 + 5]), s1.y, h1.y);
+            v[6] = fmaf(__uint_as_float(r[q * 8 + 6]), s1.z, h1.z);
+            v[7] = fmaf(__uint_as_float(r[q * 8 + 7]), s1.w, h1.w);
+            if (a.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&packed[q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hp[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          }
+        }
+        // (a) the TMA store that last used staging buffer `ob` (two chunks ago) must have read it
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        epi_barrier();  // (b)
+        uint8_t* orow = sOut + ob * CHUNK_BYTES + row * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(orow + ((q ^ swz) << 4)) = packed[q];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // (c) generic-proxy writes -> async proxy
+        epi_barrier();  // (d) staging complete; every thread is also done reading residual buffer `ob`
+        if (et == 0) {
+          tma_store_2d(&tmY, sOut + ob * CHUNK_BYTES, n0 + c * 64, m0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (a.has_res && c + 2 < Cfg::NCH) {  // next residual chunk into the buffer just released
+            mbar_expect_tx(&res_full[ob], CHUNK_BYTES);
+            tma_load_2d(&tmR, &res_full[ob], sRes + ob * CHUNK_BYTES, n0 + (c + 2) * 64, m0);
+          }
         }
       }
     }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output bytes written
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS)
+                 : "memory");
   }
+}
+
+// NCHW fp32 image -> zero-padded NHWC4 bf16: out[b][h][w + 3][c], row pitch (W + 8) pixels (stem operand)
+__global__ void stem_pack_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+  const int Wp = W + 8;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * H * Wp) return;
+  int wp = (int)(idx % Wp);
+  int64_t t = idx / Wp;
+  int h = (int)(t % H);
+  int b = (int)(t / H);
+  int w = wp - 3;
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+  if (w >= 0 && w < W) {
+    const float* p = img + ((int64_t)b * 3 * H + h) * W + w;
+    v0 = __ldg(p);
+    v1 = __ldg(p + (int64_t)H * W);
+    v2 = __ldg(p + 2 * (int64_t)H * W);
+  }
+  __nv_bfloat162 a = __floats2bfloat162_rn(v0, v1), c = __floats2bfloat162_rn(v2, 0.f);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&c);
+  *reinterpret_cast<uint2*>(out + idx * 4) = u;
+}
+
+// stem weights [64][3][7][7] fp32 -> [64][7*32] bf16 with k = ky*32 + kx*4 + c (zero elsewhere)
+__global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 224) return;
+  int k = idx % 224, n = idx / 224;
+  int ky = k / 32, r = k % 32, kx = r / 4, c = r % 4;
+  float v = (kx < 7 && c < 3) ? w[((n * 3 + c) * 7 + ky) * 7 + kx] : 0.f;
+  out[idx] = __float2bfloat16_rn(v);
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -274,6 +423,17 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 int pick_bn(int Cout) { return Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64); }
@@ -289,24 +449,69 @@ Boxes pick_boxes(int Ho, int Wo) {
   return b;
 }
 
-template <int BN>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES) !=
+// [rows][cols] bf16 row-major viewed as 64-column x 128-row boxes with 128B swizzle (epilogue store / residual load)
+bool make_rowmajor_map(CUtensorMap* tm, const void* ptr, int rows, int cols) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)BM};
+  cuuint32_t es[2] = {1, 1};
+  return get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int SW>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
+              TcArgs a, cudaStream_t st) {
+  using Cfg = TcCfg<BN, SW>;
+  static int attr_bytes = 0;
+  const int nkb = a.taps * a.cblocks;
+  int stages = MAX_STAGES;
+  while (stages > 1 && Cfg::smem_bytes(stages, a.has_res) > 227 * 1024) --stages;
+  if (stages > nkb) stages = nkb;
+  a.stages = stages;
+  const int smem = Cfg::smem_bytes(stages, a.has_res);
+  if (smem > attr_bytes) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess)
       return DIRB200_E_CUDA;
-    attr = true;
+    attr_bytes = 227 * 1024;
   }
-  const int m_tiles = (a.M + BM - 1) / BM;
-  conv_tc_kernel<BN><<<m_tiles * (a.Cout / BN), NUM_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, a);
+  const int tiles = a.m_tiles * a.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_tc_kernel<BN, SW><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmY, tmR, a);
   return DIRB200_OK;
+}
+
+template <typename Key>
+struct MapCache {
+  std::map<Key, CUtensorMap> m;
+  CUtensorMap* find(const Key& k) {
+    auto it = m.find(k);
+    return it == m.end() ? nullptr : &it->second;
+  }
+  CUtensorMap* put(const Key& k, const CUtensorMap& v) {
+    if (m.size() > 8192) m.clear();
+    return &m.emplace(k, v).first->second;
+  }
+};
+
+const CUtensorMap* rowmajor_map_cached(const void* ptr, int rows, int cols) {
+  typedef std::tuple<const void*, int, int> Key;
+  static thread_local MapCache<Key> cache;
+  Key k(ptr, rows, cols);
+  CUtensorMap* p = cache.find(k);
+  if (p) return p;
+  CUtensorMap tm;
+  if (!make_rowmajor_map(&tm, ptr, rows, cols)) return nullptr;
+  return cache.put(k, tm);
 }
 
 }  // namespace
 
 bool conv_tc_supported(const ConvLayer& L, int B, int H, int W) {
   if (!L.w16 || L.wmap_bn == 0 || !get_encode()) return false;
+  if (L.tc_stem) return H % 2 == 0 && W == 256;  // one tile = one 128-pixel output row
   if (L.Cin % 64 != 0 || L.Cout % 64 != 0 || L.K != L.Kpad) return false;
   if (L.stride != 1 && L.stride != 2) return false;
   const int Ho = (H + 2 * L.pad - L.kh) / L.stride + 1, Wo = (W + 2 * L.pad - L.kw) / L.stride + 1;
@@ -322,7 +527,7 @@ int conv_tc_prepare_weights(ConvLayer& L) {
   const int bn = pick_bn(L.Cout);
   cuuint64_t dims[2] = {(cuuint64_t)L.Kpad, (cuuint64_t)L.Cout};
   cuuint64_t strides[1] = {(cuuint64_t)L.Kpad * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
+  cuuint32_t box[2] = {64, (cuuint32_t)bn};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(&L.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, L.w16, dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -332,21 +537,91 @@ int conv_tc_prepare_weights(ConvLayer& L) {
   return DIRB200_OK;
 }
 
+// Stem (7x7 s2, 3->64): pack weights as [64][7*32] bf16 (k = ky*32 + kx*4 + c) into `w_packed` (caller-allocated,
+// 64*224 bf16) and build the SWIZZLE_64B weight map.
+int conv_tc_prepare_stem(ConvLayer& L, const float* w_raw, __nv_bfloat16* w_packed, cudaStream_t st) {
+  L.tc_stem = false;
+  EncodeTiledFn enc = get_encode();
+  if (!enc || L.Cin != 3 || L.Cout != 64 || L.kh != 7 || L.kw != 7 || L.stride != 2 || L.pad != 3) return 0;
+  stem_pack_weight_kernel<<<(64 * 224 + 255) / 256, 256, 0, st>>>(w_raw, w_packed);
+  cuuint64_t dims[2] = {224, 64};
+  cuuint64_t strides[1] = {224 * 2};
+  cuuint32_t box[2] = {32, 64};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(&L.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return DIRB200_E_CUDA;
+  L.w16 = w_packed;
+  L.wmap_bn = 64;
+  L.tc_stem = true;
+  return DIRB200_OK;
+}
+
+size_t conv_tc_stem_scratch_bytes(int B, int H, int W) { return (size_t)B * H * (W + 8) * 4 * 2; }
+
+int launch_conv_tc_stem(const ConvLayer& L, const float* img, __nv_bfloat16* scratch, __nv_bfloat16* y, int B, int H,
+                        int W, cudaStream_t st) {
+  const int Wp = W + 8, Ho = H / 2, Wo = W / 2;
+  const int64_t n = (int64_t)B * H * Wp;
+  stem_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(img, scratch, B, H, W);
+  typedef std::tuple<const void*, int, int, int> Key;
+  static thread_local MapCache<Key> cache;
+  Key key(scratch, B, H, W);
+  CUtensorMap* tmA = cache.find(key);
+  if (!tmA) {
+    // overlapping view of the padded NHWC4 buffer: window wo starts at padded pixel 2*wo (= pixel 2*wo-3)
+    CUtensorMap tm;
+    cuuint64_t dims[4] = {32, (cuuint64_t)Wo, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {16, (cuuint64_t)Wp * 8, (cuuint64_t)H * Wp * 8};
+    cuuint32_t box[4] = {32, (cuuint32_t)BM, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, scratch, dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      fprintf(stderr, "dirb200: cuTensorMapEncodeTiled(stem A, overlapping strides) failed: %d\n", (int)r);
+      return DIRB200_E_CUDA;
+    }
+    tmA = cache.put(key, tm);
+  }
+  const int M = B * Ho * Wo;
+  const CUtensorMap* tmY = rowmajor_map_cached(y, M, 64);
+  if (!tmY) return DIRB200_E_CUDA;
+  TcArgs a{};
+  a.scale = L.scale;
+  a.shift = L.shift;
+  a.M = M;
+  a.Cout = 64;
+  a.Ho = Ho;
+  a.Wo = Wo;
+  a.stride = 2;
+  a.pad = 3;
+  a.kw = 7;
+  a.taps = 7;
+  a.cblocks = 1;
+  a.relu = L.relu;
+  a.has_res = 0;
+  a.stem = 1;
+  a.m_tiles = (M + BM - 1) / BM;
+  a.n_tiles = 1;
+  return launch_tc<64, 64>(*tmA, L.wmap, *tmY, *tmY, a, st);
+}
+
 int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bfloat16* res, int B,
                    int H, int W, cudaStream_t st) {
   const int Ho = (H + 2 * L.pad - L.kh) / L.stride + 1, Wo = (W + 2 * L.pad - L.kw) / L.stride + 1;
   const Boxes bx = pick_boxes(Ho, Wo);
   // activation tensor map, cached per (pointer, geometry): encoding is host-only work
   typedef std::tuple<const void*, int, int, int, int, int, int, int, int> Key;
-  static thread_local std::map<Key, CUtensorMap> cache;
+  static thread_local MapCache<Key> cache;
   Key key(x, B, H, W, L.Cin, L.stride, bx.wbox, bx.hbox, bx.nbox);
-  auto it = cache.find(key);
-  if (it == cache.end()) {
+  CUtensorMap* tmA = cache.find(key);
+  if (!tmA) {
     CUtensorMap tm;
     cuuint64_t dims[4] = {(cuuint64_t)L.Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)L.Cin * 2, (cuuint64_t)W * L.Cin * 2, (cuuint64_t)H * W * L.Cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(bx.wbox * L.stride), (cuuint32_t)(bx.hbox * L.stride),
-                         (cuuint32_t)bx.nbox};
+    cuuint32_t box[4] = {64, (cuuint32_t)(bx.wbox * L.stride), (cuuint32_t)(bx.hbox * L.stride), (cuuint32_t)bx.nbox};
     cuuint32_t es[4] = {1, (cuuint32_t)L.stride, (cuuint32_t)L.stride, 1};
     CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x), dims, strides,
                               box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -355,15 +630,16 @@ int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y,
       fprintf(stderr, "dirb200: cuTensorMapEncodeTiled(A) failed: %d (layer %s)\n", (int)r, L.name.c_str());
       return DIRB200_E_CUDA;
     }
-    if (cache.size() > 4096) cache.clear();
-    it = cache.emplace(key, tm).first;
+    tmA = cache.put(key, tm);
   }
-  TcArgs a;
+  const int M = B * Ho * Wo;
+  const CUtensorMap* tmY = rowmajor_map_cached(y, M, L.Cout);
+  const CUtensorMap* tmR = res ? rowmajor_map_cached(res, M, L.Cout) : tmY;
+  if (!tmY || !tmR) return DIRB200_E_CUDA;
+  TcArgs a{};
   a.scale = L.scale;
   a.shift = L.shift;
-  a.res = res;
-  a.y = y;
-  a.M = B * Ho * Wo;
+  a.M = M;
   a.Cout = L.Cout;
   a.Ho = Ho;
   a.Wo = Wo;
@@ -371,12 +647,16 @@ int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y,
   a.pad = L.pad;
   a.kw = L.kw;
   a.taps = L.kh * L.kw;
-  a.cblocks = L.Cin / BK;
+  a.cblocks = L.Cin / 64;
   a.relu = L.relu;
+  a.has_res = res ? 1 : 0;
+  a.stem = 0;
+  a.m_tiles = (M + BM - 1) / BM;
+  a.n_tiles = L.Cout / L.wmap_bn;
   switch (L.wmap_bn) {
-    case 256: return launch_tc<256>(it->second, L.wmap, a, st);
-    case 128: return launch_tc<128>(it->second, L.wmap, a, st);
-    default: return launch_tc<64>(it->second, L.wmap, a, st);
+    case 256: return launch_tc<256, 128>(*tmA, L.wmap, *tmY, *tmR, a, st);
+    case 128: return launch_tc<128, 128>(*tmA, L.wmap, *tmY, *tmR, a, st);
+    default: return launch_tc<64, 128>(*tmA, L.wmap, *tmY, *tmR, a, st);
   }
 }
 

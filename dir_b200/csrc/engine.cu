@@ -274,6 +274,10 @@ int Engine::build(cudaStream_t st) {
   required.clear();
   // ---- backbone (models/backbone/resnet.py)
   stem = make_conv("backbone.conv1.weight", "", "backbone.bn1.", 2, 3, 1);
+  if (!dry && bf16() && err.empty()) {
+    __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(dalloc(64 * 224 / 2));
+    if (wp) conv_tc_prepare_stem(stem, W("backbone.conv1.weight"), wp, st);
+  }
   const int nblocks[4] = {3, 4, 6, 3};
   for (int l = 0; l < 4; ++l) {
     layers[l].clear();
@@ -418,6 +422,9 @@ template <typename T>
 int Engine::run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** c1, T** c2, T** c3, T** c4,
                          cudaStream_t st) {
   const int H2 = H / 2, W2 = W_ / 2, H4 = H / 4, W4 = W_ / 4;
+  const bool tc_stem = sizeof(T) == 2 && !disable_tc && conv_tc_supported(stem, B, H, W_);
+  __nv_bfloat16* stem_scratch =
+      tc_stem ? reinterpret_cast<__nv_bfloat16*>(ar.alloc(conv_tc_stem_scratch_bytes(B, H, W_))) : nullptr;
   T* stem_out = aalloc<T>(ar, (int64_t)B * H2 * W2 * 64);
   T* pool_out = aalloc<T>(ar, (int64_t)B * H4 * W4 * 64);
   const int64_t rsz = (int64_t)B * H4 * W4 * 256;
@@ -432,7 +439,17 @@ int Engine::run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** 
   if (!ar.base) return DIRB200_OK;
   if (ar.overflow) return DIRB200_E_WORKSPACE;
 
-  conv<T>(stem, reinterpret_cast<const T*>(img), stem_out, nullptr, B, H, W_, st, /*in_nchw=*/true);
+  if (tc_stem) {
+    int rc = launch_conv_tc_stem(stem, img, stem_scratch, reinterpret_cast<__nv_bfloat16*>(stem_out), B, H, W_, st);
+    if (rc && !sticky_rc) {
+      sticky_rc = rc;
+      err = "tcgen05 stem launch failed";
+    }
+    launches += 2;
+    tc_launches += 1;
+  } else {
+    conv<T>(stem, reinterpret_cast<const T*>(img), stem_out, nullptr, B, H, W_, st, /*in_nchw=*/true);
+  }
   launch_maxpool3x3s2<T>(stem_out, pool_out, B, H2, W2, 64, st);
   ++launches;
   const T* x = pool_out;

@@ -33,6 +33,7 @@ struct ConvLayer {
   float* shift = nullptr;
   CUtensorMap wmap;  // bf16 weights [Cout][Kpad], box 64(k) x BN rows, 128B swizzle (tensor-core path)
   int wmap_bn = 0;   // rows per weight box (0: no tensor map)
+  bool tc_stem = false;  // 7x7/s2/Cin=3 stem packed for the tensor-core stem variant
 };
 
 struct Bottleneck {
@@ -160,5 +161,9 @@ bool conv_tc_supported(const ConvLayer& L, int B, int H, int W);
 int conv_tc_prepare_weights(ConvLayer& L);  // builds L.wmap
 int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bfloat16* res, int B,
                    int H, int W, cudaStream_t st);
+int conv_tc_prepare_stem(ConvLayer& L, const float* w_raw, __nv_bfloat16* w_packed, cudaStream_t st);
+size_t conv_tc_stem_scratch_bytes(int B, int H, int W);
+int launch_conv_tc_stem(const ConvLayer& L, const float* img, __nv_bfloat16* scratch, __nv_bfloat16* y, int B, int H,
+                        int W, cudaStream_t st);
 
 }  // namespace dirb200
