@@ -22,7 +22,7 @@ EXPORTS = [
     "dirb200_num_required_keys", "dirb200_required_key", "dirb200_workspace_bytes", "dirb200_forward",
     "dirb200_forward_launches", "dirb200_backbone", "dirb200_residual", "dirb200_init_regressor", "dirb200_mano",
     "dirb200_joint2bone", "dirb200_bone_proj", "dirb200_nccl_unique_id", "dirb200_nccl_init",
-    "dirb200_allgather_records", "dirb200_profile_layer", "dirb200_profile_read", "dirb200_conv_layer",
+    "dirb200_allgather_records", "dirb200_profile_layer", "dirb200_profile_read", "dirb200_conv_layer", "dirb200_profile_dump",
 ]
 
 
@@ -75,6 +75,7 @@ def load_library():
     lib.dirb200_nccl_init.argtypes = [vp, C.c_char_p, ip, ip]
     lib.dirb200_allgather_records.argtypes = [vp, vp, vp, ip, vp]
     lib.dirb200_conv_layer.argtypes = [vp, C.c_char_p, vp, vp, ip, ip, ip, vp, C.POINTER(C.c_int), vp, C.c_size_t, vp]
+    lib.dirb200_profile_dump.argtypes = [vp, C.c_char_p, C.c_size_t]
     lib.dirb200_profile_layer.argtypes = [vp, C.c_char_p]
     lib.dirb200_profile_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)]
     for name in EXPORTS:
@@ -129,6 +130,16 @@ class Handle:
     def profile_layer(self, prefix):
         self.check(self.lib.dirb200_profile_layer(self.h, None if prefix is None else prefix.encode()),
                    "profile_layer")
+
+    def profile_dump(self):
+        buf = C.create_string_buffer(1 << 20)
+        self.check(self.lib.dirb200_profile_dump(self.h, buf, len(buf)), "profile_dump")
+        rows = []
+        for line in buf.value.decode().splitlines():
+            f = line.split("\t")
+            rows.append({"layer": f[0], "tc": int(f[1]), "kernel": f[2], "stride": f[3], "cin": int(f[4]),
+                         "cout": int(f[5]), "ms": float(f[6]), "flops": float(f[7]), "bytes": float(f[8])})
+        return rows
 
     def profile_read(self):
         ms, n, fl = C.c_float(), C.c_int(), C.c_double()

@@ -1,6 +1,7 @@
 // extern "C" boundary (include/dirb200.h). No exceptions cross it; errors are codes + last_error().
 #include <dlfcn.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -61,6 +62,8 @@ extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
   {
     const char* dis = getenv("DIRB200_DISABLE_TC");
     h->e.disable_tc = dis && dis[0] == '1';
+    const char* dense = getenv("DIRB200_DENSE_FUSION");
+    h->e.dense_fusion = dense && dense[0] == '1';
   }
   // required-key inventory (no GPU work)
   h->e.dry = true;
@@ -167,6 +170,25 @@ extern "C" int dirb200_profile_read(dirb200_handle* h, float* total_ms, int* lau
   if (launches) *launches = (int)e.prof_used;
   if (total_flops) *total_flops = fl;
   e.prof_used = 0;
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_profile_dump(dirb200_handle* h, char* buf, size_t buf_bytes) {
+  H_CHECK(h);
+  if (!buf || buf_bytes == 0) return fail(e, DIRB200_E_INVALID, "bad buffer");
+  std::string out;
+  for (size_t i = 0; i < e.prof_used; ++i) {
+    if (cudaEventSynchronize(e.prof[i].b) != cudaSuccess) return fail(e, DIRB200_E_CUDA, "event sync failed");
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e.prof[i].a, e.prof[i].b);
+    const ConvLayer* L = e.prof[i].layer;
+    char line[512];
+    snprintf(line, sizeof line, "%s\t%d\t%dx%d\ts%d\t%d\t%d\t%.6f\t%.6e\t%.6e\n", L->name.c_str(), e.prof[i].tc,
+             L->kh, L->kw, L->stride, L->Cin, L->Cout, t, e.prof[i].flops, e.prof[i].bytes);
+    out += line;
+  }
+  if (out.size() + 1 > buf_bytes) return fail(e, DIRB200_E_INVALID, "buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
   return DIRB200_OK;
 }
 

@@ -52,6 +52,76 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Register-tiled CUDA-core GEMM for the small joint-space matrices:
+//   C[r][n] = sum_k A[r][k] * Bt[k][n],  A in shared memory (row-major, lda floats, 16B-aligned rows),
+//   Bt = K-major weights in global memory (row k at Bt + k*ldb, 16B-aligned, K % 4 == 0).
+// Work item = TM rows x 4 columns (row group rg, column group cg). With consecutive threads on consecutive column
+// groups the weight loads are coalesced LDG.128 and the A reads are warp-broadcast LDS.128:
+// 16*TM FMAs per TM LDS + 4 LDG. Rows >= M are clamped on load (their accumulators are garbage, never stored).
+template <int TM>
+__device__ __forceinline__ void smem_gemm_item(const float* __restrict__ A, int lda, int M, int K,
+                                               const float* __restrict__ Bt, int ldb, int cg, int rg,
+                                               float (&acc)[TM][4]) {
+#pragma unroll
+  for (int r = 0; r < TM; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+  const float* arow[TM];
+#pragma unroll
+  for (int r = 0; r < TM; ++r) arow[r] = A + (size_t)min(rg * TM + r, M - 1) * lda;
+  const float* bp = Bt + cg * 4;
+  // weights come straight from L2 (~600 cycles): keep two k-steps (8 x LDG.128) in flight ahead of the FMAs
+  float4 bq[2][4];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      bq[u][q] = (u * 4 < K) ? __ldg(reinterpret_cast<const float4*>(bp + (size_t)(u * 4 + q) * ldb))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < K; k += 8) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int kk = k + u * 4;
+      if (kk >= K) break;
+      const float4 b0 = bq[u][0], b1 = bq[u][1], b2 = bq[u][2], b3 = bq[u][3];
+      if (kk + 8 < K) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bq[u][q] = __ldg(reinterpret_cast<const float4*>(bp + (size_t)(kk + 8 + q) * ldb));
+      }
+#pragma unroll
+      for (int r = 0; r < TM; ++r) {
+        const float4 a = *reinterpret_cast<const float4*>(arow[r] + kk);
+        acc[r][0] = fmaf(a.x, b0.x, acc[r][0]); acc[r][1] = fmaf(a.x, b0.y, acc[r][1]);
+        acc[r][2] = fmaf(a.x, b0.z, acc[r][2]); acc[r][3] = fmaf(a.x, b0.w, acc[r][3]);
+        acc[r][0] = fmaf(a.y, b1.x, acc[r][0]); acc[r][1] = fmaf(a.y, b1.y, acc[r][1]);
+        acc[r][2] = fmaf(a.y, b1.z, acc[r][2]); acc[r][3] = fmaf(a.y, b1.w, acc[r][3]);
+        acc[r][0] = fmaf(a.z, b2.x, acc[r][0]); acc[r][1] = fmaf(a.z, b2.y, acc[r][1]);
+        acc[r][2] = fmaf(a.z, b2.z, acc[r][2]); acc[r][3] = fmaf(a.z, b2.w, acc[r][3]);
+        acc[r][0] = fmaf(a.w, b3.x, acc[r][0]); acc[r][1] = fmaf(a.w, b3.y, acc[r][1]);
+        acc[r][2] = fmaf(a.w, b3.z, acc[r][2]); acc[r][3] = fmaf(a.w, b3.w, acc[r][3]);
+      }
+    }
+  }
+}
+
+// All items of an (M x N) product, strided over the CTA; epi(row, col, value) for every valid element.
+template <int TM, typename Epi>
+__device__ __forceinline__ void smem_gemm(const float* __restrict__ A, int lda, int M, int K,
+                                          const float* __restrict__ Bt, int ldb, int N, int nthreads, Epi epi) {
+  const int ncg = N >> 2, nrg = (M + TM - 1) / TM;
+  for (int item = threadIdx.x; item < ncg * nrg; item += nthreads) {
+    const int cg = item % ncg, rg = item / ncg;
+    float acc[TM][4];
+    smem_gemm_item<TM>(A, lda, M, K, Bt, ldb, cg, rg, acc);
+#pragma unroll
+    for (int r = 0; r < TM; ++r) {
+      const int row = rg * TM + r;
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) epi(row, cg * 4 + j, acc[r][j]);
+      }
+    }
+  }
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

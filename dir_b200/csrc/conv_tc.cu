@@ -137,7 +137,7 @@ struct TcCfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN;
   static constexpr int NCH = BN / 64;
   static int smem_bytes(int stages, int has_res) {
-    return 1024 + stages * STAGE_BYTES + 2 * CHUNK_BYTES + (has_res ? 2 * CHUNK_BYTES : 0) + 256;
+    return 1024 + stages * STAGE_BYTES + 2 * CHUNK_BYTES + (has_res ? 2 * CHUNK_BYTES : 0) + 2 * BN * 4 + 256;
   }
 };
 
@@ -153,7 +153,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sB = sA + stages * Cfg::A_STAGE;
   uint8_t* sOut = sB + stages * Cfg::B_STAGE;             // 2 x 16 KB output staging (128B-swizzled boxes)
   uint8_t* sRes = sOut + 2 * CHUNK_BYTES;                 // 2 x 16 KB residual staging (only if has_res)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRes + (a.has_res ? 2 * CHUNK_BYTES : 0));
+  float* s_scale = reinterpret_cast<float*>(sRes + (a.has_res ? 2 * CHUNK_BYTES : 0));  // [BN] current n-tile
+  float* s_shift = s_scale + BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + MAX_STAGES;
   uint64_t* tmem_full = bars + 2 * MAX_STAGES;
@@ -254,17 +256,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = lane_base + lane;
     const uint32_t swz = (uint32_t)(row & 7);
     uint32_t chunk_it = 0;  // running 64-column chunk counter (staging buffer / parity selection)
+    // residual prefetch runs two chunks ahead of the math across tile boundaries: global chunk g of this CTA
+    // is chunk (g % NCH) of its (g / NCH)-th tile
+    const uint32_t my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t my_chunks = my_tiles * Cfg::NCH;
+    auto issue_res = [&](uint32_t g) {
+      const int t = (int)blockIdx.x + (int)(g / Cfg::NCH) * (int)gridDim.x;
+      const int c = (int)(g % Cfg::NCH);
+      const uint32_t rb = g & 1;
+      mbar_expect_tx(&res_full[rb], CHUNK_BYTES);
+      tma_load_2d(&tmR, &res_full[rb], sRes + rb * CHUNK_BYTES, (t % a.n_tiles) * BN + c * 64, (t / a.n_tiles) * BM);
+    };
+    if (a.has_res && et == 0) {
+      if (my_chunks > 0) issue_res(0);
+      if (my_chunks > 1) issue_res(1);
+    }
     int i = 0;
+    int cur_n0 = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
       const int m0 = (tile / a.n_tiles) * BM, n0 = (tile % a.n_tiles) * BN;
       const int buf = i & 1;
-      if (a.has_res && et == 0) {  // residual chunks 0,1 of this tile (buffers are free: see barrier (d) below)
-#pragma unroll
-        for (int c = 0; c < (Cfg::NCH < 2 ? Cfg::NCH : 2); ++c) {
-          const uint32_t rb = (chunk_it + c) & 1;
-          mbar_expect_tx(&res_full[rb], CHUNK_BYTES);
-          tma_load_2d(&tmR, &res_full[rb], sRes + rb * CHUNK_BYTES, n0 + c * 64, m0);
+      if (n0 != cur_n0) {  // (re)stage the per-channel affine of this n-tile; readers are past barrier (d)
+        for (int j = et; j < BN; j += 128) {
+          s_scale[j] = a.scale[n0 + j];
+          s_shift[j] = a.shift[n0 + j];
         }
+        cur_n0 = n0;
+        epi_barrier();
       }
       mbar_wait(&tmem_full[buf], (i >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -279,8 +297,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(&tmem_empty[buf]);
         }
-        const float* sc = a.scale + n0 + c * 64;
-        const float* sh = a.shift + n0 + c * 64;
+        const float* sc = s_scale + c * 64;
+        const float* sh = s_shift + c * 64;
         const uint32_t ob = chunk_it & 1;
         uint4 packed[8];
         if (a.has_res) {
@@ -290,10 +308,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int q = 0; q < 8; ++q) {
             const uint4 u = *reinterpret_cast<const uint4*>(rrow + ((q ^ swz) << 4));
             const __nv_bfloat162* hres = reinterpret_cast<const __nv_bfloat162*>(&u);
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + q * 8));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + q * 8 + 4));
-            const float4 h0 = __ldg(reinterpret_cast<const float4*>(sh + q * 8));
-            const float4 h1 = __ldg(reinterpret_cast<const float4*>(sh + q * 8 + 4));
+            const float4 s0 = *reinterpret_cast<const float4*>(sc + q * 8);
+            const float4 s1 = *reinterpret_cast<const float4*>(sc + q * 8 + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(sh + q * 8);
+            const float4 h1 = *reinterpret_cast<const float4*>(sh + q * 8 + 4);
             float v[8];
             v[0] = fmaf(__uint_as_float(r[q * 8 + 0]), s0.x, h0.x);
             v[1] = fmaf(__uint_as_float(r[q * 8 + 1]), s0.y, h0.y);
@@ -320,10 +338,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + q * 8));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + q * 8 + 4));
-            const float4 h0 = __ldg(reinterpret_cast<const float4*>(sh + q * 8));
-            const float4 h1 = __ldg(reinterpret_cast<const float4*>(sh + q * 8 + 4));
+            const float4 s0 = *reinterpret_cast<const float4*>(sc + q * 8);
+            const float4 s1 = *reinterpret_cast<const float4*>(sc + q * 8 + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(sh + q * 8);
+            const float4 h1 = *reinterpret_cast<const float4*>(sh + q * 8 + 4);
             float v[8];
             v[0] = fmaf(__uint_as_float(r[q * 8 + 0]), s0.x, h0.x);
             v[1] = fmaf(__uint_as_float(r[q * 8 + 1]), s0.y, h0.y);
@@ -353,10 +371,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (et == 0) {
           tma_store_2d(&tmY, sOut + ob * CHUNK_BYTES, n0 + c * 64, m0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          if (a.has_res && c + 2 < Cfg::NCH) {  // next residual chunk into the buffer just released
-            mbar_expect_tx(&res_full[ob], CHUNK_BYTES);
-            tma_load_2d(&tmR, &res_full[ob], sRes + ob * CHUNK_BYTES, n0 + (c + 2) * 64, m0);
-          }
+          if (a.has_res && chunk_it + 2 < my_chunks) issue_res(chunk_it + 2);  // into the buffer just released
         }
       }
     }
@@ -468,7 +483,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   const int nkb = a.taps * a.cblocks;
   int stages = MAX_STAGES;
   while (stages > 1 && Cfg::smem_bytes(stages, a.has_res) > 227 * 1024) --stages;
-  if (stages > nkb) stages = nkb;
+  (void)nkb;  // the ring runs ahead across tiles, so short K loops still want every stage that fits
   a.stages = stages;
   const int smem = Cfg::smem_bytes(stages, a.has_res);
   if (smem > attr_bytes) {

@@ -29,7 +29,9 @@ static const float* kDummy = reinterpret_cast<const float*>(0x100);
 
 const float* Engine::W(const std::string& name, std::vector<int64_t> shape) {
   if (dry) {
-    required.push_back(name);
+    bool seen = false;
+    for (const auto& r : required) seen = seen || r == name;
+    if (!seen) required.push_back(name);
     return kDummy;
   }
   auto it = raw.find(name);
@@ -230,6 +232,12 @@ void Engine::build_stage(int s, const std::string& p) {
   st.ste.head_b = copy_of(q + "head.1.bias");
   st.fusion0 = make_conv(p + "fusion.0.weight", p + "fusion.0.bias", p + "fusion.1.", 1, 1, 1);
   st.fusion3 = make_conv(p + "fusion.3.weight", p + "fusion.3.bias", "", 1, 0, 0);
+  {
+    const float* fw = W(p + "fusion.0.weight", {256, 2560, 3, 3});
+    float* wp = dalloc((size_t)40 * 64 * 9 * 256);
+    if (!dry && fw && wp) launch_pack_fusion_weight(fw, wp, fin_stream);
+    st.fus_wp = wp;
+  }
 }
 
 // Two convs sharing their input, concatenated along Cout (attention_left|right, seg|dense first convs).
@@ -385,6 +393,10 @@ void Engine::conv(const ConvLayer& L, const T* x, T* y, const T* resid, int B, i
     }
     pr = &prof[prof_used++];
     pr->flops = 2.0 * B * Ho * Wo * (double)L.Cout * L.K;
+    pr->bytes = sizeof(T) * ((double)B * H * W_ * L.Cin + (double)B * Ho * Wo * L.Cout * (resid ? 2 : 1) +
+                             (double)L.Cout * L.K);
+    pr->layer = &L;
+    pr->tc = (sizeof(T) == 2 && !in_nchw && !disable_tc && conv_tc_supported(L, B, H, W_)) ? 1 : 0;
     cudaEventRecord(pr->a, st);
   }
   if (sizeof(T) == 2 && !in_nchw && !disable_tc && conv_tc_supported(L, B, H, W_)) {
@@ -550,7 +562,8 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
   float* jf1 = aalloc<float>(ar, (int64_t)B * 42 * 128);
   float* tok = aalloc<float>(ar, (int64_t)B * 42 * 64);
   float* jfeat = aalloc<float>(ar, (int64_t)B * 42 * 64);
-  T* bone = aalloc<T>(ar, (int64_t)B * S * S * 2560);
+  T* bone = dense_fusion ? aalloc<T>(ar, (int64_t)B * S * S * 2560) : nullptr;
+  float* coef = dense_fusion ? nullptr : aalloc<float>(ar, (int64_t)B * 40 * 2 * 9 * 256);
   T* fus_mid = aalloc<T>(ar, (int64_t)B * S * S * 256);
   T* out = aalloc<T>(ar, (int64_t)B * S * S * 256);
   if (!ar.base) return DIRB200_OK;
@@ -609,9 +622,17 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
   a.joint_feat = jfeat;
   a.B = B;
   launch_regress_mano(a, st);
-  launch_bone_raster<T>(stage_rec, rec_stride, jfeat, bone, B, S, sw.distance, st);
-  launches += 8;
-  conv<T>(sw.fusion0, bone, fus_mid, nullptr, B, S, S, st);
+  launches += 7;
+  if (dense_fusion) {
+    launch_bone_raster<T>(stage_rec, rec_stride, jfeat, bone, B, S, sw.distance, st);
+    ++launches;
+    conv<T>(sw.fusion0, bone, fus_mid, nullptr, B, S, S, st);
+  } else {
+    launch_bone_coef(jfeat, sw.fus_wp, coef, B, st);
+    launch_bone_fusion<T>(stage_rec, rec_stride, coef, sw.fusion0.scale, sw.fusion0.shift, fus_mid, B, S, sw.distance,
+                          st);
+    launches += 2;
+  }
   conv<T>(sw.fusion3, fus_mid, out, nullptr, B, S, S, st);
   if (vis_nchw) {
     launch_bone_vis_nchw(stage_rec + DIRB200_OFF_UV_L, stage_rec + DIRB200_OFF_UV_R, rec_stride, jfeat, jfeat + 21 * 64,

@@ -61,6 +61,7 @@ struct StageWeights {
   SteWeights ste;
   const float *Wm[2], *bm[2], *Wo, *bo;
   ConvLayer fusion0, fusion3;
+  const float* fus_wp = nullptr;  // fusion.0 weights packed for the factored form [40][64][9][256]
 };
 
 struct Arena {
@@ -92,6 +93,7 @@ struct Engine {
   int last_forward_launches = 0;
   int tc_launches = 0;      // convs that went to the tcgen05 kernel since the last forward() start
   int sticky_rc = 0;        // first launch error inside a forward
+  bool dense_fusion = false;  // DIRB200_DENSE_FUSION=1: materialise bone_proj and run the dense 2560-ch conv
   bool disable_tc = false;  // DIRB200_DISABLE_TC=1: force the CUDA-core conv in bf16 mode (debug A/B)
   const ConvLayer* find_conv(const std::string& weight_key) const;
   void* nccl_comm = nullptr;
@@ -99,6 +101,9 @@ struct Engine {
   struct ProfRec {
     cudaEvent_t a, b;
     double flops;
+    double bytes;  // compulsory activation+weight bytes of the launch (input + output (+ residual) + weights)
+    const ConvLayer* layer;
+    int tc;
   };
   bool prof_on = false;
   std::string prof_prefix;

@@ -1,0 +1,243 @@
+// Exact factored form of  bone_proj -> Conv2d(2560->256, 3x3) -> BN -> ReLU   (models/dir.py:57-60,120-122,146-174).
+//
+// bone_proj's 1280-channel map of one hand is, per bone g, a rank-2 field:
+//     in[b, g*64+c, p] = mask_g(p) * ( wa_g(p) * fa[c] + wb_g(p) * fb[c] ),   fa/fb = 64-d features of the bone's joints
+// so the 3x3 convolution over those 2x1280 channels factors EXACTLY (only the fp32 summation order changes):
+//     out[b, n, q] = bias[n] + sum_{hand,g,tap} mask(p) * ( wa(p) * Pa[b,hand,g,tap,n] + wb(p) * Pb[...] ),  p = q + tap - 1
+//     P{a,b}[b,hand,g,tap,n] = sum_c W[n, hand*1280+g*64+c, tap] * f{a,b}[c]
+// Step 1 (bone_coef_kernel) is a small grouped GEMM (B*2 x 64 x 2304 per bone); step 2 (bone_fusion_kernel) walks
+// only the non-zero (pixel, bone) pairs (~3-7 % of the map). 12.2 GFLOP/img of dense conv at 32x32 become
+// ~0.06 GFLOP/img, the (B,2560,S,S) tensor is never materialised, and the arithmetic stays fp32.
+// The dense tcgen05 path (bone_raster + conv_tc) remains available (DIRB200_DENSE_FUSION=1) and is tested against this.
+#include "../../include/dirb200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dirb200 {
+
+namespace {
+
+constexpr int NJ = 21;
+
+struct BoneGeom {
+  float ax, ay, bx, by, dx, dy;
+};
+
+// identical arithmetic to joint.cu::bone_weights (reference op order, no FMA contraction in the mask)
+__device__ __forceinline__ bool bone_weights(const BoneGeom& g, float px, float py, float distance, float& wa,
+                                             float& wb) {
+  float s = __fadd_rn(__fmul_rn(__fsub_rn(g.ax, px), g.dx), __fmul_rn(__fsub_rn(g.ay, py), g.dy));
+  float t = __fadd_rn(__fmul_rn(__fsub_rn(px, g.bx), g.dx), __fmul_rn(__fsub_rn(py, g.by), g.dy));
+  float h = fmaxf(fmaxf(s, t), 0.f);
+  float c = __fsub_rn(__fmul_rn(__fsub_rn(px, g.ax), g.dy), __fmul_rn(__fsub_rn(py, g.ay), g.dx));
+  float dist = hypotf(h, c);
+  if (!(dist < distance)) return false;
+  float ex = __fadd_rn(__fsub_rn(px, g.ax), 1e-6f), ey = __fadd_rn(__fsub_rn(py, g.ay), 1e-6f);
+  float da = sqrtf(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
+  ex = __fadd_rn(__fsub_rn(px, g.bx), 1e-6f);
+  ey = __fadd_rn(__fsub_rn(py, g.by), 1e-6f);
+  float db = sqrtf(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
+  float sum = __fadd_rn(da, db);
+  wa = 1.f - da / sum;
+  wb = 1.f - db / sum;
+  return true;
+}
+
+__device__ __forceinline__ BoneGeom make_bone(const float* uv, int bone, int S) {
+  int pa = (bone % 4 == 0) ? 0 : bone, ch = bone + 1;
+  BoneGeom g;
+  g.ax = (uv[pa * 2] + 1.f) / 2.f * S;
+  g.ay = (uv[pa * 2 + 1] + 1.f) / 2.f * S;
+  g.bx = (uv[ch * 2] + 1.f) / 2.f * S;
+  g.by = (uv[ch * 2 + 1] + 1.f) / 2.f * S;
+  float ex = g.bx - g.ax, ey = g.by - g.ay;
+  float len = hypotf(ex, ey);
+  g.dx = ex / len;
+  g.dy = ey / len;
+  return g;
+}
+
+// fusion.0.weight [256][2560][3][3] -> Wp[hb][c][tap][n]  (hb = hand*20 + bone)
+__global__ void pack_fusion_weight_kernel(const float* __restrict__ w, float* __restrict__ wp) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)40 * 64 * 9 * 256) return;
+  int n = (int)(idx % 256);
+  int64_t t = idx / 256;
+  int tap = (int)(t % 9);
+  t /= 9;
+  int c = (int)(t % 64);
+  int hb = (int)(t / 64);
+  wp[idx] = w[((int64_t)n * 2560 + hb * 64 + c) * 9 + tap];
+}
+
+// P[b][hb][role][tap][n] = sum_c Wp[hb][c][tap][n] * jf[b][hand][joint(hb,role)][c]
+// grid (40, 9, ceil(2B/64)), 256 threads (n); 64 rows (b,role) per CTA.
+__global__ void __launch_bounds__(256) bone_coef_kernel(const float* __restrict__ jf, const float* __restrict__ wp,
+                                                        float* __restrict__ P, int B) {
+  __shared__ __align__(16) float xs[64][68];
+  const int hb = blockIdx.x, tap = blockIdx.y, r0 = blockIdx.z * 64;
+  const int hand = hb / 20, bone = hb % 20;
+  const int pa = (bone % 4 == 0) ? 0 : bone, ch = bone + 1;
+  const int rows = min(64, 2 * B - r0);
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    int r = i >> 6, c = i & 63;
+    float v = 0.f;
+    if (r < rows) {
+      int ri = r0 + r, b = ri >> 1, role = ri & 1;
+      v = jf[((int64_t)(b * 2 + hand) * NJ + (role ? ch : pa)) * 64 + c];
+    }
+    xs[r][c] = v;
+  }
+  __syncthreads();
+  // (rows x 64)·(64 x 256): 8 row groups x 64 column groups = 512 items, 2 per thread
+  const float* Bt = wp + ((int64_t)hb * 64 * 9 + tap) * 256;  // row c at Bt + c*9*256
+  smem_gemm<8>(&xs[0][0], 68, rows, 64, Bt, 9 * 256, 256, 256, [&](int r, int col, float v) {
+    int ri = r0 + r, b = ri >> 1, role = ri & 1;
+    P[((((int64_t)b * 40 + hb) * 2 + role) * 9 + tap) * 256 + col] = v;
+  });
+}
+
+struct Entry {
+  int key;  // xs | ky << 8 | hb << 16
+  float wa, wb;
+};
+
+// One CTA per (image, output row). 256 threads = 256 output channels.
+template <typename T>
+__global__ void __launch_bounds__(256) bone_fusion_kernel(const float* __restrict__ rec, int rec_stride,
+                                                          const float* __restrict__ P, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, T* __restrict__ out, int S,
+                                                          float distance) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  float* s_out = reinterpret_cast<float*>(smraw);                  // [S][256]
+  Entry* list = reinterpret_cast<Entry*>(s_out + S * 256);         // [3*S*40]
+  int* counts = reinterpret_cast<int*>(list + 3 * S * 40);         // [nchunks + 1]
+  __shared__ BoneGeom geo[40];
+  __shared__ float uv[84];
+  const int b = blockIdx.x, y = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 84) uv[tid] = rec[(int64_t)b * rec_stride + DIRB200_OFF_UV_L + tid];
+  for (int i = tid; i < S * 256; i += 256) s_out[i] = 0.f;
+  __syncthreads();
+  if (tid < 40) geo[tid] = make_bone(uv + (tid / 20) * 42, tid % 20, S);
+  __syncthreads();
+  // ---- deterministic compaction of the non-zero (source pixel, bone) pairs of rows y-1, y, y+1
+  // test index t = (ky*S + xs)*40 + hb, processed in chunks of 32 (one warp-ballot each)
+  const int ntests = 3 * S * 40, nchunks = (ntests + 31) / 32;
+  for (int ck = warp; ck < nchunks; ck += 8) {
+    int t = ck * 32 + lane;
+    bool hit = false;
+    if (t < ntests) {
+      int hb = t % 40, xs = (t / 40) % S, ky = t / (40 * S);
+      int ys = y + ky - 1;
+      float wa, wb;
+      if (ys >= 0 && ys < S) hit = bone_weights(geo[hb], xs + 0.5f, ys + 0.5f, distance, wa, wb);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) counts[ck] = __popc(m);
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of counts[0..nchunks) -> counts (in place), total in counts[nchunks]
+    int carry = 0;
+    for (int base = 0; base < nchunks; base += 32) {
+      int i = base + lane;
+      int v = i < nchunks ? counts[i] : 0;
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      if (i < nchunks) counts[i] = carry + incl - v;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) counts[nchunks] = carry;
+  }
+  __syncthreads();
+  for (int ck = warp; ck < nchunks; ck += 8) {
+    int t = ck * 32 + lane;
+    bool hit = false;
+    float wa = 0.f, wb = 0.f;
+    int key = 0;
+    if (t < ntests) {
+      int hb = t % 40, xs = (t / 40) % S, ky = t / (40 * S);
+      int ys = y + ky - 1;
+      if (ys >= 0 && ys < S) hit = bone_weights(geo[hb], xs + 0.5f, ys + 0.5f, distance, wa, wb);
+      key = xs | (ky << 8) | (hb << 16);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      int pos = counts[ck] + __popc(m & ((1u << lane) - 1));
+      list[pos].key = key;
+      list[pos].wa = wa;
+      list[pos].wb = wb;
+    }
+  }
+  __syncthreads();
+  // ---- accumulate: thread n owns column n of s_out (no conflicts, fixed order => bit-reproducible)
+  const int n = tid, nent = counts[nchunks];
+  const float* Pb = P + (int64_t)b * 40 * 2 * 9 * 256 + n;
+  for (int e0 = 0; e0 < nent; e0 += 4) {  // 4 entries = up to 24 independent L2 loads in flight per thread
+    float va[4][3], vb[4][3], wa[4], wb[4];
+    int xs4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = min(e0 + u, nent - 1);
+      const Entry en = list[e];
+      const int ky = (en.key >> 8) & 0xff, hb = en.key >> 16;
+      xs4[u] = (e0 + u < nent) ? (en.key & 0xff) : -100;
+      wa[u] = en.wa;
+      wb[u] = en.wb;
+      // source pixel (ys, xs) feeds output (y, xs - kx + 1) through tap (ky, kx), ky = ys - y + 1
+      const float* pa = Pb + ((int64_t)(hb * 2 + 0) * 9 + ky * 3) * 256;
+      const float* pb = Pb + ((int64_t)(hb * 2 + 1) * 9 + ky * 3) * 256;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        va[u][kx] = __ldg(pa + kx * 256);
+        vb[u][kx] = __ldg(pb + kx * 256);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int x = xs4[u] - kx + 1;
+        if (x >= 0 && x < S) s_out[x * 256 + n] += fmaf(wa[u], va[u][kx], wb[u] * vb[u][kx]);
+      }
+    }
+  }
+  // ---- BN + ReLU epilogue, NHWC store (256 consecutive channels per pixel: fully coalesced)
+  const float sc = scale[n], sh = shift[n];
+  T* orow = out + ((int64_t)b * S + y) * S * 256 + n;
+  for (int x = 0; x < S; ++x) ActIO<T>::st(orow + x * 256, fmaxf(fmaf(s_out[x * 256 + n], sc, sh), 0.f));
+}
+
+}  // namespace
+
+void launch_pack_fusion_weight(const float* w, float* wp, cudaStream_t st) {
+  int64_t total = (int64_t)40 * 64 * 9 * 256;
+  pack_fusion_weight_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(w, wp);
+}
+
+void launch_bone_coef(const float* jf, const float* wp, float* P, int B, cudaStream_t st) {
+  bone_coef_kernel<<<dim3(40, 9, ceil_div(2 * B, 64)), 256, 0, st>>>(jf, wp, P, B);
+}
+
+template <typename T>
+void launch_bone_fusion(const float* rec, int rec_stride, const float* P, const float* scale, const float* shift, T* out,
+                        int B, int S, float distance, cudaStream_t st) {
+  const int nchunks = (3 * S * 40 + 31) / 32;
+  const size_t smem = (size_t)S * 256 * 4 + (size_t)3 * S * 40 * sizeof(Entry) + (nchunks + 1) * 4;
+  static bool attr[2] = {false, false};
+  const int ti = sizeof(T) == 4 ? 0 : 1;
+  if (!attr[ti]) {
+    cudaFuncSetAttribute(bone_fusion_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr[ti] = true;
+  }
+  bone_fusion_kernel<T><<<dim3(B, S), 256, smem, st>>>(rec, rec_stride, P, scale, shift, out, S, distance);
+}
+template void launch_bone_fusion<float>(const float*, int, const float*, const float*, const float*, float*, int, int,
+                                        float, cudaStream_t);
+template void launch_bone_fusion<__nv_bfloat16>(const float*, int, const float*, const float*, const float*,
+                                                __nv_bfloat16*, int, int, float, cudaStream_t);
+
+}  // namespace dirb200

@@ -54,50 +54,38 @@ __global__ void __launch_bounds__(128) joint_embed_kernel(EmbedArgs a) {
   }
   __syncthreads();
 
-  float acc[NJ];
-  float outv[NJ];
-  // ---- filters: 256 -> 128 (BN, ReLU) -> 128
-  {
+  // Three chained (21 x K)·(K x 128) products on the register-tiled CUDA-core GEMM: 3 row groups of 7 joints
+  // x 32 column groups = 96 work items (threads 96..127 only help with loads).
+  const bool worker = n < 96;
+  const int cg = n & 31, rg = n >> 5;
+  float outv[7][4];
+  float acc[7][4];
+  {  // ---- filters: 256 -> 128 (BN, ReLU) -> 128
     const PointMlp& f = a.filters[hand];
+    if (worker) {
+      smem_gemm_item<7>(&samp[0][0], 256, NJ, 256, f.w1t, 128, cg, rg, acc);
+      const float4 s1 = __ldg(reinterpret_cast<const float4*>(f.s1 + cg * 4));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(f.b1 + cg * 4));
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
-    for (int k = 0; k < 256; k += 4) {
-      float w0 = __ldg(f.w1t + (k + 0) * 128 + n), w1 = __ldg(f.w1t + (k + 1) * 128 + n);
-      float w2 = __ldg(f.w1t + (k + 2) * 128 + n), w3 = __ldg(f.w1t + (k + 3) * 128 + n);
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        float4 s = *reinterpret_cast<const float4*>(&samp[j][k]);
-        acc[j] = fmaf(s.x, w0, acc[j]);
-        acc[j] = fmaf(s.y, w1, acc[j]);
-        acc[j] = fmaf(s.z, w2, acc[j]);
-        acc[j] = fmaf(s.w, w3, acc[j]);
+      for (int r = 0; r < 7; ++r) {
+        float4 h = make_float4(fmaxf(fmaf(acc[r][0], s1.x, b1.x), 0.f), fmaxf(fmaf(acc[r][1], s1.y, b1.y), 0.f),
+                               fmaxf(fmaf(acc[r][2], s1.z, b1.z), 0.f), fmaxf(fmaf(acc[r][3], s1.w, b1.w), 0.f));
+        *reinterpret_cast<float4*>(&hid[rg * 7 + r][cg * 4]) = h;
       }
     }
-    float s1 = f.s1[n], b1 = f.b1[n];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) hid[j][n] = fmaxf(fmaf(acc[j], s1, b1), 0.f);
     __syncthreads();
-    float b2 = f.b2[n];
+    if (worker) {
+      smem_gemm_item<7>(&hid[0][0], 128, NJ, 128, f.w2t, 128, cg, rg, acc);
+      const float4 b2 = __ldg(reinterpret_cast<const float4*>(f.b2 + cg * 4));
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
-    for (int k = 0; k < 128; k += 4) {
-      float w0 = __ldg(f.w2t + (k + 0) * 128 + n), w1 = __ldg(f.w2t + (k + 1) * 128 + n);
-      float w2 = __ldg(f.w2t + (k + 2) * 128 + n), w3 = __ldg(f.w2t + (k + 3) * 128 + n);
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        float4 s = *reinterpret_cast<const float4*>(&hid[j][k]);
-        acc[j] = fmaf(s.x, w0, acc[j]);
-        acc[j] = fmaf(s.y, w1, acc[j]);
-        acc[j] = fmaf(s.z, w2, acc[j]);
-        acc[j] = fmaf(s.w, w3, acc[j]);
+      for (int r = 0; r < 7; ++r) {
+        outv[r][0] = acc[r][0] + b2.x; outv[r][1] = acc[r][1] + b2.y;
+        outv[r][2] = acc[r][2] + b2.z; outv[r][3] = acc[r][3] + b2.w;
       }
     }
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) outv[j] = acc[j] + b2;
     __syncthreads();
   }
-  // ---- pos_emb: 3 -> 128 (BN, ReLU) -> 128
-  {
+  {  // ---- pos_emb: 3 -> 128 (BN, ReLU) -> 128
     const PointMlp& f = a.pos[hand];
     float w0 = f.w1t[n], w1 = f.w1t[128 + n], w2 = f.w1t[256 + n];
     float s1 = f.s1[n], b1 = f.b1[n];
@@ -107,39 +95,35 @@ __global__ void __launch_bounds__(128) joint_embed_kernel(EmbedArgs a) {
       hid[j][n] = fmaxf(fmaf(h, s1, b1), 0.f);
     }
     __syncthreads();
-    float b2 = f.b2[n];
+    if (worker) {
+      smem_gemm_item<7>(&hid[0][0], 128, NJ, 128, f.w2t, 128, cg, rg, acc);
+      const float4 b2 = __ldg(reinterpret_cast<const float4*>(f.b2 + cg * 4));
+      float* out = a.out + ((int64_t)(b * 2 + hand) * NJ) * 128 + cg * 4;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
-    for (int k = 0; k < 128; k += 4) {
-      float q0 = __ldg(f.w2t + (k + 0) * 128 + n), q1 = __ldg(f.w2t + (k + 1) * 128 + n);
-      float q2 = __ldg(f.w2t + (k + 2) * 128 + n), q3 = __ldg(f.w2t + (k + 3) * 128 + n);
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        float4 s = *reinterpret_cast<const float4*>(&hid[j][k]);
-        acc[j] = fmaf(s.x, q0, acc[j]);
-        acc[j] = fmaf(s.y, q1, acc[j]);
-        acc[j] = fmaf(s.z, q2, acc[j]);
-        acc[j] = fmaf(s.w, q3, acc[j]);
+      for (int r = 0; r < 7; ++r) {
+        float4 o = make_float4(outv[r][0] + (acc[r][0] + b2.x), outv[r][1] + (acc[r][1] + b2.y),
+                               outv[r][2] + (acc[r][2] + b2.z), outv[r][3] + (acc[r][3] + b2.w));
+        *reinterpret_cast<float4*>(out + (rg * 7 + r) * 128) = o;
       }
     }
-    float* out = a.out + ((int64_t)(b * 2 + hand) * NJ) * 128 + n;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) out[j * 128] = outv[j] + (acc[j] + b2);
   }
 }
 
 // =================================================================== gcn_layer
 constexpr int GBT = 32;  // images per CTA
 
-__global__ void __launch_bounds__(128) gcn_layer_kernel(GcnLayerArgs a) {
+// One CTA per (output joint i, hand, 32-image tile); 256 threads = 8 row groups (4 images) x 32 column groups.
+// out = relu(bn( x_i W0[i] + sum_j A1[i][j] x_j W1[j] + bias )) (+ global_pos_emb on the last layer).
+__global__ void __launch_bounds__(256) gcn_layer_kernel(GcnLayerArgs a) {
   __shared__ __align__(16) float xs[GBT][128];
-  const int i = blockIdx.x, hand = blockIdx.y, b0 = blockIdx.z * GBT, n = threadIdx.x;
+  const int i = blockIdx.x, hand = blockIdx.y, b0 = blockIdx.z * GBT, tid = threadIdx.x;
+  const int cg = tid & 31, rg = tid >> 5;
   const int nb = min(GBT, a.B - b0);
   const float* W = a.W[hand];
   const float* A1 = a.A1[hand];
-  float tot[GBT];
+  float tot[4][4], acc[4][4];
 #pragma unroll
-  for (int bb = 0; bb < GBT; ++bb) tot[bb] = 0.f;
+  for (int r = 0; r < 4; ++r) tot[r][0] = tot[r][1] = tot[r][2] = tot[r][3] = 0.f;
 
   // sources: self (W[0][i], weight 1) then neighbours j (W[1][j], weight A1[i][j])
   for (int src = -1; src < NJ; ++src) {
@@ -157,38 +141,37 @@ __global__ void __launch_bounds__(128) gcn_layer_kernel(GcnLayerArgs a) {
       Wsrc = W + (int64_t)(NJ + src) * 128 * 128;
     }
     __syncthreads();
-    for (int bb = 0; bb < GBT; ++bb)
-      xs[bb][n] = (bb < nb) ? a.x[((int64_t)((b0 + bb) * 2 + hand) * NJ + j) * 128 + n] : 0.f;
-    __syncthreads();
-    float acc[GBT];
-#pragma unroll
-    for (int bb = 0; bb < GBT; ++bb) acc[bb] = 0.f;
-    for (int k = 0; k < 128; k += 4) {
-      float w0 = __ldg(Wsrc + (k + 0) * 128 + n), w1 = __ldg(Wsrc + (k + 1) * 128 + n);
-      float w2 = __ldg(Wsrc + (k + 2) * 128 + n), w3 = __ldg(Wsrc + (k + 3) * 128 + n);
-#pragma unroll
-      for (int bb = 0; bb < GBT; ++bb) {
-        float4 s = *reinterpret_cast<const float4*>(&xs[bb][k]);
-        acc[bb] = fmaf(s.x, w0, acc[bb]);
-        acc[bb] = fmaf(s.y, w1, acc[bb]);
-        acc[bb] = fmaf(s.z, w2, acc[bb]);
-        acc[bb] = fmaf(s.w, w3, acc[bb]);
-      }
+    for (int e = tid; e < GBT * 32; e += 256) {
+      int bb = e >> 5, c4 = e & 31;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bb < nb)
+        v = __ldg(reinterpret_cast<const float4*>(a.x + ((int64_t)((b0 + bb) * 2 + hand) * NJ + j) * 128) + c4);
+      *reinterpret_cast<float4*>(&xs[bb][c4 * 4]) = v;
     }
+    __syncthreads();
+    smem_gemm_item<4>(&xs[0][0], 128, GBT, 128, Wsrc, 128, cg, rg, acc);
 #pragma unroll
-    for (int bb = 0; bb < GBT; ++bb) tot[bb] = fmaf(aw, acc[bb], tot[bb]);
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tot[r][q] = fmaf(aw, acc[r][q], tot[r][q]);
   }
-  const float sc = a.scale[hand][n], sh = a.shift[hand][n];
+  {
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale[hand] + cg * 4));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift[hand] + cg * 4));
 #pragma unroll
-  for (int bb = 0; bb < GBT; ++bb) tot[bb] = fmaxf(fmaf(tot[bb], sc, sh), 0.f);
-
+    for (int r = 0; r < 4; ++r) {
+      tot[r][0] = fmaxf(fmaf(tot[r][0], sc.x, sh.x), 0.f);
+      tot[r][1] = fmaxf(fmaf(tot[r][1], sc.y, sh.y), 0.f);
+      tot[r][2] = fmaxf(fmaf(tot[r][2], sc.z, sh.z), 0.f);
+      tot[r][3] = fmaxf(fmaf(tot[r][3], sc.w, sh.w), 0.f);
+    }
+  }
   if (a.add_global) {  // + global_pos_emb(xyz/0.15 -/+ offset/2)   (models/dir.py:106-110)
     __syncthreads();
     const PointMlp& g = a.gpos;
-    float w0 = g.w1t[n], w1 = g.w1t[128 + n], w2 = g.w1t[256 + n];
-    float s1 = g.s1[n], b1 = g.b1[n];
     const float sgn = hand == 0 ? -1.f : 1.f;
-    for (int bb = 0; bb < GBT; ++bb) {
+    for (int e = tid; e < GBT * 128; e += 256) {
+      int bb = e >> 7, k = e & 127;
       float h = 0.f;
       if (bb < nb) {
         const float* rec = a.prev_record + (int64_t)(b0 + bb) * a.rec_stride;
@@ -197,33 +180,26 @@ __global__ void __launch_bounds__(128) gcn_layer_kernel(GcnLayerArgs a) {
         float px = p[0] / 0.15f + sgn * (off[0] / 2.f);
         float py = p[1] / 0.15f + sgn * (off[1] / 2.f);
         float pz = p[2] / 0.15f + sgn * (off[2] / 2.f);
-        h = fmaxf(fmaf(fmaf(pz, w2, fmaf(py, w1, px * w0)), s1, b1), 0.f);
+        h = fmaxf(fmaf(fmaf(pz, g.w1t[256 + k], fmaf(py, g.w1t[128 + k], px * g.w1t[k])), g.s1[k], g.b1[k]), 0.f);
       }
-      xs[bb][n] = h;
+      xs[bb][k] = h;
     }
     __syncthreads();
-    float acc[GBT];
+    smem_gemm_item<4>(&xs[0][0], 128, GBT, 128, g.w2t, 128, cg, rg, acc);
+    const float4 b2 = __ldg(reinterpret_cast<const float4*>(g.b2 + cg * 4));
 #pragma unroll
-    for (int bb = 0; bb < GBT; ++bb) acc[bb] = 0.f;
-    for (int k = 0; k < 128; k += 4) {
-      float q0 = __ldg(g.w2t + (k + 0) * 128 + n), q1 = __ldg(g.w2t + (k + 1) * 128 + n);
-      float q2 = __ldg(g.w2t + (k + 2) * 128 + n), q3 = __ldg(g.w2t + (k + 3) * 128 + n);
-#pragma unroll
-      for (int bb = 0; bb < GBT; ++bb) {
-        float4 s = *reinterpret_cast<const float4*>(&xs[bb][k]);
-        acc[bb] = fmaf(s.x, q0, acc[bb]);
-        acc[bb] = fmaf(s.y, q1, acc[bb]);
-        acc[bb] = fmaf(s.z, q2, acc[bb]);
-        acc[bb] = fmaf(s.w, q3, acc[bb]);
-      }
+    for (int r = 0; r < 4; ++r) {
+      tot[r][0] += acc[r][0] + b2.x; tot[r][1] += acc[r][1] + b2.y;
+      tot[r][2] += acc[r][2] + b2.z; tot[r][3] += acc[r][3] + b2.w;
     }
-    const float b2 = g.b2[n];
-#pragma unroll
-    for (int bb = 0; bb < GBT; ++bb) tot[bb] += acc[bb] + b2;
   }
 #pragma unroll
-  for (int bb = 0; bb < GBT; ++bb)
-    if (bb < nb) a.y[((int64_t)((b0 + bb) * 2 + hand) * NJ + i) * 128 + n] = tot[bb];
+  for (int r = 0; r < 4; ++r) {
+    const int bb = rg * 4 + r;
+    if (bb < nb)
+      *reinterpret_cast<float4*>(a.y + ((int64_t)((b0 + bb) * 2 + hand) * NJ + i) * 128 + cg * 4) =
+          make_float4(tot[r][0], tot[r][1], tot[r][2], tot[r][3]);
+  }
 }
 
 // =================================================================== STE
@@ -233,40 +209,18 @@ constexpr int SC_LD = 44;
 constexpr int STE_SMEM_FLOATS = NT * 128 * 2 + NT * 384 + 4 * NT * SC_LD;
 
 // out[r][n] = sum_k in[r][k] * Wt[k][n] + bias[n]; optional GELU; optional residual accumulate into out.
-// work item = (n, row-half) with 21 rows each.
+// 42 token rows = 6 row groups of 7 on the register-tiled GEMM.
 template <int MODE>  // 0: store, 1: store GELU, 2: out += result
 __device__ __forceinline__ void ste_linear(const float* __restrict__ in, int ldin, int K, const float* __restrict__ Wt,
                                            const float* __restrict__ bias, int N, float* __restrict__ out, int ldout) {
-  for (int item = threadIdx.x; item < N * 2; item += STE_THREADS) {
-    const int n = item % N, half = item / N;
-    const float* inr = in + half * 21 * ldin;
-    float acc[21];
-#pragma unroll
-    for (int r = 0; r < 21; ++r) acc[r] = 0.f;
-    for (int k = 0; k < K; k += 4) {
-      float w0 = __ldg(Wt + (int64_t)(k + 0) * N + n), w1 = __ldg(Wt + (int64_t)(k + 1) * N + n);
-      float w2 = __ldg(Wt + (int64_t)(k + 2) * N + n), w3 = __ldg(Wt + (int64_t)(k + 3) * N + n);
-#pragma unroll
-      for (int r = 0; r < 21; ++r) {
-        float4 s = *reinterpret_cast<const float4*>(inr + r * ldin + k);
-        acc[r] = fmaf(s.x, w0, acc[r]);
-        acc[r] = fmaf(s.y, w1, acc[r]);
-        acc[r] = fmaf(s.z, w2, acc[r]);
-        acc[r] = fmaf(s.w, w3, acc[r]);
-      }
-    }
-    const float bb = bias[n];
-    float* o = out + half * 21 * ldout + n;
-#pragma unroll
-    for (int r = 0; r < 21; ++r) {
-      float v = acc[r] + bb;
-      if (MODE == 1) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-      if (MODE == 2)
-        o[r * ldout] += v;
-      else
-        o[r * ldout] = v;
-    }
-  }
+  smem_gemm<7>(in, ldin, NT, K, Wt, N, N, STE_THREADS, [&](int r, int n, float v) {
+    v += __ldg(bias + n);
+    if (MODE == 1) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    if (MODE == 2)
+      out[r * ldout + n] += v;
+    else
+      out[r * ldout + n] = v;
+  });
 }
 
 // LayerNorm over 128 channels, one warp per row (two-pass like ATen)
@@ -484,7 +438,7 @@ template void launch_joint_embed<float>(const EmbedArgs&, cudaStream_t);
 template void launch_joint_embed<__nv_bfloat16>(const EmbedArgs&, cudaStream_t);
 
 void launch_gcn_layer(const GcnLayerArgs& a, cudaStream_t st) {
-  gcn_layer_kernel<<<dim3(NJ, 2, ceil_div(a.B, GBT)), 128, 0, st>>>(a);
+  gcn_layer_kernel<<<dim3(NJ, 2, ceil_div(a.B, GBT)), 256, 0, st>>>(a);
 }
 
 void launch_ste(const float* x, float* y, const SteWeights& w, int B, cudaStream_t st) {

@@ -145,6 +145,12 @@ void launch_mano_only(const float* para, const ManoWeights mano[2], float* stage
 template <typename T>
 void launch_bone_raster(const float* stage_record, int rec_stride, const float* joint_feat, T* out, int B, int S,
                         float distance, cudaStream_t st);
+// exact factored bone_proj -> conv3x3(2560->256) -> BN -> ReLU (fusion.cu)
+void launch_pack_fusion_weight(const float* w /*[256][2560][3][3]*/, float* wp /*[40][64][9][256]*/, cudaStream_t st);
+void launch_bone_coef(const float* joint_feat, const float* wp, float* P /*(B,40,2,9,256)*/, int B, cudaStream_t st);
+template <typename T>
+void launch_bone_fusion(const float* stage_record, int rec_stride, const float* P, const float* scale,
+                        const float* shift, T* out /*NHWC (B,S,S,256)*/, int B, int S, float distance, cudaStream_t st);
 // vis = left + right, NCHW fp32 (B,1280,S,S); uv given per hand as (B,21,2) with image stride uv_stride
 void launch_bone_vis_nchw(const float* uv_l, const float* uv_r, int uv_stride, const float* feat_l, const float* feat_r,
                           int feat_stride, float* out, int B, int S, float distance, int add_right, cudaStream_t st);

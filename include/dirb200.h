@@ -101,6 +101,9 @@ int dirb200_forward_launches(const dirb200_handle* h, int batch);
  * and their algorithmic FLOPs (2*M*N*K) since the last read, and resets. Not usable under graph capture. */
 int dirb200_profile_layer(dirb200_handle* h, const char* prefix);
 int dirb200_profile_read(dirb200_handle* h, float* total_ms, int* launches, double* total_flops);
+/* Per-launch detail of the records accumulated since the last read, one line per conv launch:
+ * "weight_key \t tensor_cores \t KhxKw \t sS \t Cin \t Cout \t ms \t flops \t compulsory_bytes". Does not reset. */
+int dirb200_profile_dump(dirb200_handle* h, char* buf, size_t buf_bytes);
 
 /* Per-seam entry points; used by the parity tests. All tensors fp32 device memory,
  * feature maps NCHW exactly as the reference module sees them; conversion to the internal NHWC /
