@@ -122,6 +122,121 @@ __device__ __forceinline__ void smem_gemm(const float* __restrict__ A, int lda, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-cooperative GEMM with the weights STREAMED through shared memory by bulk async copies (cp.async.bulk +
+// mbarrier), for the latency-bound joint-space products:
+//   C[M x NC] = A[M x K] * Bt[K x NC],   A in smem, Bt rows in global (row k at Bt + k*ldb, NC in {64,128} columns).
+// Slabs of 32 k-rows (NC*128 B) are double-buffered; warp 0 issues one 16B-aligned bulk copy per row two slabs ahead,
+// every thread owns one TM x 4 register tile. All threads of the CTA must call this (it contains __syncthreads).
+struct WStream {
+  float* wbuf;     // 2 x 32 x 128 floats (32 KB), 128B-aligned
+  uint64_t* bar;   // 2 mbarriers (initialised to count 1)
+  uint32_t it;     // running slab counter (buffer = it & 1, parity = (it >> 1) & 1)
+};
+
+__device__ __forceinline__ uint32_t cta_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void wstream_init(WStream& ws, float* wbuf, uint64_t* bar) {
+  ws.wbuf = wbuf;
+  ws.bar = bar;
+  ws.it = 0;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cta_smem_u32(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cta_smem_u32(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void wstream_issue(const WStream& ws, uint32_t g, const float* __restrict__ Bt, int ldb,
+                                              int k0, int NC) {
+  // called by warp 0 only: slab g <- rows k0 .. k0+31 (NC floats each)
+  const int lane = threadIdx.x & 31;
+  const uint32_t buf = g & 1;
+  const uint32_t bar = cta_smem_u32(&ws.bar[buf]);
+  if (lane == 0)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(32 * NC * 4))
+                 : "memory");
+  __syncwarp();
+  const uint32_t dst = cta_smem_u32(ws.wbuf + buf * (32 * 128) + lane * NC);
+  const float* src = Bt + (size_t)(k0 + lane) * ldb;
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"((uint32_t)(NC * 4)), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void wstream_wait(const WStream& ws, uint32_t g) {
+  const uint32_t bar = cta_smem_u32(&ws.bar[g & 1]);
+  const uint32_t parity = (g >> 1) & 1;
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+template <int TM, typename Epi>
+__device__ __forceinline__ void cta_gemm(const float* __restrict__ A, int lda, int M, int K,
+                                         const float* __restrict__ Bt, int ldb, int NC, WStream& ws, Epi epi) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int ncg = NC >> 2, nrg = (M + TM - 1) / TM;
+  const int cg = tid % ncg, rg = tid / ncg;
+  const bool active = tid < ncg * nrg;
+  const int nslab = K >> 5;
+  const uint32_t g0 = ws.it;
+  if (warp == 0) {
+    wstream_issue(ws, g0, Bt, ldb, 0, NC);
+    if (nslab > 1) wstream_issue(ws, g0 + 1, Bt, ldb, 32, NC);
+  }
+  float acc[TM][4];
+#pragma unroll
+  for (int r = 0; r < TM; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+  const float* arow[TM];
+#pragma unroll
+  for (int r = 0; r < TM; ++r) arow[r] = A + (size_t)min(rg * TM + r, M - 1) * lda;
+  for (int sl = 0; sl < nslab; ++sl) {
+    const uint32_t g = g0 + sl;
+    wstream_wait(ws, g);
+    if (active) {
+      const float* wb = ws.wbuf + (g & 1) * (32 * 128) + cg * 4;
+#pragma unroll
+      for (int kk = 0; kk < 32; kk += 4) {
+        const float4 b0 = *reinterpret_cast<const float4*>(wb + (kk + 0) * NC);
+        const float4 b1 = *reinterpret_cast<const float4*>(wb + (kk + 1) * NC);
+        const float4 b2 = *reinterpret_cast<const float4*>(wb + (kk + 2) * NC);
+        const float4 b3 = *reinterpret_cast<const float4*>(wb + (kk + 3) * NC);
+#pragma unroll
+        for (int r = 0; r < TM; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(arow[r] + sl * 32 + kk);
+          acc[r][0] = fmaf(a.x, b0.x, acc[r][0]); acc[r][1] = fmaf(a.x, b0.y, acc[r][1]);
+          acc[r][2] = fmaf(a.x, b0.z, acc[r][2]); acc[r][3] = fmaf(a.x, b0.w, acc[r][3]);
+          acc[r][0] = fmaf(a.y, b1.x, acc[r][0]); acc[r][1] = fmaf(a.y, b1.y, acc[r][1]);
+          acc[r][2] = fmaf(a.y, b1.z, acc[r][2]); acc[r][3] = fmaf(a.y, b1.w, acc[r][3]);
+          acc[r][0] = fmaf(a.z, b2.x, acc[r][0]); acc[r][1] = fmaf(a.z, b2.y, acc[r][1]);
+          acc[r][2] = fmaf(a.z, b2.z, acc[r][2]); acc[r][3] = fmaf(a.z, b2.w, acc[r][3]);
+          acc[r][0] = fmaf(a.w, b3.x, acc[r][0]); acc[r][1] = fmaf(a.w, b3.y, acc[r][1]);
+          acc[r][2] = fmaf(a.w, b3.z, acc[r][2]); acc[r][3] = fmaf(a.w, b3.w, acc[r][3]);
+        }
+      }
+      if (sl == nslab - 1) {
+#pragma unroll
+        for (int r = 0; r < TM; ++r) {
+          const int row = rg * TM + r;
+          if (row < M) epi(r, row, cg * 4, acc[r]);
+        }
+      }
+    }
+    __syncthreads();  // slab buffer (g & 1) fully consumed (and, on the last slab, epi() results visible)
+    if (warp == 0 && sl + 2 < nslab) wstream_issue(ws, g + 2, Bt, ldb, (sl + 2) * 32, NC);
+  }
+  ws.it = g0 + nslab;
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

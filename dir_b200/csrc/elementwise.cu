@@ -8,91 +8,142 @@ namespace dirb200 {
 
 namespace {
 
+// ---------------------------------------------------------------- vector helpers: 8 channels per thread
+template <typename T>
+struct Vec8;
+template <>
+struct Vec8<float> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <>
+struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+
 // ---------------------------------------------------------------- maxpool 3x3 s2 p1 (resnet.py:247)
+// one thread = one output pixel x 8 channels; C/8 consecutive threads share a pixel (coalesced 16B accesses)
 template <typename T>
 __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo) {
-  const int C4 = C >> 2;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t total = (int64_t)B * Ho * Wo * C4;
+  const int C8 = C >> 3;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = (unsigned)B * Ho * Wo * C8;
   if (idx >= total) return;
-  int c = (int)(idx % C4) * 4;
-  int64_t t = idx / C4;
-  int wo = (int)(t % Wo);
+  const int c = (idx % C8) * 8;
+  unsigned t = idx / C8;
+  const int wo = t % Wo;
   t /= Wo;
-  int ho = (int)(t % Ho);
-  int b = (int)(t / Ho);
-  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  const int ho = t % Ho;
+  const int b = t / Ho;
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
-    int hi = ho * 2 - 1 + dy;
+    const int hi = ho * 2 - 1 + dy;
     if (hi < 0 || hi >= H) continue;
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
-      int wi = wo * 2 - 1 + dx;
+      const int wi = wo * 2 - 1 + dx;
       if (wi < 0 || wi >= W) continue;
-      float4 v = ActIO<T>::ld4(x + (((int64_t)b * H + hi) * W + wi) * C + c);
-      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      float v[8];
+      Vec8<T>::ld(x + ((size_t)(b * H + hi) * W + wi) * C + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
     }
   }
-  ActIO<T>::st4(y + (((int64_t)b * Ho + ho) * Wo + wo) * C + c, m);
+  Vec8<T>::st(y + ((size_t)(b * Ho + ho) * Wo + wo) * C + c, m);
 }
 
 // ---------------------------------------------------------------- upsample(2x bilinear, align_corners=False) + concat + BN/ReLU
-// models/dir.py:442-444,455,459-461,470 and hourglass.py:60-61 (bn1+relu1 of the consuming Residual)
+// models/dir.py:442-444,455,459-461,470 and hourglass.py:60-61 (bn1+relu1 of the consuming Residual).
+// One CTA per output pixel (all index math once per CTA, 32-bit); threads stride over 8-channel vectors.
 template <typename T>
-__global__ void concat_preact_kernel(const T* __restrict__ s0, int C0, int up0, const T* __restrict__ s1, int C1,
-                                     const float* __restrict__ bns, const float* __restrict__ bnb, T* __restrict__ raw,
-                                     T* __restrict__ act, int B, int Ho, int Wo) {
+__global__ void __launch_bounds__(128) concat_preact_kernel(const T* __restrict__ s0, int C0, int up0,
+                                                            const T* __restrict__ s1, int C1,
+                                                            const float* __restrict__ bns,
+                                                            const float* __restrict__ bnb, T* __restrict__ raw,
+                                                            T* __restrict__ act, int Ho, int Wo) {
   const int C = C0 + C1;
-  const int C4 = C >> 2;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t total = (int64_t)B * Ho * Wo * C4;
-  if (idx >= total) return;
-  int c = (int)(idx % C4) * 4;
-  int64_t pix = idx / C4;
-  int wo = (int)(pix % Wo);
-  int64_t t = pix / Wo;
-  int ho = (int)(t % Ho);
-  int b = (int)(t / Ho);
-  float4 v;
-  if (c < C0) {
-    if (up0) {
-      const int Hi = Ho >> 1, Wi = Wo >> 1;
-      float sy = fmaxf((ho + 0.5f) * 0.5f - 0.5f, 0.f);
-      float sx = fmaxf((wo + 0.5f) * 0.5f - 0.5f, 0.f);
-      int y0 = (int)sy, x0 = (int)sx;
-      int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
-      float wy = sy - y0, wx = sx - x0;
-      const T* base = s0 + (int64_t)b * Hi * Wi * C0 + c;
-      float4 v00 = ActIO<T>::ld4(base + ((int64_t)y0 * Wi + x0) * C0);
-      float4 v01 = ActIO<T>::ld4(base + ((int64_t)y0 * Wi + x1) * C0);
-      float4 v10 = ActIO<T>::ld4(base + ((int64_t)y1 * Wi + x0) * C0);
-      float4 v11 = ActIO<T>::ld4(base + ((int64_t)y1 * Wi + x1) * C0);
-      // same association as ATen's upsample_bilinear2d: rows first, then columns
-      float w0y = 1.f - wy, w0x = 1.f - wx;
-      v.x = w0y * (w0x * v00.x + wx * v01.x) + wy * (w0x * v10.x + wx * v11.x);
-      v.y = w0y * (w0x * v00.y + wx * v01.y) + wy * (w0x * v10.y + wx * v11.y);
-      v.z = w0y * (w0x * v00.z + wx * v01.z) + wy * (w0x * v10.z + wx * v11.z);
-      v.w = w0y * (w0x * v00.w + wx * v01.w) + wy * (w0x * v10.w + wx * v11.w);
-    } else {
-      v = ActIO<T>::ld4(s0 + pix * C0 + c);
-    }
+  const unsigned pix = blockIdx.x;
+  const int wo = pix % Wo;
+  const unsigned t = pix / Wo;
+  const int ho = t % Ho;
+  const int b = t / Ho;
+  const T *p00 = nullptr, *p01 = nullptr, *p10 = nullptr, *p11 = nullptr;
+  float wy = 0.f, wx = 0.f;
+  if (up0) {
+    const int Hi = Ho >> 1, Wi = Wo >> 1;
+    const float sy = fmaxf((ho + 0.5f) * 0.5f - 0.5f, 0.f);
+    const float sx = fmaxf((wo + 0.5f) * 0.5f - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
+    wy = sy - y0;
+    wx = sx - x0;
+    const T* base = s0 + (size_t)b * Hi * Wi * C0;
+    p00 = base + ((size_t)y0 * Wi + x0) * C0;
+    p01 = base + ((size_t)y0 * Wi + x1) * C0;
+    p10 = base + ((size_t)y1 * Wi + x0) * C0;
+    p11 = base + ((size_t)y1 * Wi + x1) * C0;
   } else {
-    v = ActIO<T>::ld4(s1 + pix * C1 + (c - C0));
+    p00 = s0 + (size_t)pix * C0;
   }
-  if (raw) ActIO<T>::st4(raw + pix * C + c, v);
-  if (act) {
-    float4 s = __ldg(reinterpret_cast<const float4*>(bns + c));
-    float4 h = __ldg(reinterpret_cast<const float4*>(bnb + c));
-    if (raw && sizeof(T) == 2) {  // pre-activation must see the value the consumer of `raw` sees
-      v.x = __bfloat162float(__float2bfloat16_rn(v.x)); v.y = __bfloat162float(__float2bfloat16_rn(v.y));
-      v.z = __bfloat162float(__float2bfloat16_rn(v.z)); v.w = __bfloat162float(__float2bfloat16_rn(v.w));
+  const T* q = s1 ? s1 + (size_t)pix * C1 : nullptr;
+  const float w0y = 1.f - wy, w0x = 1.f - wx;
+  for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8) {
+    float v[8];
+    if (c < C0) {
+      if (up0) {
+        float a[8], bq[8], cc[8], d[8];
+        Vec8<T>::ld(p00 + c, a);
+        Vec8<T>::ld(p01 + c, bq);
+        Vec8<T>::ld(p10 + c, cc);
+        Vec8<T>::ld(p11 + c, d);
+        // same association as ATen's upsample_bilinear2d: columns inside rows
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = w0y * (w0x * a[i] + wx * bq[i]) + wy * (w0x * cc[i] + wx * d[i]);
+      } else {
+        Vec8<T>::ld(p00 + c, v);
+      }
+    } else {
+      Vec8<T>::ld(q + (c - C0), v);
     }
-    v.x = fmaxf(fmaf(v.x, s.x, h.x), 0.f);
-    v.y = fmaxf(fmaf(v.y, s.y, h.y), 0.f);
-    v.z = fmaxf(fmaf(v.z, s.z, h.z), 0.f);
-    v.w = fmaxf(fmaf(v.w, s.w, h.w), 0.f);
-    ActIO<T>::st4(act + pix * C + c, v);
+    if (raw) Vec8<T>::st(raw + (size_t)pix * C + c, v);
+    if (act) {
+      if (raw && sizeof(T) == 2) {  // pre-activation must see the value the consumer of `raw` sees
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+      }
+      const float4 sa = __ldg(reinterpret_cast<const float4*>(bns + c)), sb = __ldg(reinterpret_cast<const float4*>(bns + c) + 1);
+      const float4 ha = __ldg(reinterpret_cast<const float4*>(bnb + c)), hb = __ldg(reinterpret_cast<const float4*>(bnb + c) + 1);
+      v[0] = fmaxf(fmaf(v[0], sa.x, ha.x), 0.f); v[1] = fmaxf(fmaf(v[1], sa.y, ha.y), 0.f);
+      v[2] = fmaxf(fmaf(v[2], sa.z, ha.z), 0.f); v[3] = fmaxf(fmaf(v[3], sa.w, ha.w), 0.f);
+      v[4] = fmaxf(fmaf(v[4], sb.x, hb.x), 0.f); v[5] = fmaxf(fmaf(v[5], sb.y, hb.y), 0.f);
+      v[6] = fmaxf(fmaf(v[6], sb.z, hb.z), 0.f); v[7] = fmaxf(fmaf(v[7], sb.w, hb.w), 0.f);
+      Vec8<T>::st(act + (size_t)pix * C + c, v);
+    }
   }
 }
 
@@ -280,16 +331,16 @@ __global__ void attn_pool_kernel(const T* __restrict__ f, const float* __restric
 template <typename T>
 void launch_maxpool3x3s2(const T* x, T* y, int B, int H, int W, int C, cudaStream_t st) {
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  int64_t total = (int64_t)B * Ho * Wo * (C / 4);
+  int64_t total = (int64_t)B * Ho * Wo * (C / 8);
   maxpool_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(x, y, B, H, W, C, Ho, Wo);
 }
 
 template <typename T>
 void launch_concat_preact(const T* s0, int C0, int up0, const T* s1, int C1, const float* bns, const float* bnb, T* raw,
                           T* act, int B, int Ho, int Wo, cudaStream_t st) {
-  int64_t total = (int64_t)B * Ho * Wo * ((C0 + C1) / 4);
-  concat_preact_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(s0, C0, up0, s1, C1, bns, bnb, raw, act, B,
-                                                                          Ho, Wo);
+  const int C = C0 + C1;
+  const int threads = C >= 1024 ? 128 : (C >= 512 ? 64 : 32);
+  concat_preact_kernel<T><<<(unsigned)(B * Ho * Wo), threads, 0, st>>>(s0, C0, up0, s1, C1, bns, bnb, raw, act, Ho, Wo);
 }
 
 template <typename T>

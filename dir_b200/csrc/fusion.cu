@@ -23,6 +23,14 @@ struct BoneGeom {
   float ax, ay, bx, by, dx, dy;
 };
 
+// Conservative reject: a pixel centre farther than `distance` (+ slack for rounding) from the bone's bounding box
+// cannot pass the capsule test, which measures the distance to the segment. NaN geometry never rejects here.
+__device__ __forceinline__ bool bone_bbox_reject(const BoneGeom& g, float px, float py, float distance) {
+  const float m = distance + 0.01f;
+  return px < fminf(g.ax, g.bx) - m || px > fmaxf(g.ax, g.bx) + m || py < fminf(g.ay, g.by) - m ||
+         py > fmaxf(g.ay, g.by) + m;
+}
+
 // identical arithmetic to joint.cu::bone_weights (reference op order, no FMA contraction in the mask)
 __device__ __forceinline__ bool bone_weights(const BoneGeom& g, float px, float py, float distance, float& wa,
                                              float& wb) {
@@ -74,6 +82,9 @@ __global__ void pack_fusion_weight_kernel(const float* __restrict__ w, float* __
 // grid (40, 9, ceil(2B/64)), 256 threads (n); 64 rows (b,role) per CTA.
 __global__ void __launch_bounds__(256) bone_coef_kernel(const float* __restrict__ jf, const float* __restrict__ wp,
                                                         float* __restrict__ P, int B) {
+  extern __shared__ __align__(128) float dyn_smem[];  // weight stream: 2 x 32 x 128 floats + 2 mbarriers
+  WStream ws;
+  wstream_init(ws, dyn_smem, reinterpret_cast<uint64_t*>(dyn_smem + 2 * 32 * 128));
   __shared__ __align__(16) float xs[64][68];
   const int hb = blockIdx.x, tap = blockIdx.y, r0 = blockIdx.z * 64;
   const int hand = hb / 20, bone = hb % 20;
@@ -89,12 +100,15 @@ __global__ void __launch_bounds__(256) bone_coef_kernel(const float* __restrict_
     xs[r][c] = v;
   }
   __syncthreads();
-  // (rows x 64)·(64 x 256): 8 row groups x 64 column groups = 512 items, 2 per thread
-  const float* Bt = wp + ((int64_t)hb * 64 * 9 + tap) * 256;  // row c at Bt + c*9*256
-  smem_gemm<8>(&xs[0][0], 68, rows, 64, Bt, 9 * 256, 256, 256, [&](int r, int col, float v) {
-    int ri = r0 + r, b = ri >> 1, role = ri & 1;
-    P[((((int64_t)b * 40 + hb) * 2 + role) * 9 + tap) * 256 + col] = v;
-  });
+  // (rows x 64)·(64 x 256) as two 128-column blocks on the weight-streaming CTA GEMM (8 row groups x 32 col groups)
+  for (int cb = 0; cb < 256; cb += 128) {
+    const float* Bt = wp + ((int64_t)hb * 64 * 9 + tap) * 256 + cb;  // row c at Bt + c*9*256
+    cta_gemm<8>(&xs[0][0], 68, rows, 64, Bt, 9 * 256, 128, ws, [&](int, int r, int c0, float (&v)[4]) {
+      int ri = r0 + r, b = ri >> 1, role = ri & 1;
+      *reinterpret_cast<float4*>(P + ((((int64_t)b * 40 + hb) * 2 + role) * 9 + tap) * 256 + cb + c0) =
+          make_float4(v[0], v[1], v[2], v[3]);
+    });
+  }
 }
 
 struct Entry {
@@ -130,7 +144,8 @@ __global__ void __launch_bounds__(256) bone_fusion_kernel(const float* __restric
       int hb = t % 40, xs = (t / 40) % S, ky = t / (40 * S);
       int ys = y + ky - 1;
       float wa, wb;
-      if (ys >= 0 && ys < S) hit = bone_weights(geo[hb], xs + 0.5f, ys + 0.5f, distance, wa, wb);
+      if (ys >= 0 && ys < S && !bone_bbox_reject(geo[hb], xs + 0.5f, ys + 0.5f, distance))
+        hit = bone_weights(geo[hb], xs + 0.5f, ys + 0.5f, distance, wa, wb);
     }
     unsigned m = __ballot_sync(0xffffffffu, hit);
     if (lane == 0) counts[ck] = __popc(m);
@@ -161,7 +176,8 @@ __global__ void __launch_bounds__(256) bone_fusion_kernel(const float* __restric
     if (t < ntests) {
       int hb = t % 40, xs = (t / 40) % S, ky = t / (40 * S);
       int ys = y + ky - 1;
-      if (ys >= 0 && ys < S) hit = bone_weights(geo[hb], xs + 0.5f, ys + 0.5f, distance, wa, wb);
+      if (ys >= 0 && ys < S && !bone_bbox_reject(geo[hb], xs + 0.5f, ys + 0.5f, distance))
+        hit = bone_weights(geo[hb], xs + 0.5f, ys + 0.5f, distance, wa, wb);
       key = xs | (ky << 8) | (hb << 16);
     }
     unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -219,7 +235,12 @@ void launch_pack_fusion_weight(const float* w, float* wp, cudaStream_t st) {
 }
 
 void launch_bone_coef(const float* jf, const float* wp, float* P, int B, cudaStream_t st) {
-  bone_coef_kernel<<<dim3(40, 9, ceil_div(2 * B, 64)), 256, 0, st>>>(jf, wp, P, B);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(bone_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+  bone_coef_kernel<<<dim3(40, 9, ceil_div(2 * B, 64)), 256, 2 * 32 * 128 * 4 + 16, st>>>(jf, wp, P, B);
 }
 
 template <typename T>

@@ -17,6 +17,9 @@ constexpr int NJ = 21;
 // =================================================================== joint_embed
 template <typename T>
 __global__ void __launch_bounds__(128) joint_embed_kernel(EmbedArgs a) {
+  extern __shared__ __align__(128) float dyn_smem[];  // weight stream: 2 x 32 x 128 floats + 2 mbarriers
+  WStream ws;
+  wstream_init(ws, dyn_smem, reinterpret_cast<uint64_t*>(dyn_smem + 2 * 32 * 128));
   __shared__ __align__(16) float samp[NJ][256];
   __shared__ __align__(16) float hid[NJ][128];
   __shared__ float xyz[NJ][3];
@@ -54,36 +57,22 @@ __global__ void __launch_bounds__(128) joint_embed_kernel(EmbedArgs a) {
   }
   __syncthreads();
 
-  // Three chained (21 x K)·(K x 128) products on the register-tiled CUDA-core GEMM: 3 row groups of 7 joints
-  // x 32 column groups = 96 work items (threads 96..127 only help with loads).
-  const bool worker = n < 96;
-  const int cg = n & 31, rg = n >> 5;
+  // Three chained (21 x K)·(K x 128) products on the weight-streaming CTA GEMM: 3 row groups of 7 joints x 32
+  // column groups = 96 register tiles.
   float outv[7][4];
-  float acc[7][4];
   {  // ---- filters: 256 -> 128 (BN, ReLU) -> 128
     const PointMlp& f = a.filters[hand];
-    if (worker) {
-      smem_gemm_item<7>(&samp[0][0], 256, NJ, 256, f.w1t, 128, cg, rg, acc);
-      const float4 s1 = __ldg(reinterpret_cast<const float4*>(f.s1 + cg * 4));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(f.b1 + cg * 4));
-#pragma unroll
-      for (int r = 0; r < 7; ++r) {
-        float4 h = make_float4(fmaxf(fmaf(acc[r][0], s1.x, b1.x), 0.f), fmaxf(fmaf(acc[r][1], s1.y, b1.y), 0.f),
-                               fmaxf(fmaf(acc[r][2], s1.z, b1.z), 0.f), fmaxf(fmaf(acc[r][3], s1.w, b1.w), 0.f));
-        *reinterpret_cast<float4*>(&hid[rg * 7 + r][cg * 4]) = h;
-      }
-    }
-    __syncthreads();
-    if (worker) {
-      smem_gemm_item<7>(&hid[0][0], 128, NJ, 128, f.w2t, 128, cg, rg, acc);
-      const float4 b2 = __ldg(reinterpret_cast<const float4*>(f.b2 + cg * 4));
-#pragma unroll
-      for (int r = 0; r < 7; ++r) {
-        outv[r][0] = acc[r][0] + b2.x; outv[r][1] = acc[r][1] + b2.y;
-        outv[r][2] = acc[r][2] + b2.z; outv[r][3] = acc[r][3] + b2.w;
-      }
-    }
-    __syncthreads();
+    cta_gemm<7>(&samp[0][0], 256, NJ, 256, f.w1t, 128, 128, ws, [&](int, int row, int c0, float (&v)[4]) {
+      const float4 s1 = __ldg(reinterpret_cast<const float4*>(f.s1 + c0));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(f.b1 + c0));
+      *reinterpret_cast<float4*>(&hid[row][c0]) =
+          make_float4(fmaxf(fmaf(v[0], s1.x, b1.x), 0.f), fmaxf(fmaf(v[1], s1.y, b1.y), 0.f),
+                      fmaxf(fmaf(v[2], s1.z, b1.z), 0.f), fmaxf(fmaf(v[3], s1.w, b1.w), 0.f));
+    });
+    cta_gemm<7>(&hid[0][0], 128, NJ, 128, f.w2t, 128, 128, ws, [&](int r, int, int c0, float (&v)[4]) {
+      const float4 b2 = __ldg(reinterpret_cast<const float4*>(f.b2 + c0));
+      outv[r][0] = v[0] + b2.x; outv[r][1] = v[1] + b2.y; outv[r][2] = v[2] + b2.z; outv[r][3] = v[3] + b2.w;
+    });
   }
   {  // ---- pos_emb: 3 -> 128 (BN, ReLU) -> 128
     const PointMlp& f = a.pos[hand];
@@ -95,17 +84,13 @@ __global__ void __launch_bounds__(128) joint_embed_kernel(EmbedArgs a) {
       hid[j][n] = fmaxf(fmaf(h, s1, b1), 0.f);
     }
     __syncthreads();
-    if (worker) {
-      smem_gemm_item<7>(&hid[0][0], 128, NJ, 128, f.w2t, 128, cg, rg, acc);
-      const float4 b2 = __ldg(reinterpret_cast<const float4*>(f.b2 + cg * 4));
-      float* out = a.out + ((int64_t)(b * 2 + hand) * NJ) * 128 + cg * 4;
-#pragma unroll
-      for (int r = 0; r < 7; ++r) {
-        float4 o = make_float4(outv[r][0] + (acc[r][0] + b2.x), outv[r][1] + (acc[r][1] + b2.y),
-                               outv[r][2] + (acc[r][2] + b2.z), outv[r][3] + (acc[r][3] + b2.w));
-        *reinterpret_cast<float4*>(out + (rg * 7 + r) * 128) = o;
-      }
-    }
+    float* out = a.out + ((int64_t)(b * 2 + hand) * NJ) * 128;
+    cta_gemm<7>(&hid[0][0], 128, NJ, 128, f.w2t, 128, 128, ws, [&](int r, int row, int c0, float (&v)[4]) {
+      const float4 b2 = __ldg(reinterpret_cast<const float4*>(f.b2 + c0));
+      *reinterpret_cast<float4*>(out + row * 128 + c0) =
+          make_float4(outv[r][0] + (v[0] + b2.x), outv[r][1] + (v[1] + b2.y), outv[r][2] + (v[2] + b2.z),
+                      outv[r][3] + (v[3] + b2.w));
+    });
   }
 }
 
@@ -115,13 +100,16 @@ constexpr int GBT = 32;  // images per CTA
 // One CTA per (output joint i, hand, 32-image tile); 256 threads = 8 row groups (4 images) x 32 column groups.
 // out = relu(bn( x_i W0[i] + sum_j A1[i][j] x_j W1[j] + bias )) (+ global_pos_emb on the last layer).
 __global__ void __launch_bounds__(256) gcn_layer_kernel(GcnLayerArgs a) {
+  extern __shared__ __align__(128) float dyn_smem[];  // weight stream: 2 x 32 x 128 floats + 2 mbarriers
+  WStream ws;
+  wstream_init(ws, dyn_smem, reinterpret_cast<uint64_t*>(dyn_smem + 2 * 32 * 128));
   __shared__ __align__(16) float xs[GBT][128];
   const int i = blockIdx.x, hand = blockIdx.y, b0 = blockIdx.z * GBT, tid = threadIdx.x;
   const int cg = tid & 31, rg = tid >> 5;
   const int nb = min(GBT, a.B - b0);
   const float* W = a.W[hand];
   const float* A1 = a.A1[hand];
-  float tot[4][4], acc[4][4];
+  float tot[4][4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) tot[r][0] = tot[r][1] = tot[r][2] = tot[r][3] = 0.f;
 
@@ -140,8 +128,7 @@ __global__ void __launch_bounds__(256) gcn_layer_kernel(GcnLayerArgs a) {
       j = src;
       Wsrc = W + (int64_t)(NJ + src) * 128 * 128;
     }
-    __syncthreads();
-    for (int e = tid; e < GBT * 32; e += 256) {
+    for (int e = tid; e < GBT * 32; e += 256) {  // (previous readers of xs are behind cta_gemm's last barrier)
       int bb = e >> 5, c4 = e & 31;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (bb < nb)
@@ -149,11 +136,10 @@ __global__ void __launch_bounds__(256) gcn_layer_kernel(GcnLayerArgs a) {
       *reinterpret_cast<float4*>(&xs[bb][c4 * 4]) = v;
     }
     __syncthreads();
-    smem_gemm_item<4>(&xs[0][0], 128, GBT, 128, Wsrc, 128, cg, rg, acc);
+    cta_gemm<4>(&xs[0][0], 128, GBT, 128, Wsrc, 128, 128, ws, [&](int r, int, int, float (&v)[4]) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) tot[r][q] = fmaf(aw, acc[r][q], tot[r][q]);
+      for (int q = 0; q < 4; ++q) tot[r][q] = fmaf(aw, v[q], tot[r][q]);
+    });
   }
   {
     const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale[hand] + cg * 4));
@@ -167,7 +153,6 @@ __global__ void __launch_bounds__(256) gcn_layer_kernel(GcnLayerArgs a) {
     }
   }
   if (a.add_global) {  // + global_pos_emb(xyz/0.15 -/+ offset/2)   (models/dir.py:106-110)
-    __syncthreads();
     const PointMlp& g = a.gpos;
     const float sgn = hand == 0 ? -1.f : 1.f;
     for (int e = tid; e < GBT * 128; e += 256) {
@@ -185,13 +170,10 @@ __global__ void __launch_bounds__(256) gcn_layer_kernel(GcnLayerArgs a) {
       xs[bb][k] = h;
     }
     __syncthreads();
-    smem_gemm_item<4>(&xs[0][0], 128, GBT, 128, g.w2t, 128, cg, rg, acc);
     const float4 b2 = __ldg(reinterpret_cast<const float4*>(g.b2 + cg * 4));
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      tot[r][0] += acc[r][0] + b2.x; tot[r][1] += acc[r][1] + b2.y;
-      tot[r][2] += acc[r][2] + b2.z; tot[r][3] += acc[r][3] + b2.w;
-    }
+    cta_gemm<4>(&xs[0][0], 128, GBT, 128, g.w2t, 128, 128, ws, [&](int r, int, int, float (&v)[4]) {
+      tot[r][0] += v[0] + b2.x; tot[r][1] += v[1] + b2.y; tot[r][2] += v[2] + b2.z; tot[r][3] += v[3] + b2.w;
+    });
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -206,21 +188,33 @@ __global__ void __launch_bounds__(256) gcn_layer_kernel(GcnLayerArgs a) {
 constexpr int NT = 42;
 constexpr int STE_THREADS = 256;
 constexpr int SC_LD = 44;
-constexpr int STE_SMEM_FLOATS = NT * 128 * 2 + NT * 384 + 4 * NT * SC_LD;
+constexpr int STE_SMEM_FLOATS = 2 * 32 * 128 + NT * 128 * 2 + NT * 384 + 4 * NT * SC_LD + 4;
 
 // out[r][n] = sum_k in[r][k] * Wt[k][n] + bias[n]; optional GELU; optional residual accumulate into out.
-// 42 token rows = 6 row groups of 7 on the register-tiled GEMM.
+// 42 token rows = 7 row groups of 6; N is walked in 128-column blocks on the weight-streaming CTA GEMM.
 template <int MODE>  // 0: store, 1: store GELU, 2: out += result
 __device__ __forceinline__ void ste_linear(const float* __restrict__ in, int ldin, int K, const float* __restrict__ Wt,
-                                           const float* __restrict__ bias, int N, float* __restrict__ out, int ldout) {
-  smem_gemm<7>(in, ldin, NT, K, Wt, N, N, STE_THREADS, [&](int r, int n, float v) {
-    v += __ldg(bias + n);
-    if (MODE == 1) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-    if (MODE == 2)
-      out[r * ldout + n] += v;
-    else
-      out[r * ldout + n] = v;
-  });
+                                           const float* __restrict__ bias, int N, float* __restrict__ out, int ldout,
+                                           WStream& ws) {
+  for (int cb = 0; cb < N; cb += 128) {
+    const int NC = min(128, N - cb);
+    cta_gemm<6>(in, ldin, NT, K, Wt + cb, N, NC, ws, [&](int, int row, int c0, float (&v)[4]) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + cb + c0));
+      float4 o = make_float4(v[0] + bb.x, v[1] + bb.y, v[2] + bb.z, v[3] + bb.w);
+      if (MODE == 1) {
+        o.x = 0.5f * o.x * (1.f + erff(o.x * 0.70710678118654752440f));
+        o.y = 0.5f * o.y * (1.f + erff(o.y * 0.70710678118654752440f));
+        o.z = 0.5f * o.z * (1.f + erff(o.z * 0.70710678118654752440f));
+        o.w = 0.5f * o.w * (1.f + erff(o.w * 0.70710678118654752440f));
+      }
+      float4* po = reinterpret_cast<float4*>(out + row * ldout + cb + c0);
+      if (MODE == 2) {
+        const float4 p = *po;
+        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+      }
+      *po = o;
+    });
+  }
 }
 
 // LayerNorm over 128 channels, one warp per row (two-pass like ATen)
@@ -242,11 +236,13 @@ __device__ __forceinline__ void ste_layernorm(const float* __restrict__ in, floa
 
 __global__ void __launch_bounds__(STE_THREADS) ste_kernel(const float* __restrict__ xin, float* __restrict__ yout,
                                                           SteWeights w) {
-  extern __shared__ __align__(16) float sm[];
-  float* x = sm;                   // [42][128] residual stream
+  extern __shared__ __align__(128) float sm[];
+  float* x = sm + 2 * 32 * 128;    // [42][128] residual stream (after the 32 KB weight-stream buffers)
   float* h = x + NT * 128;         // [42][128] LN output / attention output
   float* big = h + NT * 128;       // [42][384] qkv, later [42][256] MLP hidden
   float* sc = big + NT * 384;      // [4][42][44] attention probabilities
+  WStream ws;
+  wstream_init(ws, sm, reinterpret_cast<uint64_t*>(sc + 4 * NT * SC_LD));
   const int b = blockIdx.x, tid = threadIdx.x;
   for (int i = tid; i < NT * 128; i += STE_THREADS) x[i] = xin[(int64_t)b * NT * 128 + i] + w.pos[i];
   __syncthreads();
@@ -254,7 +250,7 @@ __global__ void __launch_bounds__(STE_THREADS) ste_kernel(const float* __restric
     const SteWeights::Block& B = w.blk[l];
     ste_layernorm(x, h, B.n1w, B.n1b, 1e-6f);
     __syncthreads();
-    ste_linear<0>(h, 128, 128, B.qkv_t, B.qkv_b, 384, big, 384);
+    ste_linear<0>(h, 128, 128, B.qkv_t, B.qkv_b, 384, big, 384, ws);
     __syncthreads();
     // scores = q k^T * 32^-0.5
     for (int item = tid; item < 4 * NT * NT; item += STE_THREADS) {
@@ -297,20 +293,20 @@ __global__ void __launch_bounds__(STE_THREADS) ste_kernel(const float* __restric
       h[item] = s;
     }
     __syncthreads();
-    ste_linear<2>(h, 128, 128, B.proj_t, B.proj_b, 128, x, 128);
+    ste_linear<2>(h, 128, 128, B.proj_t, B.proj_b, 128, x, 128, ws);
     __syncthreads();
     ste_layernorm(x, h, B.n2w, B.n2b, 1e-6f);
     __syncthreads();
-    ste_linear<1>(h, 128, 128, B.fc1_t, B.fc1_b, 256, big, 256);
+    ste_linear<1>(h, 128, 128, B.fc1_t, B.fc1_b, 256, big, 256, ws);
     __syncthreads();
-    ste_linear<2>(big, 256, 256, B.fc2_t, B.fc2_b, 128, x, 128);
+    ste_linear<2>(big, 256, 256, B.fc2_t, B.fc2_b, 128, x, 128, ws);
     __syncthreads();
     ste_layernorm(x, x, w.snw, w.snb, 1e-6f);  // shared spatial_norm (mixSTE.py:200), in place (row-local)
     __syncthreads();
   }
   ste_layernorm(x, h, w.hnw, w.hnb, 1e-5f);
   __syncthreads();
-  ste_linear<0>(h, 128, 128, w.head_t, w.head_b, 64, big, 64);
+  ste_linear<0>(h, 128, 128, w.head_t, w.head_b, 64, big, 64, ws);
   __syncthreads();
   for (int i = tid; i < NT * 64; i += STE_THREADS) yout[(int64_t)b * NT * 64 + i] = big[i];
 }
@@ -432,13 +428,23 @@ __global__ void __launch_bounds__(256) bone_vis_kernel(const float* __restrict__
 
 template <typename T>
 void launch_joint_embed(const EmbedArgs& a, cudaStream_t st) {
-  joint_embed_kernel<T><<<dim3(a.B, 2), 128, 0, st>>>(a);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(joint_embed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+  joint_embed_kernel<T><<<dim3(a.B, 2), 128, 2 * 32 * 128 * 4 + 16, st>>>(a);
 }
 template void launch_joint_embed<float>(const EmbedArgs&, cudaStream_t);
 template void launch_joint_embed<__nv_bfloat16>(const EmbedArgs&, cudaStream_t);
 
 void launch_gcn_layer(const GcnLayerArgs& a, cudaStream_t st) {
-  gcn_layer_kernel<<<dim3(NJ, 2, ceil_div(a.B, GBT)), 256, 0, st>>>(a);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gcn_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+  gcn_layer_kernel<<<dim3(NJ, 2, ceil_div(a.B, GBT)), 256, 2 * 32 * 128 * 4 + 16, st>>>(a);
 }
 
 void launch_ste(const float* x, float* y, const SteWeights& w, int B, cudaStream_t st) {

@@ -117,12 +117,30 @@ __device__ void mano_forward(ManoSmem& s, const ManoWeights& w, float* __restric
     }
   }
   __syncthreads();
-  // 5. v_posed = v_shaped + posedirs . pose_map (manolayer.py:180-181); each thread owns its elements of vs
-  for (int i = tid; i < NV3; i += THREADS) {
-    float v = 0.f;
-#pragma unroll 9
-    for (int k = 0; k < 135; ++k) v = fmaf(__ldg(w.posedirs_t + k * NV3 + i), s.pose_map[k], v);
-    s.vs[i] += v;
+  // 5. v_posed = v_shaped + posedirs . pose_map (manolayer.py:180-181); each thread owns elements tid + 256*e of vs.
+  //    The 1.26 MB posedirs matrix streams from L2: 10 independent accumulators x 3 k-steps = 30 loads in flight.
+  {
+    constexpr int NE = (NV3 + THREADS - 1) / THREADS;  // 10
+    float pv[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) pv[e] = 0.f;
+    const float* pd = w.posedirs_t + tid;
+    for (int k = 0; k < 135; k += 3) {
+      const float m0 = s.pose_map[k], m1 = s.pose_map[k + 1], m2 = s.pose_map[k + 2];
+      float l0[NE], l1[NE], l2[NE];
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const bool ok = tid + e * THREADS < NV3;
+        l0[e] = ok ? __ldg(pd + (size_t)k * NV3 + e * THREADS) : 0.f;
+        l1[e] = ok ? __ldg(pd + (size_t)(k + 1) * NV3 + e * THREADS) : 0.f;
+        l2[e] = ok ? __ldg(pd + (size_t)(k + 2) * NV3 + e * THREADS) : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < NE; ++e) pv[e] = fmaf(l2[e], m2, fmaf(l1[e], m1, fmaf(l0[e], m0, pv[e])));
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (tid + e * THREADS < NV3) s.vs[tid + e * THREADS] += pv[e];
   }
   // 6. forward kinematics: root, then one thread per finger chain (manolayer.py:186-227)
   if (tid < 5) {
