@@ -21,13 +21,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GF_PER_IMAGE = 36.80  # dense-contraction GFLOP per image, ResNet-50, 3 stages, incl. heads (measured)
-FUSION_LAYER = "decoder.projecter_3.fusion.0"  # largest single op: conv3x3 2560->256 @32x32 (12.2 GF/img)
+# dominant kernel = largest single launch of the step: the two InitRegressor attention convs, run as one
+# conv3x3 2048->2048 @8x8 (models/dir.py:227-241), 4.83 GFLOP/img, on conv_tc_kernel<256,128>
+DOMINANT_LAYER = "init_regressor.attention_left.0"
+DOMINANT_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="images per GPU per step")
@@ -200,7 +203,7 @@ def main():
     if sampler:
         sampler.start()
     if not args.cuda_graph:
-        h.profile_layer(FUSION_LAYER)
+        h.profile_layer(DOMINANT_LAYER)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
@@ -263,10 +266,16 @@ def main():
     roof = None
     if prof_n:
         ach = prof_flops / (prof_ms / 1000.0) / 1e12
-        roof = {"bound": "tensor", "kernel": f"conv_tc_kernel<256> ({FUSION_LAYER}: conv3x3 2560->256 @32x32, "
-                                             f"{prof_flops / prof_n / 1e9:.1f} GFLOP/launch algorithmic)",
+        traffic = None
+        if os.path.exists(DOMINANT_TRAFFIC_FILE):  # dram__bytes_read+write per launch from one ncu --set full capture
+            with open(DOMINANT_TRAFFIC_FILE) as f:
+                t = json.load(f)
+            if t.get("batch") == B and t.get("precision") == args.precision:
+                traffic = t.get("dram_bytes_per_launch")
+        roof = {"bound": "tensor", "kernel": f"conv_tc_kernel<256,128> ({DOMINANT_LAYER}: conv3x3 2048->2x1024 @8x8, "
+                                             f"{prof_flops / prof_n / 1e9:.1f} GFLOP/launch algorithmic = 2*M*N*K)",
                 "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                "traffic": None, "peak_source": pk["source"], "launches_timed": prof_n,
+                "traffic": traffic, "peak_source": pk["source"], "launches_timed": prof_n,
                 "avg_launch_ms": prof_ms / prof_n, "share_of_step": prof_ms / ms}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -560,6 +560,8 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
   const int S = sw.S;
   float* jf0 = aalloc<float>(ar, (int64_t)B * 42 * 128);
   float* jf1 = aalloc<float>(ar, (int64_t)B * 42 * 128);
+  float* gh0 = aalloc<float>(ar, (int64_t)2 * B * 42 * 128);
+  float* gh1 = aalloc<float>(ar, (int64_t)2 * B * 42 * 128);
   float* tok = aalloc<float>(ar, (int64_t)B * 42 * 64);
   float* jfeat = aalloc<float>(ar, (int64_t)B * 42 * 64);
   T* bone = dense_fusion ? aalloc<T>(ar, (int64_t)B * S * S * 2560) : nullptr;
@@ -581,25 +583,40 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
   e.out = jf0;
   e.B = B;
   launch_joint_embed<T>(e, st);
-  float *gin = jf0, *gout = jf1;
-  for (int l = 0; l < 4; ++l) {
-    GcnLayerArgs g{};
-    g.x = gin;
-    g.y = gout;
+  auto agg_of = [&](int l) {
+    GcnAgg g{};
     for (int h = 0; h < 2; ++h) {
-      g.W[h] = sw.gcn[l].W[h];
       g.A1[h] = sw.gcn[l].A1[h];
       g.scale[h] = sw.gcn[l].scale[h];
       g.shift[h] = sw.gcn[l].shift[h];
     }
-    g.add_global = (l == 3);
-    g.gpos = sw.gpos;
-    g.prev_record = prev_rec;
-    g.rec_stride = prev_stride;
+    return g;
+  };
+  float *hin = nullptr, *hout = gh0;
+  for (int l = 0; l < 4; ++l) {
+    GcnGemmArgs g{};
+    g.x = l == 0 ? jf0 : nullptr;
+    g.hin = hin;
+    if (l > 0) g.agg = agg_of(l - 1);
+    g.hout = hout;
+    for (int h = 0; h < 2; ++h) g.W[h] = sw.gcn[l].W[h];
     g.B = B;
-    launch_gcn_layer(g, st);
-    std::swap(gin, gout);
+    launch_gcn_gemm(g, st);
+    hin = hout;
+    hout = (hout == gh0) ? gh1 : gh0;
   }
+  {
+    GcnFinishArgs f{};
+    f.hin = hin;
+    f.agg = agg_of(3);
+    f.gpos = sw.gpos;
+    f.prev_record = prev_rec;
+    f.rec_stride = prev_stride;
+    f.y = jf1;
+    f.B = B;
+    launch_gcn_finish(f, st);
+  }
+  float* gin = jf1;
   launch_ste(gin, tok, sw.ste, B, st);
   RegressArgs a{};
   for (int h = 0; h < 2; ++h) {
@@ -622,7 +639,7 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
   a.joint_feat = jfeat;
   a.B = B;
   launch_regress_mano(a, st);
-  launches += 7;
+  launches += 8;
   if (dense_fusion) {
     launch_bone_raster<T>(stage_rec, rec_stride, jfeat, bone, B, S, sw.distance, st);
     ++launches;

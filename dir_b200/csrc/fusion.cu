@@ -112,20 +112,23 @@ __global__ void __launch_bounds__(256) bone_coef_kernel(const float* __restrict_
 }
 
 struct Entry {
-  int key;  // xs | ky << 8 | hb << 16
+  int key;  // xs | (ky*40 + hb) << 8
   float wa, wb;
 };
 
 // One CTA per (image, output row). 256 threads = 256 output channels.
-template <typename T>
+template <typename T, int S>
 __global__ void __launch_bounds__(256) bone_fusion_kernel(const float* __restrict__ rec, int rec_stride,
                                                           const float* __restrict__ P, const float* __restrict__ scale,
-                                                          const float* __restrict__ shift, T* __restrict__ out, int S,
+                                                          const float* __restrict__ shift, T* __restrict__ out,
                                                           float distance) {
+  constexpr int LOG2S = S == 32 ? 5 : 4;
+  static_assert(S == 16 || S == 32, "feature map sizes of projecter_4 / projecter_3 (models/dir.py:395,401)");
   extern __shared__ __align__(16) uint8_t smraw[];
   float* s_out = reinterpret_cast<float*>(smraw);                  // [S][256]
   Entry* list = reinterpret_cast<Entry*>(s_out + S * 256);         // [3*S*40]
   int* counts = reinterpret_cast<int*>(list + 3 * S * 40);         // [nchunks + 1]
+  int* gstart = counts + (3 * S * 40 + 31) / 32 + 1;                // [<= 121] run starts of (ky, bone) groups
   __shared__ BoneGeom geo[40];
   __shared__ float uv[84];
   const int b = blockIdx.x, y = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -135,13 +138,14 @@ __global__ void __launch_bounds__(256) bone_fusion_kernel(const float* __restric
   if (tid < 40) geo[tid] = make_bone(uv + (tid / 20) * 42, tid % 20, S);
   __syncthreads();
   // ---- deterministic compaction of the non-zero (source pixel, bone) pairs of rows y-1, y, y+1
-  // test index t = (ky*S + xs)*40 + hb, processed in chunks of 32 (one warp-ballot each)
+  // test index t = (ky*40 + hb)*S + xs (bone-major inside a source row, so one bone's pixels are consecutive and
+  // share their 6 coefficient vectors), processed in chunks of 32 (one warp-ballot each)
   const int ntests = 3 * S * 40, nchunks = (ntests + 31) / 32;
   for (int ck = warp; ck < nchunks; ck += 8) {
     int t = ck * 32 + lane;
     bool hit = false;
     if (t < ntests) {
-      int hb = t % 40, xs = (t / 40) % S, ky = t / (40 * S);
+      int xs = t & (S - 1), g = t >> LOG2S, ky = g / 40, hb = g - ky * 40;
       int ys = y + ky - 1;
       float wa, wb;
       if (ys >= 0 && ys < S && !bone_bbox_reject(geo[hb], xs + 0.5f, ys + 0.5f, distance))
@@ -174,11 +178,11 @@ __global__ void __launch_bounds__(256) bone_fusion_kernel(const float* __restric
     float wa = 0.f, wb = 0.f;
     int key = 0;
     if (t < ntests) {
-      int hb = t % 40, xs = (t / 40) % S, ky = t / (40 * S);
+      int xs = t & (S - 1), g = t >> LOG2S, ky = g / 40, hb = g - ky * 40;
       int ys = y + ky - 1;
       if (ys >= 0 && ys < S && !bone_bbox_reject(geo[hb], xs + 0.5f, ys + 0.5f, distance))
         hit = bone_weights(geo[hb], xs + 0.5f, ys + 0.5f, distance, wa, wb);
-      key = xs | (ky << 8) | (hb << 16);
+      key = xs | (g << 8);
     }
     unsigned m = __ballot_sync(0xffffffffu, hit);
     if (hit) {
@@ -191,36 +195,76 @@ __global__ void __launch_bounds__(256) bone_fusion_kernel(const float* __restric
   __syncthreads();
   // ---- accumulate: thread n owns column n of s_out (no conflicts, fixed order => bit-reproducible)
   const int n = tid, nent = counts[nchunks];
+  __syncthreads();  // everyone has read nent before counts[nchunks] is reused for the group count
   const float* Pb = P + (int64_t)b * 40 * 2 * 9 * 256 + n;
-  for (int e0 = 0; e0 < nent; e0 += 4) {  // 4 entries = up to 24 independent L2 loads in flight per thread
-    float va[4][3], vb[4][3], wa[4], wb[4];
-    int xs4[4];
+  // Entries arrive grouped by (ky, bone) with ascending xs. Group table (start index of every (ky, bone) run):
+  if (warp == 0) {
+    int count = 0;
+    for (int base = 0; base < nent; base += 32) {
+      const int e = base + lane;
+      const bool flag = e < nent && (e == 0 || (list[e].key >> 8) != (list[e - 1].key >> 8));
+      const unsigned m = __ballot_sync(0xffffffffu, flag);
+      if (flag) gstart[count + __popc(m & ((1u << lane) - 1))] = e;
+      count += __popc(m);
+    }
+    if (lane == 0) {
+      gstart[count] = nent;
+      counts[nchunks] = count;  // number of groups (nent is gstart[count])
+    }
+  }
+  __syncthreads();
+  const int ngroups = counts[nchunks];
+  // Four groups at a time: their 24 coefficient loads (L2) are issued together, then a 3-wide register window
+  // (outputs xs-1, xs, xs+1) slides along each bone's pixels so shared memory is touched about once per pixel.
+  for (int g0 = 0; g0 < ngroups; g0 += 4) {
+    float pa[4][3], pb[4][3];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int e = min(e0 + u, nent - 1);
-      const Entry en = list[e];
-      const int ky = (en.key >> 8) & 0xff, hb = en.key >> 16;
-      xs4[u] = (e0 + u < nent) ? (en.key & 0xff) : -100;
-      wa[u] = en.wa;
-      wb[u] = en.wb;
+      const int gi = min(g0 + u, ngroups - 1);
+      const int g = list[gstart[gi]].key >> 8;
+      const int ky = g / 40, hb = g - ky * 40;
       // source pixel (ys, xs) feeds output (y, xs - kx + 1) through tap (ky, kx), ky = ys - y + 1
-      const float* pa = Pb + ((int64_t)(hb * 2 + 0) * 9 + ky * 3) * 256;
-      const float* pb = Pb + ((int64_t)(hb * 2 + 1) * 9 + ky * 3) * 256;
+      const float* qa = Pb + ((int64_t)(hb * 2 + 0) * 9 + ky * 3) * 256;
+      const float* qb = Pb + ((int64_t)(hb * 2 + 1) * 9 + ky * 3) * 256;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        va[u][kx] = __ldg(pa + kx * 256);
-        vb[u][kx] = __ldg(pb + kx * 256);
+        pa[u][kx] = __ldg(qa + kx * 256);
+        pb[u][kx] = __ldg(qb + kx * 256);
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int x = xs4[u] - kx + 1;
-        if (x >= 0 && x < S) s_out[x * 256 + n] += fmaf(wa[u], va[u][kx], wb[u] * vb[u][kx]);
+      if (g0 + u >= ngroups) break;
+      const int e0 = gstart[g0 + u], e1 = gstart[g0 + u + 1];
+      int last_xs = -100;
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+      for (int e = e0; e < e1; ++e) {
+        const Entry en = list[e];
+        const int xs = en.key & 0xff;
+        if (xs == last_xs + 1) {  // slide by one pixel: retire the left output
+          if (last_xs - 1 >= 0) s_out[(last_xs - 1) * 256 + n] += w0;
+          w0 = w1;
+          w1 = w2;
+          w2 = 0.f;
+        } else if (last_xs >= 0) {  // gap: flush the whole window
+          if (last_xs - 1 >= 0) s_out[(last_xs - 1) * 256 + n] += w0;
+          s_out[last_xs * 256 + n] += w1;
+          if (last_xs + 1 < S) s_out[(last_xs + 1) * 256 + n] += w2;
+          w0 = w1 = w2 = 0.f;
+        }
+        last_xs = xs;
+        w0 += fmaf(en.wa, pa[u][2], en.wb * pb[u][2]);  // kx = 2 -> x = xs - 1
+        w1 += fmaf(en.wa, pa[u][1], en.wb * pb[u][1]);  // kx = 1 -> x = xs
+        w2 += fmaf(en.wa, pa[u][0], en.wb * pb[u][0]);  // kx = 0 -> x = xs + 1
+      }
+      if (last_xs >= 0) {
+        if (last_xs - 1 >= 0) s_out[(last_xs - 1) * 256 + n] += w0;
+        s_out[last_xs * 256 + n] += w1;
+        if (last_xs + 1 < S) s_out[(last_xs + 1) * 256 + n] += w2;
       }
     }
   }
+  __syncthreads();
   // ---- BN + ReLU epilogue, NHWC store (256 consecutive channels per pixel: fully coalesced)
   const float sc = scale[n], sh = shift[n];
   T* orow = out + ((int64_t)b * S + y) * S * 256 + n;
@@ -247,14 +291,18 @@ template <typename T>
 void launch_bone_fusion(const float* rec, int rec_stride, const float* P, const float* scale, const float* shift, T* out,
                         int B, int S, float distance, cudaStream_t st) {
   const int nchunks = (3 * S * 40 + 31) / 32;
-  const size_t smem = (size_t)S * 256 * 4 + (size_t)3 * S * 40 * sizeof(Entry) + (nchunks + 1) * 4;
-  static bool attr[2] = {false, false};
-  const int ti = sizeof(T) == 4 ? 0 : 1;
-  if (!attr[ti]) {
-    cudaFuncSetAttribute(bone_fusion_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr[ti] = true;
+  const size_t smem = (size_t)S * 256 * 4 + (size_t)3 * S * 40 * sizeof(Entry) + (nchunks + 1) * 4 + 128 * 4;
+  static bool attr[2][2] = {{false, false}, {false, false}};
+  const int ti = sizeof(T) == 4 ? 0 : 1, si = S == 32 ? 1 : 0;
+  if (S == 32) {
+    if (!attr[ti][si]) cudaFuncSetAttribute(bone_fusion_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr[ti][si] = true;
+    bone_fusion_kernel<T, 32><<<dim3(B, S), 256, smem, st>>>(rec, rec_stride, P, scale, shift, out, distance);
+  } else {
+    if (!attr[ti][si]) cudaFuncSetAttribute(bone_fusion_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr[ti][si] = true;
+    bone_fusion_kernel<T, 16><<<dim3(B, S), 256, smem, st>>>(rec, rec_stride, P, scale, shift, out, distance);
   }
-  bone_fusion_kernel<T><<<dim3(B, S), 256, smem, st>>>(rec, rec_stride, P, scale, shift, out, S, distance);
 }
 template void launch_bone_fusion<float>(const float*, int, const float*, const float*, const float*, float*, int, int,
                                         float, cudaStream_t);

@@ -94,94 +94,87 @@ __global__ void __launch_bounds__(128) joint_embed_kernel(EmbedArgs a) {
   }
 }
 
-// =================================================================== gcn_layer
+// =================================================================== SemGCN (see kernels.h: GcnGemmArgs)
 constexpr int GBT = 32;  // images per CTA
 
-// One CTA per (output joint i, hand, 32-image tile); 256 threads = 8 row groups (4 images) x 32 column groups.
-// out = relu(bn( x_i W0[i] + sum_j A1[i][j] x_j W1[j] + bias )) (+ global_pos_emb on the last layer).
-__global__ void __launch_bounds__(256) gcn_layer_kernel(GcnLayerArgs a) {
+// value of the aggregated + normalised layer output X'[b][hand][i][c4*4 .. +3]
+__device__ __forceinline__ float4 gcn_aggregate(const float* __restrict__ hin, const GcnAgg& g, int B, int b, int hand,
+                                                int i, int c4) {
+  const size_t plane = (size_t)B * 2 * NJ * 128;  // H1 offset
+  const float* base = hin + ((size_t)(b * 2 + hand) * NJ) * 128 + c4 * 4;
+  float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)i * 128));
+  const float* A1 = g.A1[hand] + i * NJ;
+  for (int j = 0; j < NJ; ++j) {  // ascending j, like the dense A1 @ h1 of the reference
+    const float aw = __ldg(A1 + j);
+    if (aw == 0.f) continue;
+    const float4 h = __ldg(reinterpret_cast<const float4*>(base + plane + (size_t)j * 128));
+    v.x = fmaf(aw, h.x, v.x); v.y = fmaf(aw, h.y, v.y); v.z = fmaf(aw, h.z, v.z); v.w = fmaf(aw, h.w, v.w);
+  }
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(g.scale[hand] + c4 * 4));
+  const float4 sh = __ldg(reinterpret_cast<const float4*>(g.shift[hand] + c4 * 4));
+  return make_float4(fmaxf(fmaf(v.x, sc.x, sh.x), 0.f), fmaxf(fmaf(v.y, sc.y, sh.y), 0.f),
+                     fmaxf(fmaf(v.z, sc.z, sh.z), 0.f), fmaxf(fmaf(v.w, sc.w, sh.w), 0.f));
+}
+
+// grid (42 = k*21 + j, 2 hands, ceil(B/32)); 256 threads = 8 row groups (4 images) x 32 column groups
+__global__ void __launch_bounds__(256) gcn_gemm_kernel(GcnGemmArgs a) {
   extern __shared__ __align__(128) float dyn_smem[];  // weight stream: 2 x 32 x 128 floats + 2 mbarriers
   WStream ws;
   wstream_init(ws, dyn_smem, reinterpret_cast<uint64_t*>(dyn_smem + 2 * 32 * 128));
   __shared__ __align__(16) float xs[GBT][128];
-  const int i = blockIdx.x, hand = blockIdx.y, b0 = blockIdx.z * GBT, tid = threadIdx.x;
-  const int cg = tid & 31, rg = tid >> 5;
+  const int k = blockIdx.x / NJ, j = blockIdx.x % NJ, hand = blockIdx.y, b0 = blockIdx.z * GBT, tid = threadIdx.x;
   const int nb = min(GBT, a.B - b0);
-  const float* W = a.W[hand];
-  const float* A1 = a.A1[hand];
-  float tot[4][4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) tot[r][0] = tot[r][1] = tot[r][2] = tot[r][3] = 0.f;
+  for (int e = tid; e < GBT * 32; e += 256) {
+    const int bb = e >> 5, c4 = e & 31;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bb < nb) {
+      if (a.x)
+        v = __ldg(reinterpret_cast<const float4*>(a.x + ((size_t)((b0 + bb) * 2 + hand) * NJ + j) * 128) + c4);
+      else
+        v = gcn_aggregate(a.hin, a.agg, a.B, b0 + bb, hand, j, c4);
+    }
+    *reinterpret_cast<float4*>(&xs[bb][c4 * 4]) = v;
+  }
+  __syncthreads();
+  const float* Wkj = a.W[hand] + (size_t)(k * NJ + j) * 128 * 128;
+  float* out = a.hout + (size_t)k * a.B * 2 * NJ * 128;
+  cta_gemm<4>(&xs[0][0], 128, nb, 128, Wkj, 128, 128, ws, [&](int, int row, int c0, float (&v)[4]) {
+    *reinterpret_cast<float4*>(out + ((size_t)((b0 + row) * 2 + hand) * NJ + j) * 128 + c0) =
+        make_float4(v[0], v[1], v[2], v[3]);
+  });
+}
 
-  // sources: self (W[0][i], weight 1) then neighbours j (W[1][j], weight A1[i][j])
-  for (int src = -1; src < NJ; ++src) {
-    float aw;
-    const float* Wsrc;
-    int j;
-    if (src < 0) {
-      aw = 1.f;
-      j = i;
-      Wsrc = W + (int64_t)i * 128 * 128;
-    } else {
-      aw = A1[i * NJ + src];
-      if (aw == 0.f) continue;
-      j = src;
-      Wsrc = W + (int64_t)(NJ + src) * 128 * 128;
+// grid (21 joints, 2 hands, ceil(B/32)); 256 threads
+__global__ void __launch_bounds__(256) gcn_finish_kernel(GcnFinishArgs a) {
+  extern __shared__ __align__(128) float dyn_smem[];
+  WStream ws;
+  wstream_init(ws, dyn_smem, reinterpret_cast<uint64_t*>(dyn_smem + 2 * 32 * 128));
+  __shared__ __align__(16) float xs[GBT][128];
+  const int i = blockIdx.x, hand = blockIdx.y, b0 = blockIdx.z * GBT, tid = threadIdx.x;
+  const int nb = min(GBT, a.B - b0);
+  const PointMlp& g = a.gpos;
+  const float sgn = hand == 0 ? -1.f : 1.f;
+  for (int e = tid; e < GBT * 128; e += 256) {  // hidden layer of global_pos_emb: 3 -> 128, BN, ReLU
+    const int bb = e >> 7, kk = e & 127;
+    float h = 0.f;
+    if (bb < nb) {
+      const float* rec = a.prev_record + (size_t)(b0 + bb) * a.rec_stride;
+      const float* p = rec + DIRB200_OFF_JOINT_L + hand * 63 + i * 3;
+      const float* off = rec + DIRB200_OFF_OFFSET;
+      const float px = p[0] / 0.15f + sgn * (off[0] / 2.f);
+      const float py = p[1] / 0.15f + sgn * (off[1] / 2.f);
+      const float pz = p[2] / 0.15f + sgn * (off[2] / 2.f);
+      h = fmaxf(fmaf(fmaf(pz, g.w1t[256 + kk], fmaf(py, g.w1t[128 + kk], px * g.w1t[kk])), g.s1[kk], g.b1[kk]), 0.f);
     }
-    for (int e = tid; e < GBT * 32; e += 256) {  // (previous readers of xs are behind cta_gemm's last barrier)
-      int bb = e >> 5, c4 = e & 31;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (bb < nb)
-        v = __ldg(reinterpret_cast<const float4*>(a.x + ((int64_t)((b0 + bb) * 2 + hand) * NJ + j) * 128) + c4);
-      *reinterpret_cast<float4*>(&xs[bb][c4 * 4]) = v;
-    }
-    __syncthreads();
-    cta_gemm<4>(&xs[0][0], 128, GBT, 128, Wsrc, 128, 128, ws, [&](int r, int, int, float (&v)[4]) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) tot[r][q] = fmaf(aw, v[q], tot[r][q]);
-    });
+    xs[bb][kk] = h;
   }
-  {
-    const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale[hand] + cg * 4));
-    const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift[hand] + cg * 4));
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      tot[r][0] = fmaxf(fmaf(tot[r][0], sc.x, sh.x), 0.f);
-      tot[r][1] = fmaxf(fmaf(tot[r][1], sc.y, sh.y), 0.f);
-      tot[r][2] = fmaxf(fmaf(tot[r][2], sc.z, sh.z), 0.f);
-      tot[r][3] = fmaxf(fmaf(tot[r][3], sc.w, sh.w), 0.f);
-    }
-  }
-  if (a.add_global) {  // + global_pos_emb(xyz/0.15 -/+ offset/2)   (models/dir.py:106-110)
-    const PointMlp& g = a.gpos;
-    const float sgn = hand == 0 ? -1.f : 1.f;
-    for (int e = tid; e < GBT * 128; e += 256) {
-      int bb = e >> 7, k = e & 127;
-      float h = 0.f;
-      if (bb < nb) {
-        const float* rec = a.prev_record + (int64_t)(b0 + bb) * a.rec_stride;
-        const float* p = rec + DIRB200_OFF_JOINT_L + hand * 63 + i * 3;
-        const float* off = rec + DIRB200_OFF_OFFSET;
-        float px = p[0] / 0.15f + sgn * (off[0] / 2.f);
-        float py = p[1] / 0.15f + sgn * (off[1] / 2.f);
-        float pz = p[2] / 0.15f + sgn * (off[2] / 2.f);
-        h = fmaxf(fmaf(fmaf(pz, g.w1t[256 + k], fmaf(py, g.w1t[128 + k], px * g.w1t[k])), g.s1[k], g.b1[k]), 0.f);
-      }
-      xs[bb][k] = h;
-    }
-    __syncthreads();
-    const float4 b2 = __ldg(reinterpret_cast<const float4*>(g.b2 + cg * 4));
-    cta_gemm<4>(&xs[0][0], 128, GBT, 128, g.w2t, 128, 128, ws, [&](int r, int, int, float (&v)[4]) {
-      tot[r][0] += v[0] + b2.x; tot[r][1] += v[1] + b2.y; tot[r][2] += v[2] + b2.z; tot[r][3] += v[3] + b2.w;
-    });
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int bb = rg * 4 + r;
-    if (bb < nb)
-      *reinterpret_cast<float4*>(a.y + ((int64_t)((b0 + bb) * 2 + hand) * NJ + i) * 128 + cg * 4) =
-          make_float4(tot[r][0], tot[r][1], tot[r][2], tot[r][3]);
-  }
+  __syncthreads();
+  cta_gemm<4>(&xs[0][0], 128, nb, 128, g.w2t, 128, 128, ws, [&](int, int row, int c0, float (&v)[4]) {
+    const float4 x = gcn_aggregate(a.hin, a.agg, a.B, b0 + row, hand, i, c0 >> 2);
+    const float4 b2 = __ldg(reinterpret_cast<const float4*>(g.b2 + c0));
+    *reinterpret_cast<float4*>(a.y + ((size_t)((b0 + row) * 2 + hand) * NJ + i) * 128 + c0) =
+        make_float4(x.x + (v[0] + b2.x), x.y + (v[1] + b2.y), x.z + (v[2] + b2.z), x.w + (v[3] + b2.w));
+  });
 }
 
 // =================================================================== STE
@@ -438,13 +431,22 @@ void launch_joint_embed(const EmbedArgs& a, cudaStream_t st) {
 template void launch_joint_embed<float>(const EmbedArgs&, cudaStream_t);
 template void launch_joint_embed<__nv_bfloat16>(const EmbedArgs&, cudaStream_t);
 
-void launch_gcn_layer(const GcnLayerArgs& a, cudaStream_t st) {
+void launch_gcn_gemm(const GcnGemmArgs& a, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(gcn_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(gcn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr = true;
   }
-  gcn_layer_kernel<<<dim3(NJ, 2, ceil_div(a.B, GBT)), 256, 2 * 32 * 128 * 4 + 16, st>>>(a);
+  gcn_gemm_kernel<<<dim3(2 * NJ, 2, ceil_div(a.B, GBT)), 256, 2 * 32 * 128 * 4 + 16, st>>>(a);
+}
+
+void launch_gcn_finish(const GcnFinishArgs& a, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gcn_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+  gcn_finish_kernel<<<dim3(NJ, 2, ceil_div(a.B, GBT)), 256, 2 * 32 * 128 * 4 + 16, st>>>(a);
 }
 
 void launch_ste(const float* x, float* y, const SteWeights& w, int B, cudaStream_t st) {

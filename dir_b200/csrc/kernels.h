@@ -76,21 +76,34 @@ struct EmbedArgs {
 template <typename T>
 void launch_joint_embed(const EmbedArgs& a, cudaStream_t st);
 
-struct GcnLayerArgs {
-  const float* x;      // (B,2,21,128)
-  float* y;            // (B,2,21,128)
-  const float* W[2];   // per hand: (2,21,128,128)
-  const float* A1[2];  // per hand: (21,21) softmaxed
-  const float* scale[2];  // folded BN scale (128)
-  const float* shift[2];  // folded BN shift incl. gconv bias
-  // fused tail of the 4th layer: y += global_pos_emb(xyz/0.15 -/+ offset/2)
-  int add_global;
+// SemGCN stack, restructured for uniform work: every layer is 42 independent (B x 128)·(128 x 128) products per hand,
+//   H[k][b][hand][j] = X[b][hand][j] · W[k][j]   (k = 0 self weight, k = 1 neighbour weight),
+// and the graph aggregation + BN + ReLU of layer l,  X' [i] = relu(bn(H0[i] + sum_j A1[i][j] H1[j] + bias)),
+// is applied on the fly when layer l+1 (or the final kernel) loads its operand.
+struct GcnAgg {          // aggregation parameters of the layer that PRODUCED H
+  const float* A1[2];    // per hand: (21,21) softmaxed adjacency
+  const float* scale[2]; // folded BN scale (128)
+  const float* shift[2]; // folded BN shift incl. gconv bias
+};
+struct GcnGemmArgs {
+  const float* x;     // first layer: (B,2,21,128) features; otherwise nullptr
+  const float* hin;   // later layers: H of the previous layer, [2][B][2][21][128]
+  GcnAgg agg;         // how to turn hin into this layer's input
+  float* hout;        // [2][B][2][21][128]
+  const float* W[2];  // this layer's weights per hand: (2,21,128,128)
+  int B;
+};
+void launch_gcn_gemm(const GcnGemmArgs& a, cudaStream_t st);
+struct GcnFinishArgs {  // tokens = relu(bn(agg(H))) + global_pos_emb(xyz/0.15 -/+ offset/2)   (models/dir.py:103-110)
+  const float* hin;
+  GcnAgg agg;
   PointMlp gpos;
   const float* prev_record;
   int rec_stride;
+  float* y;  // (B,2,21,128) = (B,42,128) tokens
   int B;
 };
-void launch_gcn_layer(const GcnLayerArgs& a, cudaStream_t st);
+void launch_gcn_finish(const GcnFinishArgs& a, cudaStream_t st);
 
 struct SteWeights {
   const float* pos;  // (42,128)

@@ -1,0 +1,54 @@
+"""Multi-GPU plumbing: the forward has no exchange step, so images shard over ranks and the only
+collective is one all-gather of the packed per-image records (58.6 KB/img). One process per GPU
+(torchrun / torch.distributed for rendezvous only); the all-gather itself is `dirb200_allgather_records`
+(NCCL over NVLink) on the compute stream. The reference has no distributed code to mirror."""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous balanced split of n images: the first n % world ranks take one extra."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def padded_shard(n: int, world: int) -> int:
+    """ncclAllGather needs equal contributions: every rank sends ceil(n / world) records (tail zero-padded)."""
+    return (n + world - 1) // world
+
+
+def broadcast_bytes(payload, src: int = 0, group=None) -> bytes:
+    """Rank `src` passes bytes, the others None; everybody gets src's bytes (used for the 128-byte NCCL id)."""
+    obj = [payload]
+    dist.broadcast_object_list(obj, src=src, group=group)
+    return obj[0]
+
+
+def assemble(gathered: torch.Tensor, n: int, world: int) -> torch.Tensor:
+    """(world * padded, R) rank-major gather result -> (n, R) in original image order (pads dropped)."""
+    pad = padded_shard(n, world)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_bounds(n, r, world)
+        parts.append(gathered[r * pad:r * pad + (hi - lo)])
+    return torch.cat(parts, 0)
+
+
+def init_nccl(model):
+    """Create the library's communicator for an initialised torch.distributed job."""
+    model.init_nccl(dist.get_rank(), dist.get_world_size(), lambda b: broadcast_bytes(b))
+
+
+def forward_sharded(model, img_global: torch.Tensor):
+    """Every rank holds the same (n,3,256,256) batch (or at least its own slice of it); each runs its shard and all
+    ranks return the reference's outs_list for all n images (aux maps stay local and are not gathered)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = img_global.shape[0]
+    lo, hi = shard_bounds(n, rank, world)
+    pad = padded_shard(n, world)
+    local = model.run_raw(img_global[lo:hi])["record"]
+    if local.shape[0] < pad:
+        local = torch.cat([local, local.new_zeros(pad - local.shape[0], local.shape[1])], 0)
+    full = assemble(model.allgather_records(local.contiguous()), n, world)
+    return model.unpack_record(full)
