@@ -210,14 +210,32 @@ class DIR(nn.Module):
         g.replay()
         return {k: v.clone() for k, v in so.items()}
 
+    def _to_device(self, img):
+        """models/dir.py:514 does `input['img'].cuda()` on the compute stream. Host tensors are uploaded on a
+        dedicated copy stream instead (pinned memory => truly asynchronous), so the H2D copy of call i+1 overlaps
+        the kernels of call i; the compute stream waits on an event, never the host."""
+        dev = self._device()
+        if img.device.type == "cuda":
+            return img.to(device=dev, dtype=torch.float32).contiguous()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(self._copy_stream):
+            x = img.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        cur.wait_event(ev)
+        x.record_stream(cur)
+        return x
+
     def run_raw(self, img):
         """img (B,3,256,256) on the module's device -> dict of packed output buffers (record, mano_para, ...)."""
         self._ensure_handle()
         if not self._packed:
             self._pack()
-        x = img.to(device=self._device(), dtype=torch.float32).contiguous()
-        if x.dim() != 4 or tuple(x.shape[1:]) != (3, 256, 256):
-            raise ValueError(f"expected (B,3,256,256) images, got {tuple(x.shape)}")
+        if img.dim() != 4 or tuple(img.shape[1:]) != (3, 256, 256):
+            raise ValueError(f"expected (B,3,256,256) images, got {tuple(img.shape)}")
+        x = self._to_device(img)
         with torch.cuda.device(self._device()):
             if x.shape[0] <= self.max_batch:
                 return self._run_chunk(x)
