@@ -178,20 +178,135 @@ __global__ void __launch_bounds__(256) gcn_finish_kernel(GcnFinishArgs a) {
 }
 
 // =================================================================== STE
+// One CTA per image: the whole 3-block transformer + head with the token state in shared memory.
+// 8 consumer warps do the math; a 9th warp is a dedicated weight producer that streams every Linear's K-major
+// weights (100 slabs of 32 x 128 floats per image) through a 4-deep smem ring with cp.async.bulk + full/empty
+// mbarriers, running ahead across layer boundaries, so no GEMM ever starts on a cold L2 fetch.
 constexpr int NT = 42;
-constexpr int STE_THREADS = 256;
+constexpr int STE_CONSUMERS = 256;
+constexpr int STE_THREADS = STE_CONSUMERS + 32;
 constexpr int SC_LD = 44;
-constexpr int STE_SMEM_FLOATS = 2 * 32 * 128 + NT * 128 * 2 + NT * 384 + 4 * NT * SC_LD + 4;
+constexpr int RING_D = 4;
+constexpr int SLAB_FLOATS = 32 * 128;
+constexpr int STE_NSEG = 22;
+constexpr int STE_SMEM_FLOATS = RING_D * SLAB_FLOATS + NT * 128 * 2 + NT * 384 + 4 * NT * SC_LD;
+constexpr int STE_SMEM_BYTES = STE_SMEM_FLOATS * 4 + 2 * RING_D * 8 + STE_NSEG * 24 + 64;
+
+struct WSeg {
+  const float* ptr;  // first row of this 128-(or 64-)column block, K-major
+  int ldb;           // floats between consecutive k rows
+  int nslab;         // K / 32
+  int nc;            // columns in the block (128 or 64)
+};
+struct WRing {
+  float* buf;
+  uint64_t* full;
+  uint64_t* empty;
+  uint32_t it;  // slabs consumed so far
+};
+
+__device__ __forceinline__ void ste_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = cta_smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// producer warp: walk the schedule, one 32-row slab per ring slot
+__device__ __forceinline__ void ste_producer(const WSeg* segs, int nseg, float* ring, uint64_t* full, uint64_t* empty) {
+  const int lane = threadIdx.x & 31;
+  uint32_t g = 0;
+  for (int sgi = 0; sgi < nseg; ++sgi) {
+    const WSeg sg = segs[sgi];
+    for (int sl = 0; sl < sg.nslab; ++sl, ++g) {
+      const uint32_t buf = g % RING_D;
+      if (g >= RING_D) mbar_wait_parity(&empty[buf], ((g / RING_D) - 1) & 1);
+      const uint32_t bar = cta_smem_u32(&full[buf]);
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(32 * sg.nc * 4))
+                     : "memory");
+      __syncwarp();
+      const uint32_t dst = cta_smem_u32(ring + buf * SLAB_FLOATS + lane * sg.nc);
+      const float* src = sg.ptr + (size_t)(sl * 32 + lane) * sg.ldb;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(src), "r"((uint32_t)(sg.nc * 4)), "r"(bar)
+                   : "memory");
+    }
+  }
+}
+
+// consumer side of one (M x K)·(K x NC) product; the next K/32 slabs of the ring must hold its weights
+template <int TM, typename Epi>
+__device__ __forceinline__ void ring_gemm(const float* __restrict__ A, int lda, int M, int K, int NC, WRing& rg,
+                                          Epi epi) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int ncg = NC >> 2, nrg = (M + TM - 1) / TM;
+  const int cg = tid % ncg, rgi = tid / ncg;
+  const bool active = tid < ncg * nrg;
+  const int nslab = K >> 5;
+  float acc[TM][4];
+#pragma unroll
+  for (int r = 0; r < TM; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+  const float* arow[TM];
+#pragma unroll
+  for (int r = 0; r < TM; ++r) arow[r] = A + (size_t)min(rgi * TM + r, M - 1) * lda;
+  for (int sl = 0; sl < nslab; ++sl) {
+    const uint32_t g = rg.it + sl, buf = g % RING_D;
+    mbar_wait_parity(&rg.full[buf], (g / RING_D) & 1);
+    if (active) {
+      const float* wb = rg.buf + buf * SLAB_FLOATS + cg * 4;
+#pragma unroll
+      for (int kk = 0; kk < 32; kk += 4) {
+        const float4 b0 = *reinterpret_cast<const float4*>(wb + (kk + 0) * NC);
+        const float4 b1 = *reinterpret_cast<const float4*>(wb + (kk + 1) * NC);
+        const float4 b2 = *reinterpret_cast<const float4*>(wb + (kk + 2) * NC);
+        const float4 b3 = *reinterpret_cast<const float4*>(wb + (kk + 3) * NC);
+#pragma unroll
+        for (int r = 0; r < TM; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(arow[r] + sl * 32 + kk);
+          acc[r][0] = fmaf(a.x, b0.x, acc[r][0]); acc[r][1] = fmaf(a.x, b0.y, acc[r][1]);
+          acc[r][2] = fmaf(a.x, b0.z, acc[r][2]); acc[r][3] = fmaf(a.x, b0.w, acc[r][3]);
+          acc[r][0] = fmaf(a.y, b1.x, acc[r][0]); acc[r][1] = fmaf(a.y, b1.y, acc[r][1]);
+          acc[r][2] = fmaf(a.y, b1.z, acc[r][2]); acc[r][3] = fmaf(a.y, b1.w, acc[r][3]);
+          acc[r][0] = fmaf(a.z, b2.x, acc[r][0]); acc[r][1] = fmaf(a.z, b2.y, acc[r][1]);
+          acc[r][2] = fmaf(a.z, b2.z, acc[r][2]); acc[r][3] = fmaf(a.z, b2.w, acc[r][3]);
+          acc[r][0] = fmaf(a.w, b3.x, acc[r][0]); acc[r][1] = fmaf(a.w, b3.y, acc[r][1]);
+          acc[r][2] = fmaf(a.w, b3.z, acc[r][2]); acc[r][3] = fmaf(a.w, b3.w, acc[r][3]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0)  // this warp is done with the slot
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cta_smem_u32(&rg.empty[buf])) : "memory");
+  }
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < TM; ++r) {
+      const int row = rgi * TM + r;
+      if (row < M) epi(r, row, cg * 4, acc[r]);
+    }
+  }
+  rg.it += nslab;
+}
 
 // out[r][n] = sum_k in[r][k] * Wt[k][n] + bias[n]; optional GELU; optional residual accumulate into out.
-// 42 token rows = 7 row groups of 6; N is walked in 128-column blocks on the weight-streaming CTA GEMM.
+// 42 token rows = 7 row groups of 6; N is walked in 128-column blocks (the producer's schedule order).
 template <int MODE>  // 0: store, 1: store GELU, 2: out += result
-__device__ __forceinline__ void ste_linear(const float* __restrict__ in, int ldin, int K, const float* __restrict__ Wt,
+__device__ __forceinline__ void ste_linear(const float* __restrict__ in, int ldin, int K,
                                            const float* __restrict__ bias, int N, float* __restrict__ out, int ldout,
-                                           WStream& ws) {
+                                           WRing& rg) {
   for (int cb = 0; cb < N; cb += 128) {
     const int NC = min(128, N - cb);
-    cta_gemm<6>(in, ldin, NT, K, Wt + cb, N, NC, ws, [&](int, int row, int c0, float (&v)[4]) {
+    ring_gemm<6>(in, ldin, NT, K, NC, rg, [&](int, int row, int c0, float (&v)[4]) {
       const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + cb + c0));
       float4 o = make_float4(v[0] + bb.x, v[1] + bb.y, v[2] + bb.z, v[3] + bb.w);
       if (MODE == 1) {
@@ -210,11 +325,11 @@ __device__ __forceinline__ void ste_linear(const float* __restrict__ in, int ldi
   }
 }
 
-// LayerNorm over 128 channels, one warp per row (two-pass like ATen)
+// LayerNorm over 128 channels, one warp per row (two-pass like ATen); consumer warps only
 __device__ __forceinline__ void ste_layernorm(const float* __restrict__ in, float* __restrict__ out,
                                               const float* __restrict__ w, const float* __restrict__ b, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < NT; r += STE_THREADS / 32) {
+  for (int r = warp; r < NT; r += STE_CONSUMERS / 32) {
     float4 v = *reinterpret_cast<const float4*>(in + r * 128 + lane * 4);
     float mu = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
     float dx = v.x - mu, dy = v.y - mu, dz = v.z - mu, dw = v.w - mu;
@@ -230,40 +345,64 @@ __device__ __forceinline__ void ste_layernorm(const float* __restrict__ in, floa
 __global__ void __launch_bounds__(STE_THREADS) ste_kernel(const float* __restrict__ xin, float* __restrict__ yout,
                                                           SteWeights w) {
   extern __shared__ __align__(128) float sm[];
-  float* x = sm + 2 * 32 * 128;    // [42][128] residual stream (after the 32 KB weight-stream buffers)
-  float* h = x + NT * 128;         // [42][128] LN output / attention output
-  float* big = h + NT * 128;       // [42][384] qkv, later [42][256] MLP hidden
-  float* sc = big + NT * 384;      // [4][42][44] attention probabilities
-  WStream ws;
-  wstream_init(ws, sm, reinterpret_cast<uint64_t*>(sc + 4 * NT * SC_LD));
+  float* ring = sm;                        // [4][32][128] weight slabs
+  float* x = ring + RING_D * SLAB_FLOATS;  // [42][128] residual stream
+  float* h = x + NT * 128;                 // [42][128] LN output / attention output
+  float* big = h + NT * 128;               // [42][384] qkv, later [42][256] MLP hidden
+  float* sc = big + NT * 384;              // [4][42][44] attention probabilities
+  uint64_t* full = reinterpret_cast<uint64_t*>(sc + 4 * NT * SC_LD);
+  uint64_t* empty = full + RING_D;
+  WSeg* segs = reinterpret_cast<WSeg*>(empty + RING_D);
   const int b = blockIdx.x, tid = threadIdx.x;
-  for (int i = tid; i < NT * 128; i += STE_THREADS) x[i] = xin[(int64_t)b * NT * 128 + i] + w.pos[i];
+  if (tid == 0) {
+    for (int i = 0; i < RING_D; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cta_smem_u32(&full[i])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cta_smem_u32(&empty[i])), "r"(STE_CONSUMERS / 32));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    int n = 0;
+    for (int l = 0; l < 3; ++l) {  // consumption order of ste_linear calls below
+      const SteWeights::Block& B = w.blk[l];
+      for (int cb = 0; cb < 384; cb += 128) segs[n++] = WSeg{B.qkv_t + cb, 384, 4, 128};
+      segs[n++] = WSeg{B.proj_t, 128, 4, 128};
+      for (int cb = 0; cb < 256; cb += 128) segs[n++] = WSeg{B.fc1_t + cb, 256, 4, 128};
+      segs[n++] = WSeg{B.fc2_t, 128, 8, 128};
+    }
+    segs[n++] = WSeg{w.head_t, 64, 4, 64};
+  }
   __syncthreads();
+  if (tid >= STE_CONSUMERS) {  // producer warp
+    ste_producer(segs, STE_NSEG, ring, full, empty);
+    return;
+  }
+  WRing rg{ring, full, empty, 0};
+  for (int i = tid; i < NT * 128; i += STE_CONSUMERS) x[i] = xin[(int64_t)b * NT * 128 + i] + w.pos[i];
+  ste_bar();
   for (int l = 0; l < 3; ++l) {
     const SteWeights::Block& B = w.blk[l];
     ste_layernorm(x, h, B.n1w, B.n1b, 1e-6f);
-    __syncthreads();
-    ste_linear<0>(h, 128, 128, B.qkv_t, B.qkv_b, 384, big, 384, ws);
-    __syncthreads();
+    ste_bar();
+    ste_linear<0>(h, 128, 128, B.qkv_b, 384, big, 384, rg);
+    ste_bar();
     // scores = q k^T * 32^-0.5
-    for (int item = tid; item < 4 * NT * NT; item += STE_THREADS) {
+    for (int item = tid; item < 4 * NT * NT; item += STE_CONSUMERS) {
       int j = item % NT, t = item / NT;
       int i = t % NT, hd = t / NT;
       const float* q = big + i * 384 + hd * 32;
       const float* k = big + j * 384 + 128 + hd * 32;
-      float s = 0.f;
+      float s2 = 0.f;
 #pragma unroll
       for (int d = 0; d < 32; d += 4) {
         float4 a4 = *reinterpret_cast<const float4*>(q + d);
         float4 b4 = *reinterpret_cast<const float4*>(k + d);
-        s = fmaf(a4.x, b4.x, s); s = fmaf(a4.y, b4.y, s); s = fmaf(a4.z, b4.z, s); s = fmaf(a4.w, b4.w, s);
+        s2 = fmaf(a4.x, b4.x, s2); s2 = fmaf(a4.y, b4.y, s2); s2 = fmaf(a4.z, b4.z, s2); s2 = fmaf(a4.w, b4.w, s2);
       }
-      sc[(hd * NT + i) * SC_LD + j] = s * 0.17677669529663688110f;
+      sc[(hd * NT + i) * SC_LD + j] = s2 * 0.17677669529663688110f;
     }
-    __syncthreads();
+    ste_bar();
     {  // softmax rows
       const int warp = tid >> 5, lane = tid & 31;
-      for (int r = warp; r < 4 * NT; r += STE_THREADS / 32) {
+      for (int r = warp; r < 4 * NT; r += STE_CONSUMERS / 32) {
         float* row = sc + r * SC_LD;
         float v0 = row[lane], v1 = (lane + 32 < NT) ? row[lane + 32] : -INFINITY;
         float mx = warp_max(fmaxf(v0, v1));
@@ -273,35 +412,35 @@ __global__ void __launch_bounds__(STE_THREADS) ste_kernel(const float* __restric
         if (lane + 32 < NT) row[lane + 32] = e1 * inv;
       }
     }
-    __syncthreads();
+    ste_bar();
     // o = P v  -> h[i][hd*32+d]
-    for (int item = tid; item < NT * 128; item += STE_THREADS) {
+    for (int item = tid; item < NT * 128; item += STE_CONSUMERS) {
       int c = item & 127, i = item >> 7;
       int hd = c >> 5;
       const float* p = sc + (hd * NT + i) * SC_LD;
       const float* v = big + 256 + c;
-      float s = 0.f;
+      float s2 = 0.f;
 #pragma unroll 6
-      for (int j = 0; j < NT; ++j) s = fmaf(p[j], v[j * 384], s);
-      h[item] = s;
+      for (int j = 0; j < NT; ++j) s2 = fmaf(p[j], v[j * 384], s2);
+      h[item] = s2;
     }
-    __syncthreads();
-    ste_linear<2>(h, 128, 128, B.proj_t, B.proj_b, 128, x, 128, ws);
-    __syncthreads();
+    ste_bar();
+    ste_linear<2>(h, 128, 128, B.proj_b, 128, x, 128, rg);
+    ste_bar();
     ste_layernorm(x, h, B.n2w, B.n2b, 1e-6f);
-    __syncthreads();
-    ste_linear<1>(h, 128, 128, B.fc1_t, B.fc1_b, 256, big, 256, ws);
-    __syncthreads();
-    ste_linear<2>(big, 256, 256, B.fc2_t, B.fc2_b, 128, x, 128, ws);
-    __syncthreads();
+    ste_bar();
+    ste_linear<1>(h, 128, 128, B.fc1_b, 256, big, 256, rg);
+    ste_bar();
+    ste_linear<2>(big, 256, 256, B.fc2_b, 128, x, 128, rg);
+    ste_bar();
     ste_layernorm(x, x, w.snw, w.snb, 1e-6f);  // shared spatial_norm (mixSTE.py:200), in place (row-local)
-    __syncthreads();
+    ste_bar();
   }
   ste_layernorm(x, h, w.hnw, w.hnb, 1e-5f);
-  __syncthreads();
-  ste_linear<0>(h, 128, 128, w.head_t, w.head_b, 64, big, 64, ws);
-  __syncthreads();
-  for (int i = tid; i < NT * 64; i += STE_THREADS) yout[(int64_t)b * NT * 64 + i] = big[i];
+  ste_bar();
+  ste_linear<0>(h, 128, 128, w.head_b, 64, big, 64, rg);
+  ste_bar();
+  for (int i = tid; i < NT * 64; i += STE_CONSUMERS) yout[(int64_t)b * NT * 64 + i] = big[i];
 }
 
 // =================================================================== bone rasterisation
@@ -451,7 +590,7 @@ void launch_gcn_finish(const GcnFinishArgs& a, cudaStream_t st) {
 
 void launch_ste(const float* x, float* y, const SteWeights& w, int B, cudaStream_t st) {
   static bool attr_set = false;
-  const int smem = STE_SMEM_FLOATS * (int)sizeof(float);
+  const int smem = STE_SMEM_BYTES;
   if (!attr_set) {
     cudaFuncSetAttribute(ste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_set = true;
