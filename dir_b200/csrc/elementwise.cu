@@ -249,6 +249,15 @@ __global__ void transpose2d_kernel(const float* __restrict__ src, float* __restr
   }
 }
 
+// Linear weight [N][K] (PyTorch) -> k-pair interleaved K-major [K/2][N][2]: (w[n][2p], w[n][2p+1]) adjacent, so a
+// 128-bit shared-memory load yields two (k, k+1) operand pairs for the packed FFMA2 of ring_gemm.
+__global__ void transpose_pairs_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int K) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * K) return;
+  int e = idx & 1, n = (idx >> 1) % N, p = (idx >> 1) / N;
+  dst[idx] = src[(size_t)n * K + 2 * p + e];
+}
+
 // A_1 = row softmax of the 40 learned logits placed at the row-major nonzeros of the symmetric
 // 21-joint skeleton adjacency (SemGCN/p_graph_conv.py:43-50, SemGCN/utils.py:27-43,66-71).
 __global__ void gcn_adjacency_kernel(const float* __restrict__ e1, float* __restrict__ A) {
@@ -376,6 +385,10 @@ void launch_pack_conv_weight(const float* src, float* d32, __nv_bfloat16* d16, i
 void launch_transpose2d(const float* src, float* dst, int rows, int cols, cudaStream_t st) {
   dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
   transpose2d_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, rows, cols);
+}
+
+void launch_transpose_pairs(const float* src, float* dst, int N, int K, cudaStream_t st) {
+  transpose_pairs_kernel<<<ceil_div(N * K, 256), 256, 0, st>>>(src, dst, N, K);
 }
 
 void launch_gcn_adjacency(const float* e1, float* A, cudaStream_t st) { gcn_adjacency_kernel<<<1, 32, 0, st>>>(e1, A); }

@@ -83,6 +83,19 @@ float* Engine::transposed(const std::string& name, int rows, int cols) {
   return d;
 }
 
+// src is a Linear weight (N, K) -> k-pair interleaved K-major [K/2][N][2]
+float* Engine::transposed_pairs(const std::string& name, int N, int K) {
+  const float* src = W(name);
+  if (dry || !src) return nullptr;
+  if (raw[name].numel() != (int64_t)N * K) {
+    if (err.empty()) err = "unexpected size for " + name;
+    return nullptr;
+  }
+  float* d = dalloc((size_t)N * K);
+  if (d) launch_transpose_pairs(src, d, N, K, fin_stream);
+  return d;
+}
+
 // scale/shift = eval-BN folded with an optional preceding conv bias. Writes n values at offset `off` of
 // buffers of `total` (allocated on first use when *scale == nullptr).
 void Engine::fold(const std::string& conv_bias, const std::string& bn, float** scale, float** shift, int n, int off,
@@ -213,22 +226,22 @@ void Engine::build_stage(int s, const std::string& p) {
     auto& B = st.ste.blk[l];
     B.n1w = copy_of(bq + "norm1.weight");
     B.n1b = copy_of(bq + "norm1.bias");
-    B.qkv_t = transposed(bq + "attn.qkv.weight", 384, 128);
+    B.qkv_t = transposed_pairs(bq + "attn.qkv.weight", 384, 128);
     B.qkv_b = copy_of(bq + "attn.qkv.bias");
-    B.proj_t = transposed(bq + "attn.proj.weight", 128, 128);
+    B.proj_t = transposed_pairs(bq + "attn.proj.weight", 128, 128);
     B.proj_b = copy_of(bq + "attn.proj.bias");
     B.n2w = copy_of(bq + "norm2.weight");
     B.n2b = copy_of(bq + "norm2.bias");
-    B.fc1_t = transposed(bq + "mlp.fc1.weight", 256, 128);
+    B.fc1_t = transposed_pairs(bq + "mlp.fc1.weight", 256, 128);
     B.fc1_b = copy_of(bq + "mlp.fc1.bias");
-    B.fc2_t = transposed(bq + "mlp.fc2.weight", 128, 256);
+    B.fc2_t = transposed_pairs(bq + "mlp.fc2.weight", 128, 256);
     B.fc2_b = copy_of(bq + "mlp.fc2.bias");
   }
   st.ste.snw = copy_of(q + "spatial_norm.weight");
   st.ste.snb = copy_of(q + "spatial_norm.bias");
   st.ste.hnw = copy_of(q + "head.0.weight");
   st.ste.hnb = copy_of(q + "head.0.bias");
-  st.ste.head_t = transposed(q + "head.1.weight", 64, 128);
+  st.ste.head_t = transposed_pairs(q + "head.1.weight", 64, 128);
   st.ste.head_b = copy_of(q + "head.1.bias");
   st.fusion0 = make_conv(p + "fusion.0.weight", p + "fusion.0.bias", p + "fusion.1.", 1, 1, 1);
   st.fusion3 = make_conv(p + "fusion.3.weight", p + "fusion.3.bias", "", 1, 0, 0);

@@ -132,6 +132,7 @@ struct Engine {
   float* dalloc(size_t nfloats);
   float* copy_of(const std::string& name);
   float* transposed(const std::string& name, int rows, int cols);
+  float* transposed_pairs(const std::string& name, int N, int K);
   void fold(const std::string& conv_bias, const std::string& bn, float** scale, float** shift, int n, int off = 0,
             int total = 0);
   ConvLayer make_conv(const std::string& wname, const std::string& bias, const std::string& bn, int stride, int pad,

@@ -183,13 +183,16 @@ __global__ void __launch_bounds__(256) gcn_finish_kernel(GcnFinishArgs a) {
 // weights (100 slabs of 32 x 128 floats per image) through a 4-deep smem ring with cp.async.bulk + full/empty
 // mbarriers, running ahead across layer boundaries, so no GEMM ever starts on a cold L2 fetch.
 constexpr int NT = 42;
-constexpr int STE_CONSUMERS = 256;
+constexpr int STE_CONSUMERS = 512;  // two groups of 256: group g multiplies the slabs with (slab index & 1) == g
+constexpr int STE_GROUP = 256;
 constexpr int STE_THREADS = STE_CONSUMERS + 32;
 constexpr int SC_LD = 44;
 constexpr int RING_D = 4;
 constexpr int SLAB_FLOATS = 32 * 128;
 constexpr int STE_NSEG = 22;
-constexpr int STE_SMEM_FLOATS = RING_D * SLAB_FLOATS + NT * 128 * 2 + NT * 384 + 4 * NT * SC_LD;
+constexpr int QLD = 388;  // qkv row pitch: 388 % 32 = 4 banks of skew per token, so 128-bit K-row reads by 8
+                          // consecutive lanes cover all 32 banks (a pitch of 384 makes them 8-way conflicted)
+constexpr int STE_SMEM_FLOATS = RING_D * SLAB_FLOATS + NT * 128 * 2 + NT * QLD + 16 * 48 + NT * 128;
 constexpr int STE_SMEM_BYTES = STE_SMEM_FLOATS * 4 + 2 * RING_D * 8 + STE_NSEG * 24 + 64;
 
 struct WSeg {
@@ -205,7 +208,7 @@ struct WRing {
   uint32_t it;  // slabs consumed so far
 };
 
-__device__ __forceinline__ void ste_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void ste_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = cta_smem_u32(bar);
@@ -235,52 +238,63 @@ __device__ __forceinline__ void ste_producer(const WSeg* segs, int nseg, float* 
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(32 * sg.nc * 4))
                      : "memory");
       __syncwarp();
-      const uint32_t dst = cta_smem_u32(ring + buf * SLAB_FLOATS + lane * sg.nc);
-      const float* src = sg.ptr + (size_t)(sl * 32 + lane) * sg.ldb;
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                   "l"(src), "r"((uint32_t)(sg.nc * 4)), "r"(bar)
-                   : "memory");
+      if (lane < 16) {  // slab = 16 k-pair rows of (nc x 2) floats
+        const uint32_t dst = cta_smem_u32(ring + buf * SLAB_FLOATS + lane * sg.nc * 2);
+        const float* src = sg.ptr + (size_t)(sl * 16 + lane) * sg.ldb;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(src), "r"((uint32_t)(sg.nc * 8)), "r"(bar)
+                     : "memory");
+      }
     }
   }
 }
 
-// consumer side of one (M x K)·(K x NC) product; the next K/32 slabs of the ring must hold its weights
+// consumer side of one (M x K)·(K x NC) product; the next K/32 slabs of the ring must hold its weights.
+// 512 consumers = 2 groups x (TM x 4 register tiles); group g takes the slabs of its parity, the two partial sums
+// meet in `part` (group 1 -> smem, group 0 adds and runs the epilogue). Inner product on packed FFMA2: the pair
+// (even k, odd k) of one output rides in one 64-bit register, operands come pre-paired from smem.
 template <int TM, typename Epi>
 __device__ __forceinline__ void ring_gemm(const float* __restrict__ A, int lda, int M, int K, int NC, WRing& rg,
-                                          Epi epi) {
+                                          float* __restrict__ part, Epi epi) {
   const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid >> 8, gt = tid & 255;
   const int ncg = NC >> 2, nrg = (M + TM - 1) / TM;
-  const int cg = tid % ncg, rgi = tid / ncg;
-  const bool active = tid < ncg * nrg;
+  const int cg = gt % ncg, rgi = gt / ncg;
+  const bool active = gt < ncg * nrg;
   const int nslab = K >> 5;
-  float acc[TM][4];
+  float2 acc[TM][4];
 #pragma unroll
-  for (int r = 0; r < TM; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+  for (int r = 0; r < TM; ++r)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[r][q] = make_float2(0.f, 0.f);
   const float* arow[TM];
 #pragma unroll
   for (int r = 0; r < TM; ++r) arow[r] = A + (size_t)min(rgi * TM + r, M - 1) * lda;
   for (int sl = 0; sl < nslab; ++sl) {
-    const uint32_t g = rg.it + sl, buf = g % RING_D;
+    const uint32_t g = rg.it + sl;
+    if ((int)(g & 1) != grp) continue;
+    const uint32_t buf = g % RING_D;
     mbar_wait_parity(&rg.full[buf], (g / RING_D) & 1);
     if (active) {
-      const float* wb = rg.buf + buf * SLAB_FLOATS + cg * 4;
+      const float* wb = rg.buf + buf * SLAB_FLOATS + cg * 8;  // row p: [n][2] pairs
 #pragma unroll
-      for (int kk = 0; kk < 32; kk += 4) {
-        const float4 b0 = *reinterpret_cast<const float4*>(wb + (kk + 0) * NC);
-        const float4 b1 = *reinterpret_cast<const float4*>(wb + (kk + 1) * NC);
-        const float4 b2 = *reinterpret_cast<const float4*>(wb + (kk + 2) * NC);
-        const float4 b3 = *reinterpret_cast<const float4*>(wb + (kk + 3) * NC);
+      for (int kp = 0; kp < 16; kp += 2) {  // two k-pairs = 4 k per step
+        const float4 b0 = *reinterpret_cast<const float4*>(wb + (kp + 0) * NC * 2);      // (k0,k1) for n, n+1
+        const float4 b1 = *reinterpret_cast<const float4*>(wb + (kp + 0) * NC * 2 + 4);  // (k0,k1) for n+2, n+3
+        const float4 b2 = *reinterpret_cast<const float4*>(wb + (kp + 1) * NC * 2);      // (k2,k3) for n, n+1
+        const float4 b3 = *reinterpret_cast<const float4*>(wb + (kp + 1) * NC * 2 + 4);
 #pragma unroll
         for (int r = 0; r < TM; ++r) {
-          const float4 a = *reinterpret_cast<const float4*>(arow[r] + sl * 32 + kk);
-          acc[r][0] = fmaf(a.x, b0.x, acc[r][0]); acc[r][1] = fmaf(a.x, b0.y, acc[r][1]);
-          acc[r][2] = fmaf(a.x, b0.z, acc[r][2]); acc[r][3] = fmaf(a.x, b0.w, acc[r][3]);
-          acc[r][0] = fmaf(a.y, b1.x, acc[r][0]); acc[r][1] = fmaf(a.y, b1.y, acc[r][1]);
-          acc[r][2] = fmaf(a.y, b1.z, acc[r][2]); acc[r][3] = fmaf(a.y, b1.w, acc[r][3]);
-          acc[r][0] = fmaf(a.z, b2.x, acc[r][0]); acc[r][1] = fmaf(a.z, b2.y, acc[r][1]);
-          acc[r][2] = fmaf(a.z, b2.z, acc[r][2]); acc[r][3] = fmaf(a.z, b2.w, acc[r][3]);
-          acc[r][0] = fmaf(a.w, b3.x, acc[r][0]); acc[r][1] = fmaf(a.w, b3.y, acc[r][1]);
-          acc[r][2] = fmaf(a.w, b3.z, acc[r][2]); acc[r][3] = fmaf(a.w, b3.w, acc[r][3]);
+          const float4 a = *reinterpret_cast<const float4*>(arow[r] + sl * 32 + kp * 2);
+          const float2 a01 = make_float2(a.x, a.y), a23 = make_float2(a.z, a.w);
+          acc[r][0] = __ffma2_rn(a01, make_float2(b0.x, b0.y), acc[r][0]);
+          acc[r][1] = __ffma2_rn(a01, make_float2(b0.z, b0.w), acc[r][1]);
+          acc[r][2] = __ffma2_rn(a01, make_float2(b1.x, b1.y), acc[r][2]);
+          acc[r][3] = __ffma2_rn(a01, make_float2(b1.z, b1.w), acc[r][3]);
+          acc[r][0] = __ffma2_rn(a23, make_float2(b2.x, b2.y), acc[r][0]);
+          acc[r][1] = __ffma2_rn(a23, make_float2(b2.z, b2.w), acc[r][1]);
+          acc[r][2] = __ffma2_rn(a23, make_float2(b3.x, b3.y), acc[r][2]);
+          acc[r][3] = __ffma2_rn(a23, make_float2(b3.z, b3.w), acc[r][3]);
         }
       }
     }
@@ -288,11 +302,27 @@ __device__ __forceinline__ void ring_gemm(const float* __restrict__ A, int lda, 
     if (lane == 0)  // this warp is done with the slot
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cta_smem_u32(&rg.empty[buf])) : "memory");
   }
-  if (active) {
+  if (grp == 1 && active) {
 #pragma unroll
     for (int r = 0; r < TM; ++r) {
       const int row = rgi * TM + r;
-      if (row < M) epi(r, row, cg * 4, acc[r]);
+      if (row < M)
+        *reinterpret_cast<float4*>(part + row * 128 + cg * 4) =
+            make_float4(acc[r][0].x + acc[r][0].y, acc[r][1].x + acc[r][1].y, acc[r][2].x + acc[r][2].y,
+                        acc[r][3].x + acc[r][3].y);
+    }
+  }
+  ste_bar();
+  if (grp == 0 && active) {
+#pragma unroll
+    for (int r = 0; r < TM; ++r) {
+      const int row = rgi * TM + r;
+      if (row < M) {
+        const float4 p = *reinterpret_cast<const float4*>(part + row * 128 + cg * 4);
+        float v[4] = {(acc[r][0].x + acc[r][0].y) + p.x, (acc[r][1].x + acc[r][1].y) + p.y,
+                      (acc[r][2].x + acc[r][2].y) + p.z, (acc[r][3].x + acc[r][3].y) + p.w};
+        epi(r, row, cg * 4, v);
+      }
     }
   }
   rg.it += nslab;
@@ -303,10 +333,11 @@ __device__ __forceinline__ void ring_gemm(const float* __restrict__ A, int lda, 
 template <int MODE>  // 0: store, 1: store GELU, 2: out += result
 __device__ __forceinline__ void ste_linear(const float* __restrict__ in, int ldin, int K,
                                            const float* __restrict__ bias, int N, float* __restrict__ out, int ldout,
-                                           WRing& rg) {
+                                           WRing& rg, float* __restrict__ part) {
   for (int cb = 0; cb < N; cb += 128) {
     const int NC = min(128, N - cb);
-    ring_gemm<6>(in, ldin, NT, K, NC, rg, [&](int, int row, int c0, float (&v)[4]) {
+    if (cb) ste_bar();  // `part` of the previous column block has been consumed
+    ring_gemm<6>(in, ldin, NT, K, NC, rg, part, [&](int, int row, int c0, float (&v)[4]) {
       const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + cb + c0));
       float4 o = make_float4(v[0] + bb.x, v[1] + bb.y, v[2] + bb.z, v[3] + bb.w);
       if (MODE == 1) {
@@ -348,27 +379,29 @@ __global__ void __launch_bounds__(STE_THREADS) ste_kernel(const float* __restric
   float* ring = sm;                        // [4][32][128] weight slabs
   float* x = ring + RING_D * SLAB_FLOATS;  // [42][128] residual stream
   float* h = x + NT * 128;                 // [42][128] LN output / attention output
-  float* big = h + NT * 128;               // [42][384] qkv, later [42][256] MLP hidden
-  float* sc = big + NT * 384;              // [4][42][44] attention probabilities
-  uint64_t* full = reinterpret_cast<uint64_t*>(sc + 4 * NT * SC_LD);
+  float* big = h + NT * 128;               // [42][388] qkv, later [42][256] MLP hidden
+  float* sc = big + NT * QLD;              // [16 warps][48] one attention probability row per warp
+  float* part = sc + 16 * 48;              // [42][128] partial sums of consumer group 1
+  uint64_t* full = reinterpret_cast<uint64_t*>(part + NT * 128);
   uint64_t* empty = full + RING_D;
   WSeg* segs = reinterpret_cast<WSeg*>(empty + RING_D);
   const int b = blockIdx.x, tid = threadIdx.x;
   if (tid == 0) {
     for (int i = 0; i < RING_D; ++i) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cta_smem_u32(&full[i])));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cta_smem_u32(&empty[i])), "r"(STE_CONSUMERS / 32));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cta_smem_u32(&empty[i])), "r"(STE_GROUP / 32));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     int n = 0;
     for (int l = 0; l < 3; ++l) {  // consumption order of ste_linear calls below
       const SteWeights::Block& B = w.blk[l];
-      for (int cb = 0; cb < 384; cb += 128) segs[n++] = WSeg{B.qkv_t + cb, 384, 4, 128};
-      segs[n++] = WSeg{B.proj_t, 128, 4, 128};
-      for (int cb = 0; cb < 256; cb += 128) segs[n++] = WSeg{B.fc1_t + cb, 256, 4, 128};
-      segs[n++] = WSeg{B.fc2_t, 128, 8, 128};
+      // k-pair interleaved weights [K/2][N][2]: a row (one k-pair) is 2N floats, column block cb starts at 2*cb
+      for (int cb = 0; cb < 384; cb += 128) segs[n++] = WSeg{B.qkv_t + 2 * cb, 2 * 384, 4, 128};
+      segs[n++] = WSeg{B.proj_t, 2 * 128, 4, 128};
+      for (int cb = 0; cb < 256; cb += 128) segs[n++] = WSeg{B.fc1_t + 2 * cb, 2 * 256, 4, 128};
+      segs[n++] = WSeg{B.fc2_t, 2 * 128, 8, 128};
     }
-    segs[n++] = WSeg{w.head_t, 64, 4, 64};
+    segs[n++] = WSeg{w.head_t, 2 * 64, 4, 64};
   }
   __syncthreads();
   if (tid >= STE_CONSUMERS) {  // producer warp
@@ -382,63 +415,57 @@ __global__ void __launch_bounds__(STE_THREADS) ste_kernel(const float* __restric
     const SteWeights::Block& B = w.blk[l];
     ste_layernorm(x, h, B.n1w, B.n1b, 1e-6f);
     ste_bar();
-    ste_linear<0>(h, 128, 128, B.qkv_b, 384, big, 384, rg);
+    ste_linear<0>(h, 128, 128, B.qkv_b, 384, big, QLD, rg, part);
     ste_bar();
-    // scores = q k^T * 32^-0.5
-    for (int item = tid; item < 4 * NT * NT; item += STE_CONSUMERS) {
-      int j = item % NT, t = item / NT;
-      int i = t % NT, hd = t / NT;
-      const float* q = big + i * 384 + hd * 32;
-      const float* k = big + j * 384 + 128 + hd * 32;
-      float s2 = 0.f;
-#pragma unroll
-      for (int d = 0; d < 32; d += 4) {
-        float4 a4 = *reinterpret_cast<const float4*>(q + d);
-        float4 b4 = *reinterpret_cast<const float4*>(k + d);
-        s2 = fmaf(a4.x, b4.x, s2); s2 = fmaf(a4.y, b4.y, s2); s2 = fmaf(a4.z, b4.z, s2); s2 = fmaf(a4.w, b4.w, s2);
-      }
-      sc[(hd * NT + i) * SC_LD + j] = s2 * 0.17677669529663688110f;
-    }
-    ste_bar();
-    {  // softmax rows
+    {  // attention, one warp per (head, query token): scores -> softmax -> P·V without leaving the warp
       const int warp = tid >> 5, lane = tid & 31;
+      float* prow = sc + warp * 48;
       for (int r = warp; r < 4 * NT; r += STE_CONSUMERS / 32) {
-        float* row = sc + r * SC_LD;
-        float v0 = row[lane], v1 = (lane + 32 < NT) ? row[lane + 32] : -INFINITY;
-        float mx = warp_max(fmaxf(v0, v1));
-        float e0 = expf(v0 - mx), e1 = (lane + 32 < NT) ? expf(v1 - mx) : 0.f;
-        float inv = 1.f / warp_sum(e0 + e1);
-        row[lane] = e0 * inv;
-        if (lane + 32 < NT) row[lane + 32] = e1 * inv;
+        const int hd = r / NT, i = r - hd * NT;
+        const float* q = big + i * QLD + hd * 32;
+        const int j1 = lane + 32;
+        const float* k0 = big + lane * QLD + 128 + hd * 32;
+        const float* k1 = big + min(j1, NT - 1) * QLD + 128 + hd * 32;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int d = 0; d < 32; d += 4) {
+          const float4 q4 = *reinterpret_cast<const float4*>(q + d);
+          const float4 a4 = *reinterpret_cast<const float4*>(k0 + d);
+          const float4 b4 = *reinterpret_cast<const float4*>(k1 + d);
+          s0 = fmaf(q4.x, a4.x, s0); s0 = fmaf(q4.y, a4.y, s0); s0 = fmaf(q4.z, a4.z, s0); s0 = fmaf(q4.w, a4.w, s0);
+          s1 = fmaf(q4.x, b4.x, s1); s1 = fmaf(q4.y, b4.y, s1); s1 = fmaf(q4.z, b4.z, s1); s1 = fmaf(q4.w, b4.w, s1);
+        }
+        s0 *= 0.17677669529663688110f;  // 32^-0.5 (mixSTE.py:59)
+        s1 = (j1 < NT) ? s1 * 0.17677669529663688110f : -INFINITY;
+        const float mx = warp_max(fmaxf(s0, s1));
+        const float e0 = expf(s0 - mx), e1 = (j1 < NT) ? expf(s1 - mx) : 0.f;
+        const float inv = 1.f / warp_sum(e0 + e1);
+        prow[lane] = e0 * inv;
+        if (j1 < NT) prow[j1] = e1 * inv;
+        __syncwarp();
+        const float* v = big + 256 + hd * 32 + lane;  // lane = channel of this head
+        float o = 0.f;
+#pragma unroll 6
+        for (int j = 0; j < NT; ++j) o = fmaf(prow[j], v[j * QLD], o);
+        h[i * 128 + hd * 32 + lane] = o;
+        __syncwarp();
       }
     }
     ste_bar();
-    // o = P v  -> h[i][hd*32+d]
-    for (int item = tid; item < NT * 128; item += STE_CONSUMERS) {
-      int c = item & 127, i = item >> 7;
-      int hd = c >> 5;
-      const float* p = sc + (hd * NT + i) * SC_LD;
-      const float* v = big + 256 + c;
-      float s2 = 0.f;
-#pragma unroll 6
-      for (int j = 0; j < NT; ++j) s2 = fmaf(p[j], v[j * 384], s2);
-      h[item] = s2;
-    }
-    ste_bar();
-    ste_linear<2>(h, 128, 128, B.proj_b, 128, x, 128, rg);
+    ste_linear<2>(h, 128, 128, B.proj_b, 128, x, 128, rg, part);
     ste_bar();
     ste_layernorm(x, h, B.n2w, B.n2b, 1e-6f);
     ste_bar();
-    ste_linear<1>(h, 128, 128, B.fc1_b, 256, big, 256, rg);
+    ste_linear<1>(h, 128, 128, B.fc1_b, 256, big, 256, rg, part);
     ste_bar();
-    ste_linear<2>(big, 256, 256, B.fc2_b, 128, x, 128, rg);
+    ste_linear<2>(big, 256, 256, B.fc2_b, 128, x, 128, rg, part);
     ste_bar();
     ste_layernorm(x, x, w.snw, w.snb, 1e-6f);  // shared spatial_norm (mixSTE.py:200), in place (row-local)
     ste_bar();
   }
   ste_layernorm(x, h, w.hnw, w.hnb, 1e-5f);
   ste_bar();
-  ste_linear<0>(h, 128, 128, w.head_b, 64, big, 64, rg);
+  ste_linear<0>(h, 128, 128, w.head_b, 64, big, 64, rg, part);
   ste_bar();
   for (int i = tid; i < NT * 64; i += STE_CONSUMERS) yout[(int64_t)b * NT * 64 + i] = big[i];
 }

@@ -44,6 +44,7 @@ void launch_fold_affine(const float* conv_bias, const float* gamma, const float*
 void launch_pack_conv_weight(const float* src, float* dst32, __nv_bfloat16* dst16, int Cout, int Cin, int kh, int kw,
                              int Kpad, cudaStream_t st);
 void launch_transpose2d(const float* src, float* dst, int rows, int cols, cudaStream_t st);  // dst[c][r]=src[r][c]
+void launch_transpose_pairs(const float* src /*[N][K]*/, float* dst /*[K/2][N][2]*/, int N, int K, cudaStream_t st);
 void launch_gcn_adjacency(const float* e1, float* A /*21x21*/, cudaStream_t st);
 
 // ---------------------------------------------------------------- init regressor
@@ -108,6 +109,7 @@ void launch_gcn_finish(const GcnFinishArgs& a, cudaStream_t st);
 struct SteWeights {
   const float* pos;  // (42,128)
   struct Block {
+    // *_t weights are k-pair interleaved K-major: [K/2][N][2] (launch_transpose_pairs)
     const float *n1w, *n1b, *qkv_t, *qkv_b, *proj_t, *proj_b, *n2w, *n2b, *fc1_t, *fc1_b, *fc2_t, *fc2_b;
   } blk[3];
   const float *snw, *snb, *hnw, *hnb, *head_t, *head_b;
