@@ -32,9 +32,10 @@ namespace dirb200 {
 namespace {
 
 constexpr int BM = 128;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // producer warp + MMA warp + 2 epilogue groups of 4 warps
 constexpr int MAX_STAGES = 8;
 constexpr int CHUNK_BYTES = BM * 128;  // one 64-column bf16 epilogue box: 16 KB
+constexpr int RES_BUFS = 4;            // residual ring: the producer prefetches residual chunks ~2 tiles ahead
 
 struct TcArgs {
   const float* scale;
@@ -124,7 +125,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier(int group) {  // named barrier of one 128-thread epilogue group
+  asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
 
 template <int BN, int SW>
 struct TcCfg {
@@ -137,7 +140,7 @@ struct TcCfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN;
   static constexpr int NCH = BN / 64;
   static int smem_bytes(int stages, int has_res) {
-    return 1024 + stages * STAGE_BYTES + 2 * CHUNK_BYTES + (has_res ? 2 * CHUNK_BYTES : 0) + 2 * BN * 4 + 256;
+    return 1024 + stages * STAGE_BYTES + 2 * CHUNK_BYTES + (has_res ? RES_BUFS * CHUNK_BYTES : 0) + 4 * BN * 4 + 256;
   }
 };
 
@@ -152,16 +155,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sA = smem;
   uint8_t* sB = sA + stages * Cfg::A_STAGE;
   uint8_t* sOut = sB + stages * Cfg::B_STAGE;             // 2 x 16 KB output staging (128B-swizzled boxes)
-  uint8_t* sRes = sOut + 2 * CHUNK_BYTES;                 // 2 x 16 KB residual staging (only if has_res)
-  float* s_scale = reinterpret_cast<float*>(sRes + (a.has_res ? 2 * CHUNK_BYTES : 0));  // [BN] current n-tile
-  float* s_shift = s_scale + BN;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN);
+  uint8_t* sRes = sOut + 2 * CHUNK_BYTES;                 // RES_BUFS x 16 KB residual ring (only if has_res)
+  float* s_affine = reinterpret_cast<float*>(sRes + (a.has_res ? RES_BUFS * CHUNK_BYTES : 0));  // [2 groups][2][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_affine + 4 * BN);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + MAX_STAGES;
   uint64_t* tmem_full = bars + 2 * MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_full = tmem_empty + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_full + 2);
+  uint64_t* res_empty = res_full + RES_BUFS;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty + RES_BUFS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = a.m_tiles * a.n_tiles;
@@ -177,8 +180,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 256);
+    }
+    for (int i = 0; i < RES_BUFS; ++i) {
       mbar_init(&res_full[i], 1);
+      mbar_init(&res_empty[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -196,12 +202,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {  // ===================== TMA producer
       int s = 0;
-      uint32_t ph = 0;
+      uint32_t ph = 0, rchunk = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m0 = (tile / a.n_tiles) * BM, n0 = (tile % a.n_tiles) * BN;
         const int wo0 = m0 % a.Wo;
         const int ho0 = (m0 / a.Wo) % a.Ho;
         const int b0 = m0 / (a.Wo * a.Ho);
+        if (a.has_res) {  // residual chunks of this tile, into the residual ring (freed by the epilogue)
+          for (int c = 0; c < Cfg::NCH; ++c, ++rchunk) {
+            const uint32_t rb = rchunk % RES_BUFS;
+            mbar_wait(&res_empty[rb], ((rchunk / RES_BUFS) & 1) ^ 1);
+            mbar_expect_tx(&res_full[rb], CHUNK_BYTES);
+            tma_load_2d(&tmR, &res_full[rb], sRes + rb * CHUNK_BYTES, n0 + c * 64, m0);
+          }
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
@@ -250,60 +264,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (128 threads); warp w may touch TMEM lanes 32*(w%4) .. +31
-    const int et = threadIdx.x - 64;
+    // ===================== epilogue: two groups of 4 warps take alternate 64-column chunks (global chunk parity),
+    // each with its own staging buffer, named barrier and bulk-store groups, so one group's TMEM->smem->TMA chain
+    // overlaps the other's. Warp w may touch TMEM lanes 32*(w%4) .. +31.
+    const int eg = (warp - 2) >> 2;
+    const int et = (threadIdx.x - 64) & 127;
     const int lane_base = (warp & 3) * 32;
     const int row = lane_base + lane;
     const uint32_t swz = (uint32_t)(row & 7);
-    uint32_t chunk_it = 0;  // running 64-column chunk counter (staging buffer / parity selection)
-    // residual prefetch runs two chunks ahead of the math across tile boundaries: global chunk g of this CTA
-    // is chunk (g % NCH) of its (g / NCH)-th tile
-    const uint32_t my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const uint32_t my_chunks = my_tiles * Cfg::NCH;
-    auto issue_res = [&](uint32_t g) {
-      const int t = (int)blockIdx.x + (int)(g / Cfg::NCH) * (int)gridDim.x;
-      const int c = (int)(g % Cfg::NCH);
-      const uint32_t rb = g & 1;
-      mbar_expect_tx(&res_full[rb], CHUNK_BYTES);
-      tma_load_2d(&tmR, &res_full[rb], sRes + rb * CHUNK_BYTES, (t % a.n_tiles) * BN + c * 64, (t / a.n_tiles) * BM);
-    };
-    if (a.has_res && et == 0) {
-      if (my_chunks > 0) issue_res(0);
-      if (my_chunks > 1) issue_res(1);
-    }
+    float* s_scale = s_affine + eg * 2 * BN;
+    float* s_shift = s_scale + BN;
+    uint8_t* sOutG = sOut + eg * CHUNK_BYTES;
     int i = 0;
     int cur_n0 = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
       const int m0 = (tile / a.n_tiles) * BM, n0 = (tile % a.n_tiles) * BN;
       const int buf = i & 1;
-      if (n0 != cur_n0) {  // (re)stage the per-channel affine of this n-tile; readers are past barrier (d)
+      if (n0 != cur_n0) {  // (re)stage the per-channel affine of this n-tile; the group's readers are past (d)
         for (int j = et; j < BN; j += 128) {
           s_scale[j] = a.scale[n0 + j];
           s_shift[j] = a.shift[n0 + j];
         }
         cur_n0 = n0;
-        epi_barrier();
+        epi_barrier(eg);
       }
       mbar_wait(&tmem_full[buf], (i >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int c = 0; c < Cfg::NCH; ++c, ++chunk_it) {
+      for (int c = 0; c < Cfg::NCH; ++c) {
+        const uint32_t rchunk = (uint32_t)i * Cfg::NCH + c;  // global chunk index of this CTA
+        if ((int)(rchunk & 1) != eg) continue;
         uint32_t r[64];
         const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + buf * BN + c * 64;
         tmem_ld32(taddr, r);
         tmem_ld32(taddr + 32, r + 32);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c == Cfg::NCH - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(&tmem_empty[buf]);
-        }
         const float* sc = s_scale + c * 64;
         const float* sh = s_shift + c * 64;
-        const uint32_t ob = chunk_it & 1;
         uint4 packed[8];
         if (a.has_res) {
-          mbar_wait(&res_full[ob], (chunk_it >> 1) & 1);
-          const uint8_t* rrow = sRes + ob * CHUNK_BYTES + row * 128;
+          const uint32_t rb = rchunk % RES_BUFS;
+          mbar_wait(&res_full[rb], (rchunk / RES_BUFS) & 1);
+          const uint8_t* rrow = sRes + rb * CHUNK_BYTES + row * 128;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const uint4 u = *reinterpret_cast<const uint4*>(rrow + ((q ^ swz) << 4));
@@ -360,20 +362,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int e = 0; e < 4; ++e) hp[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
           }
         }
-        // (a) the TMA store that last used staging buffer `ob` (two chunks ago) must have read it
-        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        epi_barrier();  // (b)
-        uint8_t* orow = sOut + ob * CHUNK_BYTES + row * 128;
+        // (a) this group's previous TMA store must have finished reading its staging buffer
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        epi_barrier(eg);  // (b)
+        uint8_t* orow = sOutG + row * 128;
 #pragma unroll
         for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(orow + ((q ^ swz) << 4)) = packed[q];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // (c) generic-proxy writes -> async proxy
-        epi_barrier();  // (d) staging complete; every thread is also done reading residual buffer `ob`
+        epi_barrier(eg);  // (d) staging complete; every thread of the group is also done reading its residual slot
         if (et == 0) {
-          tma_store_2d(&tmY, sOut + ob * CHUNK_BYTES, n0 + c * 64, m0);
+          tma_store_2d(&tmY, sOutG, n0 + c * 64, m0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          if (a.has_res && chunk_it + 2 < my_chunks) issue_res(chunk_it + 2);  // into the buffer just released
+          if (a.has_res) mbar_arrive(&res_empty[rchunk % RES_BUFS]);  // every thread is past its residual reads
         }
       }
+      // this thread has read everything it needs from accumulator buffer `buf` (256 arrivals hand it back to the MMA warp)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tmem_empty[buf]);
     }
     if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output bytes written
   }
@@ -539,7 +544,8 @@ int conv_tc_prepare_weights(ConvLayer& L) {
   L.wmap_bn = 0;
   EncodeTiledFn enc = get_encode();
   if (!enc || L.Cin % 64 != 0 || L.Cout % 64 != 0 || L.K != L.Kpad) return 0;
-  const int bn = pick_bn(L.Cout);
+  int bn = pick_bn(L.Cout);
+  if (bn > L.tc_bn_cap) bn = L.tc_bn_cap;
   cuuint64_t dims[2] = {(cuuint64_t)L.Kpad, (cuuint64_t)L.Cout};
   cuuint64_t strides[1] = {(cuuint64_t)L.Kpad * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)bn};

@@ -169,6 +169,10 @@ ResidualBlock Engine::make_residual(const std::string& p) {
   r.c1 = make_conv(p + "conv1.conv.weight", p + "conv1.conv.bias", p + "bn2.", 1, 0, 1);
   r.c2 = make_conv(p + "conv2.conv.weight", p + "conv2.conv.bias", p + "bn3.", 1, 1, 1);
   r.c3 = make_conv(p + "conv3.conv.weight", p + "conv3.conv.bias", "", 1, 0, 0);
+  if (!dry && bf16() && r.c3.w16) {
+    r.c3.tc_bn_cap = 128;
+    conv_tc_prepare_weights(r.c3);
+  }
   r.skip = make_conv(p + "skip_layer.conv.weight", p + "skip_layer.conv.bias", "", 1, 0, 0);
   r.cin = r.c1.Cin;
   r.cout = r.c3.Cout;
@@ -309,6 +313,10 @@ int Engine::build(cudaStream_t st) {
       bk.c1 = make_conv(p + "conv1.weight", "", p + "bn1.", 1, 0, 1);
       bk.c2 = make_conv(p + "conv2.weight", "", p + "bn2.", stride, 1, 1);
       bk.c3 = make_conv(p + "conv3.weight", "", p + "bn3.", 1, 0, 1);
+      if (!dry && bf16() && bk.c3.w16) {  // residual-adding layer: smaller n-tile leaves room for the residual ring
+        bk.c3.tc_bn_cap = 128;
+        conv_tc_prepare_weights(bk.c3);
+      }
       bk.has_ds = (b == 0);
       if (bk.has_ds) bk.ds = make_conv(p + "downsample.0.weight", "", p + "downsample.1.", stride, 0, 0);
       layers[l].push_back(bk);
