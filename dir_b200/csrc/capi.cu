@@ -144,6 +144,27 @@ extern "C" int dirb200_forward(dirb200_handle* h, const float* img, int batch, v
   return rc;
 }
 
+extern "C" int dirb200_forward_u8(dirb200_handle* h, const unsigned char* img_bgr, int batch, void* workspace,
+                                  size_t workspace_bytes, const dirb200_outputs* out, void* stream) {
+  if (!h) return DIRB200_E_INVALID;
+  if (!img_bgr) {
+    h->e.err = "bad forward_u8 argument";
+    return DIRB200_E_INVALID;
+  }
+  h->e.img_u8 = img_bgr;
+  int rc = dirb200_forward(h, reinterpret_cast<const float*>(img_bgr), batch, workspace, workspace_bytes, out, stream);
+  h->e.img_u8 = nullptr;
+  return rc;
+}
+
+extern "C" int dirb200_preprocess_u8(dirb200_handle* h, const unsigned char* img_bgr, int batch, int height, int width,
+                                     float* out_nchw, void* stream) {
+  H_CHECK(h);
+  if (!img_bgr || !out_nchw || batch <= 0 || height <= 0 || width <= 0) return fail(e, DIRB200_E_INVALID, "bad argument");
+  launch_preprocess_u8(img_bgr, out_nchw, batch, height, width, reinterpret_cast<cudaStream_t>(stream));
+  return DIRB200_OK;
+}
+
 extern "C" int dirb200_forward_launches(const dirb200_handle* h, int) { return h ? h->e.last_forward_launches : 0; }
 
 extern "C" int dirb200_profile_layer(dirb200_handle* h, const char* prefix) {

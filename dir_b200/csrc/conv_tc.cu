@@ -414,6 +414,32 @@ __global__ void stem_pack_kernel(const float* __restrict__ img, __nv_bfloat16* _
   *reinterpret_cast<uint2*>(out + idx * 4) = u;
 }
 
+// uint8 HWC BGR image -> the same padded NHWC4 bf16 operand, with the reference's preprocessing fused in
+// (apps/eval.py:56-61: BGR->RGB, /255, ImageNet mean/std)
+__global__ void stem_pack_u8_kernel(const unsigned char* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H,
+                                    int W) {
+  const int Wp = W + 8;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * H * Wp) return;
+  int wp = (int)(idx % Wp);
+  int64_t t = idx / Wp;
+  int h = (int)(t % H);
+  int b = (int)(t / H);
+  int w = wp - 3;
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+  if (w >= 0 && w < W) {
+    const unsigned char* p = img + (((int64_t)b * H + h) * W + w) * 3;  // B, G, R
+    v0 = ((float)p[2] / 255.f - 0.485f) / 0.229f;
+    v1 = ((float)p[1] / 255.f - 0.456f) / 0.224f;
+    v2 = ((float)p[0] / 255.f - 0.406f) / 0.225f;
+  }
+  __nv_bfloat162 a = __floats2bfloat162_rn(v0, v1), c = __floats2bfloat162_rn(v2, 0.f);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&c);
+  *reinterpret_cast<uint2*>(out + idx * 4) = u;
+}
+
 // stem weights [64][3][7][7] fp32 -> [64][7*32] bf16 with k = ky*32 + kx*4 + c (zero elsewhere)
 __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -581,11 +607,14 @@ int conv_tc_prepare_stem(ConvLayer& L, const float* w_raw, __nv_bfloat16* w_pack
 
 size_t conv_tc_stem_scratch_bytes(int B, int H, int W) { return (size_t)B * H * (W + 8) * 4 * 2; }
 
-int launch_conv_tc_stem(const ConvLayer& L, const float* img, __nv_bfloat16* scratch, __nv_bfloat16* y, int B, int H,
-                        int W, cudaStream_t st) {
+int launch_conv_tc_stem(const ConvLayer& L, const float* img, const unsigned char* img_u8, __nv_bfloat16* scratch,
+                        __nv_bfloat16* y, int B, int H, int W, cudaStream_t st) {
   const int Wp = W + 8, Ho = H / 2, Wo = W / 2;
   const int64_t n = (int64_t)B * H * Wp;
-  stem_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(img, scratch, B, H, W);
+  if (img_u8)
+    stem_pack_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(img_u8, scratch, B, H, W);
+  else
+    stem_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(img, scratch, B, H, W);
   typedef std::tuple<const void*, int, int, int> Key;
   static thread_local MapCache<Key> cache;
   Key key(scratch, B, H, W);

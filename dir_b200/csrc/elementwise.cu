@@ -147,6 +147,25 @@ __global__ void __launch_bounds__(128) concat_preact_kernel(const T* __restrict_
   }
 }
 
+// ---------------------------------------------------------------- input pipeline (apps/eval.py:56-61): uint8 HWC BGR ->
+// RGB, /255, ImageNet mean/std, NCHW fp32. Same op order as torchvision Normalize: (x/255 - mean) / std.
+__device__ __forceinline__ float normalize_px(unsigned char v, int c) {
+  const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+  const float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+  return ((float)v / 255.f - mean) / sd;
+}
+
+__global__ void preprocess_u8_kernel(const unsigned char* __restrict__ img, float* __restrict__ out, int B, int HW) {
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)B * HW) return;
+  const unsigned b = idx / HW, p = idx - b * HW;
+  const unsigned char* px = img + (size_t)idx * 3;  // B, G, R
+  float* o = out + (size_t)b * 3 * HW + p;
+  o[0] = normalize_px(px[2], 0);
+  o[HW] = normalize_px(px[1], 1);
+  o[2 * (size_t)HW] = normalize_px(px[0], 2);
+}
+
 // ---------------------------------------------------------------- layout conversion (seam entry points, aux outputs)
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int B, int C, int HW) {
@@ -369,6 +388,10 @@ void launch_head3(const T* x, int Cx, int coff, int C, const float* w, const flo
                   cudaStream_t st) {
   int warps = B * HW;
   head3_kernel<T><<<ceil_div(warps * 32, 256), 256, 0, st>>>(x, Cx, coff, C, w, bias, out, B, HW);
+}
+
+void launch_preprocess_u8(const unsigned char* img, float* out, int B, int H, int W, cudaStream_t st) {
+  preprocess_u8_kernel<<<ceil_div(B * H * W, 256), 256, 0, st>>>(img, out, B, H * W);
 }
 
 void launch_fold_affine(const float* cb, const float* g, const float* be, const float* mu, const float* var,

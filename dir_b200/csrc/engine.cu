@@ -458,6 +458,7 @@ int Engine::run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** 
   const bool tc_stem = sizeof(T) == 2 && !disable_tc && conv_tc_supported(stem, B, H, W_);
   __nv_bfloat16* stem_scratch =
       tc_stem ? reinterpret_cast<__nv_bfloat16*>(ar.alloc(conv_tc_stem_scratch_bytes(B, H, W_))) : nullptr;
+  float* u8_scratch = tc_stem ? nullptr : aalloc<float>(ar, (int64_t)B * 3 * H * W_);  // fp32 image from uint8 frames
   T* stem_out = aalloc<T>(ar, (int64_t)B * H2 * W2 * 64);
   T* pool_out = aalloc<T>(ar, (int64_t)B * H4 * W4 * 64);
   const int64_t rsz = (int64_t)B * H4 * W4 * 256;
@@ -472,8 +473,14 @@ int Engine::run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** 
   if (!ar.base) return DIRB200_OK;
   if (ar.overflow) return DIRB200_E_WORKSPACE;
 
+  if (img_u8 && !tc_stem) {  // input pipeline (apps/eval.py:56-61) as its own pass on the CUDA-core path
+    launch_preprocess_u8(img_u8, u8_scratch, B, H, W_, st);
+    ++launches;
+    img = u8_scratch;
+  }
   if (tc_stem) {
-    int rc = launch_conv_tc_stem(stem, img, stem_scratch, reinterpret_cast<__nv_bfloat16*>(stem_out), B, H, W_, st);
+    int rc = launch_conv_tc_stem(stem, img, img_u8, stem_scratch, reinterpret_cast<__nv_bfloat16*>(stem_out), B, H, W_,
+                                 st);
     if (rc && !sticky_rc) {
       sticky_rc = rc;
       err = "tcgen05 stem launch failed";

@@ -98,6 +98,7 @@ struct Engine {
   bool disable_tc = false;  // DIRB200_DISABLE_TC=1: force the CUDA-core conv in bf16 mode (debug A/B)
   const ConvLayer* find_conv(const std::string& weight_key) const;
   void* nccl_comm = nullptr;
+  const unsigned char* img_u8 = nullptr;  // set by forward_u8: raw uint8 HWC BGR frames instead of the fp32 image
   // timing hook (bench.py roofline): CUDA events around every conv launch whose name starts with prof_prefix
   struct ProfRec {
     cudaEvent_t a, b;
@@ -170,7 +171,7 @@ int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y,
                    int H, int W, cudaStream_t st);
 int conv_tc_prepare_stem(ConvLayer& L, const float* w_raw, __nv_bfloat16* w_packed, cudaStream_t st);
 size_t conv_tc_stem_scratch_bytes(int B, int H, int W);
-int launch_conv_tc_stem(const ConvLayer& L, const float* img, __nv_bfloat16* scratch, __nv_bfloat16* y, int B, int H,
-                        int W, cudaStream_t st);
+int launch_conv_tc_stem(const ConvLayer& L, const float* img, const unsigned char* img_u8, __nv_bfloat16* scratch,
+                        __nv_bfloat16* y, int B, int H, int W, cudaStream_t st);
 
 }  // namespace dirb200

@@ -37,6 +37,9 @@ template <typename T>
 void launch_head3(const T* x, int Cx, int coff, int C, const float* w, const float* bias, float* out, int B, int HW,
                   cudaStream_t st);
 
+// uint8 (B,H,W,3) BGR -> normalised fp32 NCHW RGB (apps/eval.py:56-61)
+void launch_preprocess_u8(const unsigned char* img, float* out, int B, int H, int W, cudaStream_t st);
+
 // ---------------------------------------------------------------- weight packing (finalize time)
 void launch_fold_affine(const float* conv_bias, const float* gamma, const float* beta, const float* mean,
                         const float* var, float* scale, float* shift, int n, cudaStream_t st);

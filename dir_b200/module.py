@@ -185,8 +185,9 @@ class DIR(nn.Module):
                             o["seg"].data_ptr() if self.aux_outputs else None,
                             o["dense"].data_ptr() if self.aux_outputs else None,
                             o["proj_feat"].data_ptr() if self.aux_outputs else None)
-        rc = h.lib.dirb200_forward(h.h, C.c_void_p(x.data_ptr()), B, C.c_void_p(ws.data_ptr()), ws.numel(),
-                                   C.byref(outs), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        fwd = h.lib.dirb200_forward_u8 if x.dtype == torch.uint8 else h.lib.dirb200_forward
+        rc = fwd(h.h, C.c_void_p(x.data_ptr()), B, C.c_void_p(ws.data_ptr()), ws.numel(),
+                 C.byref(outs), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         h.check(rc, "dirb200_forward")
 
     def _run_chunk(self, x):
@@ -195,7 +196,8 @@ class DIR(nn.Module):
             o = self._alloc_outputs(B)
             self._enqueue(x, o)
             return o
-        if B not in self._graphs:
+        key = (B, x.dtype)
+        if key not in self._graphs:
             sx = torch.empty_like(x)
             so = self._alloc_outputs(B)
             sx.copy_(x)
@@ -204,8 +206,8 @@ class DIR(nn.Module):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._enqueue(sx, so)
-            self._graphs[B] = (g, sx, so)
-        g, sx, so = self._graphs[B]
+            self._graphs[key] = (g, sx, so)
+        g, sx, so = self._graphs[key]
         sx.copy_(x)
         g.replay()
         return {k: v.clone() for k, v in so.items()}
@@ -215,13 +217,14 @@ class DIR(nn.Module):
         dedicated copy stream instead (pinned memory => truly asynchronous), so the H2D copy of call i+1 overlaps
         the kernels of call i; the compute stream waits on an event, never the host."""
         dev = self._device()
+        dt = torch.uint8 if img.dtype == torch.uint8 else torch.float32
         if img.device.type == "cuda":
-            return img.to(device=dev, dtype=torch.float32).contiguous()
+            return img.to(device=dev, dtype=dt).contiguous()
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
         cur = torch.cuda.current_stream(dev)
         with torch.cuda.stream(self._copy_stream):
-            x = img.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+            x = img.to(device=dev, dtype=dt, non_blocking=True).contiguous()
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         cur.wait_event(ev)
@@ -233,8 +236,10 @@ class DIR(nn.Module):
         self._ensure_handle()
         if not self._packed:
             self._pack()
-        if img.dim() != 4 or tuple(img.shape[1:]) != (3, 256, 256):
-            raise ValueError(f"expected (B,3,256,256) images, got {tuple(img.shape)}")
+        u8 = img.dtype == torch.uint8
+        if img.dim() != 4 or tuple(img.shape[1:]) != ((256, 256, 3) if u8 else (3, 256, 256)):
+            raise ValueError("expected (B,3,256,256) float images (apps/eval.py:50-61) or raw (B,256,256,3) uint8 BGR "
+                             f"frames, got {tuple(img.shape)} {img.dtype}")
         x = self._to_device(img)
         with torch.cuda.device(self._device()):
             if x.shape[0] <= self.max_batch:

@@ -160,3 +160,13 @@ def conv_layer(model, weight_key, x, res=None):
     h.check(h.lib.dirb200_conv_layer(h.h, weight_key.encode(), _ptr(x), _ptr(res), B, H, W, _ptr(y), C.byref(used),
                                      _ptr(ws), ws.numel(), _stream()), "conv_layer")
     return y, used.value
+
+
+def preprocess_u8(model, frames):
+    """apps/eval.py:56-61 on the device: (B,H,W,3) uint8 BGR -> (B,3,H,W) fp32 normalised RGB."""
+    frames = frames.contiguous()
+    B, H, W, _ = frames.shape
+    h, _ = _prep(model, B)
+    out = torch.empty(B, 3, H, W, device=frames.device)
+    h.check(h.lib.dirb200_preprocess_u8(h.h, _ptr(frames), B, H, W, _ptr(out), _stream()), "preprocess_u8")
+    return out

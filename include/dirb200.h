@@ -92,6 +92,14 @@ const char* dirb200_required_key(const dirb200_handle* h, int i);
 int dirb200_workspace_bytes(const dirb200_handle* h, int batch, size_t* bytes);
 int dirb200_forward(dirb200_handle* h, const float* img, int batch, void* workspace, size_t workspace_bytes,
                     const dirb200_outputs* out, void* stream);
+/* Same forward fed with raw frames: img_bgr (B,256,256,3) uint8, HWC, BGR (what cv2 hands to apps/eval.py:56-61). The
+ * reference's host-side preprocessing (BGR->RGB, /255, ImageNet mean/std, HWC->CHW) runs on the device, fused into
+ * the stem operand packing in the bf16 configuration. 4x fewer host->device bytes than the fp32 image. */
+int dirb200_forward_u8(dirb200_handle* h, const unsigned char* img_bgr, int batch, void* workspace,
+                       size_t workspace_bytes, const dirb200_outputs* out, void* stream);
+/* The preprocessing alone: (B,H,W,3) uint8 BGR -> (B,3,H,W) fp32 normalised RGB (apps/eval.py:56-61). */
+int dirb200_preprocess_u8(dirb200_handle* h, const unsigned char* img_bgr, int batch, int height, int width,
+                          float* out_nchw, void* stream);
 /* number of kernels one dirb200_forward(batch) enqueues (for launch accounting) */
 int dirb200_forward_launches(const dirb200_handle* h, int batch);
 

@@ -361,3 +361,29 @@ def test_factored_fusion_equals_dense_path(synth_sd, X, monkeypatch):
     same = (pa != 0) == (pb != 0)
     assert float((~same).float().mean()) < 1e-4
     assert float(((pa - pb).abs() * same).max()) < 1e-4 * float(pb.abs().max())
+
+
+def _ref_preprocess(frames_u8):
+    """apps/eval.py:56-61 / dataset/interhand.py:223-225 with torch ops: BGR->RGB, /255, HWC->CHW, Normalize."""
+    rgb = frames_u8.flip(-1).float() / 255
+    x = rgb.permute(0, 3, 1, 2)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    return (x - mean) / std
+
+
+def test_u8_input_pipeline(m32, m16):
+    """Next-row N1: raw uint8 BGR frames in, preprocessing on the device."""
+    from dir_b200 import seams
+
+    frames = torch.randint(0, 256, (3, 256, 256, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(8))
+    want = _ref_preprocess(frames)
+    got = seams.preprocess_u8(m32, frames.cuda())
+    assert float((got.cpu() - want).abs().max()) < 2e-6
+    # whole forward: uint8 frames == the reference-preprocessed fp32 image
+    a = m32.run_raw(frames.cuda())["record"]
+    b = m32.run_raw(want.cuda())["record"]
+    assert rel(a, b) < 1e-5
+    outs, _ = m16({"img": frames}, None, None)  # host uint8 tensor through the public forward
+    c = m16.run_raw(want.cuda())["record"]
+    assert rel(outs[2]["pd_mesh_xyz_left"], m16.unpack_record(c)[2]["pd_mesh_xyz_left"]) < 2e-2
