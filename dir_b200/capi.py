@@ -22,7 +22,7 @@ EXPORTS = [
     "dirb200_num_required_keys", "dirb200_required_key", "dirb200_workspace_bytes", "dirb200_forward",
     "dirb200_forward_launches", "dirb200_backbone", "dirb200_residual", "dirb200_init_regressor", "dirb200_mano",
     "dirb200_joint2bone", "dirb200_bone_proj", "dirb200_nccl_unique_id", "dirb200_nccl_init",
-    "dirb200_allgather_records", "dirb200_profile_layer", "dirb200_profile_read", "dirb200_conv_layer", "dirb200_profile_dump", "dirb200_forward_u8", "dirb200_preprocess_u8",
+    "dirb200_allgather_records", "dirb200_profile_layer", "dirb200_profile_read", "dirb200_conv_layer", "dirb200_profile_dump", "dirb200_forward_u8", "dirb200_preprocess_u8", "dirb200_eval_metrics",
 ]
 
 
@@ -66,6 +66,7 @@ def load_library():
     lib.dirb200_forward.argtypes = [vp, vp, ip, vp, C.c_size_t, C.POINTER(Outputs), vp]
     lib.dirb200_forward_u8.argtypes = [vp, vp, ip, vp, C.c_size_t, C.POINTER(Outputs), vp]
     lib.dirb200_preprocess_u8.argtypes = [vp, vp, ip, ip, ip, vp, vp]
+    lib.dirb200_eval_metrics.argtypes = [vp, vp, vp, vp, vp, vp, ip, ip, vp, vp, vp, vp, vp, vp]
     lib.dirb200_forward_launches.argtypes = [vp, ip]
     lib.dirb200_backbone.argtypes = [vp, vp, ip, ip, ip, vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.dirb200_residual.argtypes = [vp, C.c_char_p, vp, ip, ip, ip, ip, vp, vp, C.c_size_t, vp]

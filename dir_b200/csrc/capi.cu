@@ -391,6 +391,19 @@ extern "C" int dirb200_conv_layer(dirb200_handle* h, const char* weight_key, con
   return rc;
 }
 
+extern "C" int dirb200_eval_metrics(dirb200_handle* h, const float* record, const float* gt_verts,
+                                    const float* gt_verts2d, const float* cam, const float* jreg21, int batch,
+                                    int use_scale, float* joint_err, float* vert_err, float* joint2d_err,
+                                    float* vert2d_err, float* root_err, void* stream) {
+  H_CHECK(h);
+  if (!record || !gt_verts || !gt_verts2d || !cam || !jreg21 || !joint_err || !vert_err || !joint2d_err || !vert2d_err ||
+      !root_err || batch <= 0)
+    return fail(e, DIRB200_E_INVALID, "bad eval_metrics argument");
+  launch_eval_metric(record, gt_verts, gt_verts2d, cam, jreg21, batch, use_scale, joint_err, vert_err, joint2d_err,
+                     vert2d_err, root_err, reinterpret_cast<cudaStream_t>(stream));
+  return DIRB200_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ NCCL (run-time bound)
 namespace {
 struct NcclId {

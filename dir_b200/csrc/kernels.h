@@ -173,4 +173,9 @@ void launch_bone_fusion(const float* stage_record, int rec_stride, const float* 
 void launch_bone_vis_nchw(const float* uv_l, const float* uv_r, int uv_stride, const float* feat_l, const float* feat_r,
                           int feat_stride, float* out, int B, int S, float distance, int add_right, cudaStream_t st);
 
+// eval metric (apps/eval.py:151-241) from the packed record (eval_metric.cu)
+void launch_eval_metric(const float* record, const float* gt_verts, const float* gt_verts2d, const float* cam,
+                        const float* jreg21, int B, int use_scale, float* joint_err, float* vert_err,
+                        float* joint2d_err, float* vert2d_err, float* root_err, cudaStream_t st);
+
 }  // namespace dirb200

@@ -170,3 +170,29 @@ def preprocess_u8(model, frames):
     out = torch.empty(B, 3, H, W, device=frames.device)
     h.check(h.lib.dirb200_preprocess_u8(h.h, _ptr(frames), B, H, W, _ptr(out), _stream()), "preprocess_u8")
     return out
+
+
+def eval_jregressor(jreg16):
+    """class Jr of apps/eval.py:22-44: (16,778) MANO joint regressor -> (21,778) incl. the 5 tip vertices, reordered."""
+    tips = torch.zeros(5, 778, device=jreg16.device)
+    for i, v in enumerate([745, 317, 444, 556, 673]):
+        tips[i, v] = 1.0
+    order = [0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20]
+    return torch.cat([jreg16.float(), tips], 0)[order].contiguous()
+
+
+def eval_metrics(model, record, gt_verts, gt_verts2d, cam, jreg21, scale=True):
+    """apps/eval.py:151-241 on the device. record (B,14661); gt_verts (B,2,778,3); gt_verts2d (B,2,778,2);
+    cam (B,3,3); jreg21 (2,21,778). Returns dict of per-sample error tensors (metres / pixels)."""
+    B = record.shape[0]
+    h, _ = _prep(model, B)
+    dev = record.device
+    args = [_f32(t) for t in (record, gt_verts, gt_verts2d, cam, jreg21)]
+    je, j2 = torch.empty(B, 2, 21, device=dev), torch.empty(B, 2, 21, device=dev)
+    ve, v2 = torch.empty(B, 2, 778, device=dev), torch.empty(B, 2, 778, device=dev)
+    re = torch.empty(B, device=dev)
+    h.check(h.lib.dirb200_eval_metrics(h.h, *[_ptr(a) for a in args], B, int(bool(scale)), _ptr(je), _ptr(ve), _ptr(j2),
+                                       _ptr(v2), _ptr(re), _stream()), "eval_metrics")
+    return {"joint_left": je[:, 0], "joint_right": je[:, 1], "vert_left": ve[:, 0], "vert_right": ve[:, 1],
+            "joint2d_left": j2[:, 0], "joint2d_right": j2[:, 1], "vert2d_left": v2[:, 0], "vert2d_right": v2[:, 1],
+            "root": re}

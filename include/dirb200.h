@@ -148,6 +148,15 @@ int dirb200_conv_layer(dirb200_handle* h, const char* weight_key, const float* x
                        int height, int width, float* y, int* used_tensor_cores, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* The evaluation metric of apps/eval.py:151-241 (root_joint = 0) computed on the device from the packed record of
+ * dirb200_forward: joints regressed from vertices with the 21x778 regressor of class Jr (apps/eval.py:22-44), wrist
+ * alignment, optional |j9-j0| scale alignment (opt.scale), L2 errors in metres and re-projection errors in pixels.
+ * record (B,RECORD); gt_verts (B,2,778,3); gt_verts2d (B,2,778,2); cam (B,3,3); jreg21 (2,21,778) [left,right].
+ * Outputs: joint_err, joint2d_err (B,2,21); vert_err, vert2d_err (B,2,778); root_err (B). */
+int dirb200_eval_metrics(dirb200_handle* h, const float* record, const float* gt_verts, const float* gt_verts2d,
+                         const float* cam, const float* jreg21, int batch, int use_scale, float* joint_err,
+                         float* vert_err, float* joint2d_err, float* vert2d_err, float* root_err, void* stream);
+
 /* Multi-GPU: images shard over ranks with no exchange inside the forward; the only
  * collective is one all-gather of the per-image records over NVLink (the reference has no distributed
  * code at all). The library resolves NCCL at run time (dlopen of the libnccl the host process already

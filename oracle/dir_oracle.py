@@ -423,3 +423,48 @@ def dir_forward(sd, img):
             outs.append(d)
         outs.append({"dense": dec["dense"], "seg": dec["seg"], "proj_feat": dec["proj_feat"]})
         return outs
+
+
+# --------------------------------------------------------------------------- eval metric (next row N2)
+def eval_jregressor(jreg16):
+    """apps/eval.py:27-41 (class Jr): 16-joint MANO regressor -> 21 joints (5 tip vertices appended, reordered).
+    Note: the reference uses tip vertex 444 for BOTH hands here (unlike manopth's 445 for the left hand)."""
+    tips = torch.zeros(5, jreg16.shape[1])
+    for i, v in enumerate([745, 317, 444, 556, 673]):
+        tips[i, v] = 1.0
+    return torch.cat([jreg16, tips], 0)[JOINT_REORDER].contiguous()
+
+
+def xyz2uvd(xyz, cam):
+    """apps/eval.py:80-83."""
+    p = xyz @ cam.permute(0, 2, 1)
+    return p[:, :, :2] / p[:, :, 2:]
+
+
+def eval_metrics(pred_verts, pred_offset, gt_verts, gt_verts2d, cam, jreg21, scale=True):
+    """apps/eval.py:151-241 for root_joint=0. pred_verts/gt_verts: dict side->(B,778,3); gt_verts2d: side->(B,778,2);
+    jreg21: side->(21,778). Returns per-sample error arrays like the lists the reference accumulates."""
+    out = {}
+    roots = {}
+    for side in ("left", "right"):
+        J = jreg21[side]
+        j_gt = J @ gt_verts[side]
+        j2d_gt = xyz2uvd(j_gt, cam)
+        root_gt = j_gt[:, 0:1].clone()
+        roots[side] = root_gt
+        len_gt = torch.linalg.norm(j_gt[:, 9] - j_gt[:, 0], dim=-1)
+        j_gt = j_gt - root_gt
+        v_gt = gt_verts[side] - root_gt
+        j_ori = J @ pred_verts[side]
+        root_p = j_ori[:, 0:1].clone()
+        len_p = torch.linalg.norm(j_ori[:, 9] - j_ori[:, 0], dim=-1)
+        sc = (len_gt / len_p).unsqueeze(-1).unsqueeze(-1) if scale else 1
+        j_p = (j_ori - root_p) * sc
+        v_p = (pred_verts[side] - root_p) * sc
+        out[f"joint_{side}"] = torch.linalg.norm(j_p - j_gt, dim=-1)
+        out[f"vert_{side}"] = torch.linalg.norm(v_p - v_gt, dim=-1)
+        out[f"vert2d_{side}"] = torch.linalg.norm(xyz2uvd(v_p + root_gt, cam) - gt_verts2d[side], dim=-1)
+        out[f"joint2d_{side}"] = torch.linalg.norm(xyz2uvd(j_p + root_gt, cam) - j2d_gt, dim=-1)
+    gt_offset = roots["right"] - roots["left"]
+    out["root"] = torch.linalg.norm(gt_offset - pred_offset.unsqueeze(1) * 0.15, dim=-1).reshape(-1)
+    return out

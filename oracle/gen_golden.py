@@ -64,8 +64,67 @@ def seam_inputs():
     }
 
 
+def eval_metric_inputs():
+    """Seeded inputs of the eval-metric seam (shared with the tests)."""
+    B = 3
+    gv = {s: rnd(40 + i, B, 778, 3, scale=0.05) + torch.tensor([0.0, 0.0, 0.6]) for i, s in enumerate(("left", "right"))}
+    pv = {s: gv[s] * 0.9 + rnd(42 + i, B, 778, 3, scale=0.004) - torch.tensor([0.01, 0.0, 0.55])
+          for i, s in enumerate(("left", "right"))}
+    cam = torch.tensor([[1400.0, 0, 128.0], [0, 1400.0, 128.0], [0, 0, 1.0]]).repeat(B, 1, 1)
+    gv2d = {s: rnd(44 + i, B, 778, 2, scale=30.0) + 128 for i, s in enumerate(("left", "right"))}
+    off = rnd(46, B, 3, scale=0.5)
+    jreg16 = {s: torch.from_numpy(__import__("dir_b200.synth", fromlist=["mano_buffers"]).mano_buffers(s)["th_J_regressor"])
+              for s in ("left", "right")}
+    return {"gt_verts": gv, "pred_verts": pv, "cam": cam, "gt_verts2d": gv2d, "pred_offset": off, "jreg16": jreg16}
+
+
+def run_reference_eval_lines(E):
+    """Execute apps/eval.py's own metric code (class Jr :22-44, xyz2uvd :80-83, loop body :140-241) on E."""
+    import textwrap
+    import types
+
+    src = open("/root/reference/apps/eval.py").read().replace("\r", "").split("\n")
+
+    def find(prefix, start=0):
+        return next(i for i in range(start, len(src)) if src[i].startswith(prefix))
+
+    ns = {"torch": torch, "np": np}
+    exec("\n".join(src[find("class Jr"):find("class handDataset")]), ns)  # apps/eval.py:22-44
+    i0 = find("def xyz2uvd")
+    exec("\n".join(src[i0:i0 + 4]), ns)  # apps/eval.py:80-83
+    B = E["cam"].shape[0]
+    ns["J_regressor"] = {s: ns["Jr"](E["jreg16"][s], device="cpu") for s in ("left", "right")}
+    ns["opt"] = types.SimpleNamespace(root_joint=0, scale=True)
+    ns["stage_num"] = 3
+    result = [None, None, {"pd_offset": E["pred_offset"], "pd_mesh_xyz_left": E["pred_verts"]["left"],
+                           "pd_mesh_xyz_right": E["pred_verts"]["right"]}]
+    ns["network"] = lambda inp, a, b: (result, None)
+    z = torch.zeros(B, 1)
+    ns["data"] = [z, z, z, E["gt_verts"]["left"], z, E["gt_verts"]["right"], z, E["gt_verts2d"]["left"], z,
+                  E["gt_verts2d"]["right"], E["cam"]]
+    for n in ("joints_loss", "verts_loss", "joints_xyz_list", "joints_xyz_gt_list", "joints_2d_loss", "verts_2d_loss"):
+        ns[n] = {"left": [], "right": []}
+    ns["root_loss_list"] = []
+    ns["idx"] = 0
+    b0 = find("        for data in tqdm(dataloader):") + 1
+    b1 = find("    joints_loss['left'] = np.concatenate")
+    body = textwrap.dedent("\n".join(src[b0:b1]))  # the loop body, apps/eval.py:140-241
+    exec(body, ns)
+    return {"joint_left": ns["joints_loss"]["left"][0], "joint_right": ns["joints_loss"]["right"][0],
+            "vert_left": ns["verts_loss"]["left"][0], "vert_right": ns["verts_loss"]["right"][0],
+            "joint2d_left": ns["joints_2d_loss"]["left"][0], "joint2d_right": ns["joints_2d_loss"]["right"][0],
+            "vert2d_left": ns["verts_2d_loss"]["left"][0], "vert2d_right": ns["verts_2d_loss"]["right"][0],
+            "root": ns["root_loss_list"][0].reshape(-1)}
+
+
 def main():
     ref = load_reference()
+    E = eval_metric_inputs()
+    gold = run_reference_eval_lines(E)
+    jr = {s: O.eval_jregressor(E["jreg16"][s]) for s in ("left", "right")}
+    om = O.eval_metrics(E["pred_verts"], E["pred_offset"], E["gt_verts"], E["gt_verts2d"], E["cam"], jr)
+    print("eval metric:", " ".join(f"{k} {rel(om[k], torch.as_tensor(v)):.1e}" for k, v in gold.items()))
+    save("eval_metric.npz", **gold)
     net = ref.dir.DIR(21, "./misc/mano")
     net.eval()
     shapes = {k: list(v.shape) for k, v in net.state_dict().items()}

@@ -387,3 +387,26 @@ def test_u8_input_pipeline(m32, m16):
     outs, _ = m16({"img": frames}, None, None)  # host uint8 tensor through the public forward
     c = m16.run_raw(want.cuda())["record"]
     assert rel(outs[2]["pd_mesh_xyz_left"], m16.unpack_record(c)[2]["pd_mesh_xyz_left"]) < 2e-2
+
+
+def test_eval_metric_kernel_vs_golden(m32, golden_dir):
+    """Next-row N2: device-side MPJPE/MPVPE/2-D/root errors vs the reference's own metric lines (apps/eval.py:151-241)."""
+    from dir_b200 import capi, seams
+    from oracle.gen_golden import eval_metric_inputs
+
+    E = eval_metric_inputs()
+    g = load(golden_dir, "eval_metric.npz")
+    B = E["cam"].shape[0]
+    rec = torch.zeros(B, capi.RECORD_FLOATS)
+    s2 = 2 * capi.STAGE_FLOATS
+    rec[:, s2 + capi.OFF["mesh_l"]:s2 + capi.OFF["mesh_l"] + 2334] = E["pred_verts"]["left"].reshape(B, -1)
+    rec[:, s2 + capi.OFF["mesh_r"]:s2 + capi.OFF["mesh_r"] + 2334] = E["pred_verts"]["right"].reshape(B, -1)
+    rec[:, s2 + capi.OFF["offset"]:s2 + capi.OFF["offset"] + 3] = E["pred_offset"]
+    gv = torch.stack((E["gt_verts"]["left"], E["gt_verts"]["right"]), 1)
+    g2 = torch.stack((E["gt_verts2d"]["left"], E["gt_verts2d"]["right"]), 1)
+    jr = torch.stack([seams.eval_jregressor(E["jreg16"][s]) for s in ("left", "right")])
+    out = seams.eval_metrics(m32, rec.cuda(), gv.cuda(), g2.cuda(), E["cam"].cuda(), jr.cuda())
+    for k in g.files:  # errors are differences of aligned coordinates: fp32 cancellation, ~5e-7 m absolute
+        assert rel(out[k], g[k]) < 1e-4, k
+    mpjpe = float(out["joint_left"].mean() * 1000)
+    assert abs(mpjpe - float(g["joint_left"].mean() * 1000)) < 0.01  # mm
