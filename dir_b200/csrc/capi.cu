@@ -62,6 +62,8 @@ extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
   {
     const char* dis = getenv("DIRB200_DISABLE_TC");
     h->e.disable_tc = dis && dis[0] == '1';
+    const char* nopair = getenv("DIRB200_NO_PAIR_FUSION");
+    h->e.disable_pair_fusion = nopair && nopair[0] == '1';
     const char* dense = getenv("DIRB200_DENSE_FUSION");
     h->e.dense_fusion = dense && dense[0] == '1';
   }

@@ -45,6 +45,7 @@ struct TcArgs {
   int taps, cblocks;  // K loop = taps * cblocks k-blocks
   int relu, has_res, stem;
   int m_tiles, n_tiles, stages;
+  int kb2, stride2;  // K-concatenated second operand: kb2 extra 1x1 k-blocks read from tmA2 at spatial stride2
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -147,7 +148,8 @@ struct TcCfg {
 template <int BN, int SW>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const TcArgs a) {
+               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmA2, const TcArgs a) {
   using Cfg = TcCfg<BN, SW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -168,7 +170,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = a.m_tiles * a.n_tiles;
-  const int nkb = a.taps * a.cblocks;
+  const int nkb1 = a.taps * a.cblocks;
+  const int nkb = nkb1 + a.kb2;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -222,6 +225,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (a.stem) {  // k-block = kernel row ky; overlapped view: {32 elems, wo (16 B apart), h, n}
             tma_load_4d(&tmA, &full_bar[s], sA + s * Cfg::A_STAGE, 0, wo0, ho0 * 2 + kb - 3, b0);
             tma_load_2d(&tmB, &full_bar[s], sB + s * Cfg::B_STAGE, kb * 32, n0);
+          } else if (kb >= nkb1) {  // second operand of a K-concatenated pair (1x1, own stride): skip / downsample conv
+            tma_load_4d(&tmA2, &full_bar[s], sA + s * Cfg::A_STAGE, (kb - nkb1) * 64, wo0 * a.stride2, ho0 * a.stride2,
+                        b0);
+            tma_load_2d(&tmB, &full_bar[s], sB + s * Cfg::B_STAGE, kb * 64, n0);
           } else {
             const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
             const int ky = tap / a.kw, kx = tap - ky * a.kw;
@@ -450,6 +457,24 @@ __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat
   out[idx] = __float2bfloat16_rn(v);
 }
 
+// dst[n][k] = k < K1 ? w1[n][k] * s1[n] : w2[n][k - K1] * s2[n]  (bf16); shift[n] = h1[n] + h2[n]; scale[n] = 1
+__global__ void pack_dual_weight_kernel(const float* __restrict__ w1, int K1, const float* __restrict__ s1,
+                                        const float* __restrict__ h1, const float* __restrict__ w2, int K2,
+                                        const float* __restrict__ s2, const float* __restrict__ h2,
+                                        __nv_bfloat16* __restrict__ dst, float* __restrict__ scale,
+                                        float* __restrict__ shift, int Cout) {
+  const int K = K1 + K2;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)Cout * K) return;
+  const int k = (int)(idx % K), n = (int)(idx / K);
+  const float v = k < K1 ? w1[(size_t)n * K1 + k] * s1[n] : w2[(size_t)n * K2 + (k - K1)] * s2[n];
+  dst[idx] = __float2bfloat16_rn(v);
+  if (k == 0) {
+    scale[n] = 1.f;
+    shift[n] = h1[n] + h2[n];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -508,10 +533,10 @@ bool make_rowmajor_map(CUtensorMap* tm, const void* ptr, int rows, int cols) {
 
 template <int BN, int SW>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
-              TcArgs a, cudaStream_t st) {
+              const CUtensorMap& tmA2, TcArgs a, cudaStream_t st) {
   using Cfg = TcCfg<BN, SW>;
   static int attr_bytes = 0;
-  const int nkb = a.taps * a.cblocks;
+  const int nkb = a.taps * a.cblocks + a.kb2;
   int stages = MAX_STAGES;
   while (stages > 1 && Cfg::smem_bytes(stages, a.has_res) > 227 * 1024) --stages;
   (void)nkb;  // the ring runs ahead across tiles, so short K loops still want every stage that fits
@@ -525,7 +550,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_tc_kernel<BN, SW><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmY, tmR, a);
+  conv_tc_kernel<BN, SW><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmY, tmR, tmA2, a);
   return DIRB200_OK;
 }
 
@@ -582,6 +607,29 @@ int conv_tc_prepare_weights(ConvLayer& L) {
   if (r != CUDA_SUCCESS) return DIRB200_E_CUDA;
   L.wmap_bn = bn;
   return DIRB200_OK;
+}
+
+// Build the K-concatenated layer of a (main 1x1, second 1x1) pair; `w16`, `scale`, `shift` are caller-allocated.
+int conv_tc_prepare_dual(ConvLayer& F, const ConvLayer& main, const ConvLayer& second, __nv_bfloat16* w16, float* scale,
+                         float* shift, cudaStream_t st) {
+  F = ConvLayer();
+  if (!get_encode() || main.kh != 1 || second.kh != 1 || main.Cout != second.Cout || main.Cin % 64 || second.Cin % 64 ||
+      main.Cout % 64)
+    return 0;
+  F.name = main.name + "+" + second.name;
+  F.Cin = main.Cin + second.Cin;
+  F.Cout = main.Cout;
+  F.K = F.Kpad = F.Cin;
+  F.relu = main.relu;
+  F.w16 = w16;
+  F.scale = scale;
+  F.shift = shift;
+  F.tc_bn_cap = 256;
+  const int64_t total = (int64_t)F.Cout * F.K;
+  pack_dual_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(main.w32, main.K, main.scale, main.shift,
+                                                                           second.w32, second.K, second.scale,
+                                                                           second.shift, w16, scale, shift, F.Cout);
+  return conv_tc_prepare_weights(F);
 }
 
 // Stem (7x7 s2, 3->64): pack weights as [64][7*32] bf16 (k = ky*32 + kx*4 + c) into `w_packed` (caller-allocated,
@@ -655,33 +703,75 @@ int launch_conv_tc_stem(const ConvLayer& L, const float* img, const unsigned cha
   a.stem = 1;
   a.m_tiles = (M + BM - 1) / BM;
   a.n_tiles = 1;
-  return launch_tc<64, 64>(*tmA, L.wmap, *tmY, *tmY, a, st);
+  return launch_tc<64, 64>(*tmA, L.wmap, *tmY, *tmY, *tmA, a, st);
+}
+
+namespace {
+// activation tensor map {C, W, H, N} with box {64, wbox*s, hbox*s, nbox}, cached per (pointer, geometry)
+const CUtensorMap* act_map_cached(const __nv_bfloat16* x, int B, int H, int W, int C, int stride, const Boxes& bx,
+                                  const char* name) {
+  typedef std::tuple<const void*, int, int, int, int, int, int, int, int> Key;
+  static thread_local MapCache<Key> cache;
+  Key key(x, B, H, W, C, stride, bx.wbox, bx.hbox, bx.nbox);
+  CUtensorMap* tm = cache.find(key);
+  if (tm) return tm;
+  CUtensorMap t;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(bx.wbox * stride), (cuuint32_t)(bx.hbox * stride), (cuuint32_t)bx.nbox};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = get_encode()(&t, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x), dims, strides, box,
+                            es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "dirb200: cuTensorMapEncodeTiled(A) failed: %d (layer %s)\n", (int)r, name);
+    return nullptr;
+  }
+  return cache.put(key, t);
+}
+}  // namespace
+
+// K-concatenated pair: y = act( [x1 | x2(strided)] . [W1 | W2]^T + shift ) — a 1x1 conv over x1 (spatial Ho x Wo) fused
+// with a 1x1 stride-`stride2` conv over x2 (the ResNet downsample / hourglass skip branch). L holds the concatenated,
+// BN-scale-folded weights [Cout][C1 + C2].
+int launch_conv_tc_dual(const ConvLayer& L, const __nv_bfloat16* x1, int C1, const __nv_bfloat16* x2, int C2,
+                        int stride2, __nv_bfloat16* y, int B, int Ho, int Wo, cudaStream_t st) {
+  const Boxes bx = pick_boxes(Ho, Wo);
+  const CUtensorMap* tmA = act_map_cached(x1, B, Ho, Wo, C1, 1, bx, L.name.c_str());
+  const CUtensorMap* tmA2 = act_map_cached(x2, B, Ho * stride2, Wo * stride2, C2, stride2, bx, L.name.c_str());
+  const int M = B * Ho * Wo;
+  const CUtensorMap* tmY = rowmajor_map_cached(y, M, L.Cout);
+  if (!tmA || !tmA2 || !tmY) return DIRB200_E_CUDA;
+  TcArgs a{};
+  a.scale = L.scale;
+  a.shift = L.shift;
+  a.M = M;
+  a.Cout = L.Cout;
+  a.Ho = Ho;
+  a.Wo = Wo;
+  a.stride = 1;
+  a.pad = 0;
+  a.kw = 1;
+  a.taps = 1;
+  a.cblocks = C1 / 64;
+  a.kb2 = C2 / 64;
+  a.stride2 = stride2;
+  a.relu = L.relu;
+  a.m_tiles = (M + BM - 1) / BM;
+  a.n_tiles = L.Cout / L.wmap_bn;
+  switch (L.wmap_bn) {
+    case 256: return launch_tc<256, 128>(*tmA, L.wmap, *tmY, *tmY, *tmA2, a, st);
+    case 128: return launch_tc<128, 128>(*tmA, L.wmap, *tmY, *tmY, *tmA2, a, st);
+    default: return launch_tc<64, 128>(*tmA, L.wmap, *tmY, *tmY, *tmA2, a, st);
+  }
 }
 
 int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bfloat16* res, int B,
                    int H, int W, cudaStream_t st) {
   const int Ho = (H + 2 * L.pad - L.kh) / L.stride + 1, Wo = (W + 2 * L.pad - L.kw) / L.stride + 1;
   const Boxes bx = pick_boxes(Ho, Wo);
-  // activation tensor map, cached per (pointer, geometry): encoding is host-only work
-  typedef std::tuple<const void*, int, int, int, int, int, int, int, int> Key;
-  static thread_local MapCache<Key> cache;
-  Key key(x, B, H, W, L.Cin, L.stride, bx.wbox, bx.hbox, bx.nbox);
-  CUtensorMap* tmA = cache.find(key);
-  if (!tmA) {
-    CUtensorMap tm;
-    cuuint64_t dims[4] = {(cuuint64_t)L.Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)L.Cin * 2, (cuuint64_t)W * L.Cin * 2, (cuuint64_t)H * W * L.Cin * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)(bx.wbox * L.stride), (cuuint32_t)(bx.hbox * L.stride), (cuuint32_t)bx.nbox};
-    cuuint32_t es[4] = {1, (cuuint32_t)L.stride, (cuuint32_t)L.stride, 1};
-    CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x), dims, strides,
-                              box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      fprintf(stderr, "dirb200: cuTensorMapEncodeTiled(A) failed: %d (layer %s)\n", (int)r, L.name.c_str());
-      return DIRB200_E_CUDA;
-    }
-    tmA = cache.put(key, tm);
-  }
+  const CUtensorMap* tmA = act_map_cached(x, B, H, W, L.Cin, L.stride, bx, L.name.c_str());
+  if (!tmA) return DIRB200_E_CUDA;
   const int M = B * Ho * Wo;
   const CUtensorMap* tmY = rowmajor_map_cached(y, M, L.Cout);
   const CUtensorMap* tmR = res ? rowmajor_map_cached(res, M, L.Cout) : tmY;
@@ -704,9 +794,9 @@ int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y,
   a.m_tiles = (M + BM - 1) / BM;
   a.n_tiles = L.Cout / L.wmap_bn;
   switch (L.wmap_bn) {
-    case 256: return launch_tc<256, 128>(*tmA, L.wmap, *tmY, *tmR, a, st);
-    case 128: return launch_tc<128, 128>(*tmA, L.wmap, *tmY, *tmR, a, st);
-    default: return launch_tc<64, 128>(*tmA, L.wmap, *tmY, *tmR, a, st);
+    case 256: return launch_tc<256, 128>(*tmA, L.wmap, *tmY, *tmR, *tmA, a, st);
+    case 128: return launch_tc<128, 128>(*tmA, L.wmap, *tmY, *tmR, *tmA, a, st);
+    default: return launch_tc<64, 128>(*tmA, L.wmap, *tmY, *tmR, *tmA, a, st);
   }
 }
 

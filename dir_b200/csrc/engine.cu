@@ -152,6 +152,16 @@ ConvLayer Engine::make_conv(const std::string& wname, const std::string& bias, c
   return L;
 }
 
+void Engine::make_dual(ConvLayer& F, const ConvLayer& main, const ConvLayer& second) {
+  F = ConvLayer();
+  if (dry || !bf16() || !err.empty() || !main.w32 || !second.w32) return;
+  const size_t K = (size_t)main.K + second.K;
+  __nv_bfloat16* w16 = reinterpret_cast<__nv_bfloat16*>(dalloc(((size_t)main.Cout * K + 1) / 2));
+  float* sc = dalloc(main.Cout);
+  float* sh = dalloc(main.Cout);
+  if (w16 && sc && sh) conv_tc_prepare_dual(F, main, second, w16, sc, sh, fin_stream);
+}
+
 PointMlp Engine::make_mlp(const std::string& p, int cin, int cmid, int cout) {
   PointMlp m{};
   m.w1t = transposed(p + "0.weight", cmid, cin);
@@ -177,6 +187,7 @@ ResidualBlock Engine::make_residual(const std::string& p) {
   r.cin = r.c1.Cin;
   r.cout = r.c3.Cout;
   r.need_skip = r.cin != r.cout;  // hourglass.py:49-52
+  if (r.need_skip) make_dual(r.c3skip, r.c3, r.skip);
   fold("", p + "bn1.", &r.bn1s, &r.bn1b, r.cin);  // pre-activation BN, applied by concat_preact
   return r;
 }
@@ -318,7 +329,10 @@ int Engine::build(cudaStream_t st) {
         conv_tc_prepare_weights(bk.c3);
       }
       bk.has_ds = (b == 0);
-      if (bk.has_ds) bk.ds = make_conv(p + "downsample.0.weight", "", p + "downsample.1.", stride, 0, 0);
+      if (bk.has_ds) {
+        bk.ds = make_conv(p + "downsample.0.weight", "", p + "downsample.1.", stride, 0, 0);
+        make_dual(bk.c3ds, bk.c3, bk.ds);
+      }
       layers[l].push_back(bk);
     }
   }
@@ -446,6 +460,45 @@ void Engine::conv(const ConvLayer& L, const T* x, T* y, const T* resid, int B, i
   if (pr) cudaEventRecord(pr->b, st);
 }
 
+// conv3 + (downsample | skip) as one K-concatenated tensor-core GEMM; returns false if the pair must run separately
+template <typename T>
+bool Engine::conv_pair(const ConvLayer& F, const ConvLayer& main, const ConvLayer& second, const T* x1, const T* x2,
+                       T* y, int B, int Ho, int Wo, cudaStream_t st) {
+  if (sizeof(T) != 2 || disable_tc || disable_pair_fusion || F.wmap_bn == 0) return false;
+  ConvLayer probe = F;  // same geometry checks as a 1x1 stride-1 conv on the output grid
+  probe.kh = probe.kw = 1;
+  probe.stride = 1;
+  probe.pad = 0;
+  if (!conv_tc_supported(probe, B, Ho, Wo)) return false;
+  ++launches;
+  ++tc_launches;
+  Engine::ProfRec* pr = nullptr;
+  if (prof_on && F.name.compare(0, prof_prefix.size(), prof_prefix) == 0) {
+    if (prof_used == prof.size()) {
+      ProfRec r;
+      cudaEventCreate(&r.a);
+      cudaEventCreate(&r.b);
+      prof.push_back(r);
+    }
+    pr = &prof[prof_used++];
+    pr->flops = 2.0 * B * Ho * Wo * (double)F.Cout * F.K;
+    pr->bytes = 2.0 * ((double)B * Ho * Wo * main.Cin + (double)B * Ho * Wo * second.stride * second.stride * second.Cin +
+                       (double)B * Ho * Wo * F.Cout + (double)F.Cout * F.K);
+    pr->layer = &F;
+    pr->tc = 1;
+    cudaEventRecord(pr->a, st);
+  }
+  int rc = launch_conv_tc_dual(F, reinterpret_cast<const __nv_bfloat16*>(x1), main.Cin,
+                               reinterpret_cast<const __nv_bfloat16*>(x2), second.Cin, second.stride,
+                               reinterpret_cast<__nv_bfloat16*>(y), B, Ho, Wo, st);
+  if (pr) cudaEventRecord(pr->b, st);
+  if (rc && !sticky_rc) {
+    sticky_rc = rc;
+    err = "tcgen05 paired conv launch failed for " + F.name;
+  }
+  return true;
+}
+
 template <typename T>
 static T* aalloc(Arena& ar, int64_t n) {
   return reinterpret_cast<T*>(ar.alloc((size_t)n * sizeof(T)));
@@ -505,14 +558,16 @@ int Engine::run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** 
       const bool last = b + 1 == layers[l].size();
       if (last && keep[l]) out = keep[l];
       const int ho = h / bk.c2.stride, wo = w / bk.c2.stride;
-      const T* identity = x;
-      if (bk.has_ds) {
-        conv<T>(bk.ds, x, dsb, nullptr, B, h, w, st);
-        identity = dsb;
-      }
       conv<T>(bk.c1, x, t1, nullptr, B, h, w, st);
       conv<T>(bk.c2, t1, t2, nullptr, B, h, w, st);
-      conv<T>(bk.c3, t2, out, identity, B, ho, wo, st);
+      if (!(bk.has_ds && conv_pair<T>(bk.c3ds, bk.c3, bk.ds, t2, x, out, B, ho, wo, st))) {
+        const T* identity = x;
+        if (bk.has_ds) {
+          conv<T>(bk.ds, x, dsb, nullptr, B, h, w, st);
+          identity = dsb;
+        }
+        conv<T>(bk.c3, t2, out, identity, B, ho, wo, st);
+      }
       x = out;
       xi = (last && keep[l]) ? -1 : idx[3];
       h = ho;
@@ -537,6 +592,7 @@ T* Engine::run_residual(const ResidualBlock& r, const T* rawx, const T* act, int
   if (!ar.base || ar.overflow) return nullptr;
   conv<T>(r.c1, act, t1, nullptr, B, H, W_, st);
   conv<T>(r.c2, t1, t2, nullptr, B, H, W_, st);
+  if (r.need_skip && conv_pair<T>(r.c3skip, r.c3, r.skip, t2, rawx, out, B, H, W_, st)) return out;
   const T* resid = rawx;
   if (r.need_skip) {
     conv<T>(r.skip, rawx, sk, nullptr, B, H, W_, st);

@@ -40,6 +40,7 @@ struct ConvLayer {
 struct Bottleneck {
   ConvLayer c1, c2, c3, ds;
   bool has_ds = false;
+  ConvLayer c3ds;  // tensor-core path: conv3 and the downsample conv as one K-concatenated GEMM (wmap_bn > 0 if built)
 };
 
 struct ResidualBlock {  // hourglass Residual
@@ -47,6 +48,7 @@ struct ResidualBlock {  // hourglass Residual
   bool need_skip = true;
   float *bn1s = nullptr, *bn1b = nullptr;
   ConvLayer c1, c2, c3, skip;
+  ConvLayer c3skip;  // tensor-core path: conv3 and the skip conv as one K-concatenated GEMM
 };
 
 struct StageWeights {
@@ -95,6 +97,7 @@ struct Engine {
   int tc_launches = 0;      // convs that went to the tcgen05 kernel since the last forward() start
   int sticky_rc = 0;        // first launch error inside a forward
   bool dense_fusion = false;  // DIRB200_DENSE_FUSION=1: materialise bone_proj and run the dense 2560-ch conv
+  bool disable_pair_fusion = false;  // DIRB200_NO_PAIR_FUSION=1: keep conv3 and skip/downsample as separate launches
   bool disable_tc = false;  // DIRB200_DISABLE_TC=1: force the CUDA-core conv in bf16 mode (debug A/B)
   const ConvLayer* find_conv(const std::string& weight_key) const;
   void* nccl_comm = nullptr;
@@ -149,6 +152,10 @@ struct Engine {
   template <typename T>
   void conv(const ConvLayer& L, const T* x, T* y, const T* res, int B, int H, int W_, cudaStream_t st,
             bool in_nchw = false);
+  void make_dual(ConvLayer& F, const ConvLayer& main, const ConvLayer& second);
+  template <typename T>
+  bool conv_pair(const ConvLayer& F, const ConvLayer& main, const ConvLayer& second, const T* x1, const T* x2, T* y,
+                 int B, int Ho, int Wo, cudaStream_t st);
   template <typename T>
   int run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** c1, T** c2, T** c3, T** c4, cudaStream_t st);
   template <typename T>
@@ -169,6 +176,10 @@ bool conv_tc_supported(const ConvLayer& L, int B, int H, int W);
 int conv_tc_prepare_weights(ConvLayer& L);  // builds L.wmap
 int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bfloat16* res, int B,
                    int H, int W, cudaStream_t st);
+int conv_tc_prepare_dual(ConvLayer& F, const ConvLayer& main, const ConvLayer& second, __nv_bfloat16* w16, float* scale,
+                         float* shift, cudaStream_t st);
+int launch_conv_tc_dual(const ConvLayer& L, const __nv_bfloat16* x1, int C1, const __nv_bfloat16* x2, int C2,
+                        int stride2, __nv_bfloat16* y, int B, int Ho, int Wo, cudaStream_t st);
 int conv_tc_prepare_stem(ConvLayer& L, const float* w_raw, __nv_bfloat16* w_packed, cudaStream_t st);
 size_t conv_tc_stem_scratch_bytes(int B, int H, int W);
 int launch_conv_tc_stem(const ConvLayer& L, const float* img, const unsigned char* img_u8, __nv_bfloat16* scratch,

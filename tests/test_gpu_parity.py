@@ -410,3 +410,24 @@ def test_eval_metric_kernel_vs_golden(m32, golden_dir):
         assert rel(out[k], g[k]) < 1e-4, k
     mpjpe = float(out["joint_left"].mean() * 1000)
     assert abs(mpjpe - float(g["joint_left"].mean() * 1000)) < 0.01  # mm
+
+
+def test_pair_fused_convs_match_separate_launches(synth_sd, X, monkeypatch):
+    """bf16 path: conv3 + (downsample | skip) as ONE K-concatenated tcgen05 GEMM vs two launches with a residual add.
+    Same math up to bf16 rounding of the scale-folded weights and of the (no longer materialised) branch output."""
+    fused = _make(synth_sd, "bf16", max_batch=4)
+    monkeypatch.setenv("DIRB200_NO_PAIR_FUSION", "1")
+    sep = _make(synth_sd, "bf16", max_batch=4)
+    sep._ensure_handle()
+    monkeypatch.delenv("DIRB200_NO_PAIR_FUSION")
+    from dir_b200 import seams
+
+    img = X["img"][:1]
+    fa, fb = seams.backbone(fused, img.cuda()), seams.backbone(sep, img.cuda())
+    for a, b in zip(fa, fb):
+        assert float((a - b).abs().mean() / b.abs().mean()) < 1e-2
+    ra, rb = fused.run_raw(X["img"].cuda())["record"], sep.run_raw(X["img"].cuda())["record"]
+    assert rel(ra, rb) < 5e-2
+    n_fused = fused._handle.lib.dirb200_forward_launches(fused._handle.h, 2)
+    n_sep = sep._handle.lib.dirb200_forward_launches(sep._handle.h, 2)
+    assert n_fused == n_sep - 10  # 4 downsample + 6 skip convs disappear
