@@ -45,6 +45,7 @@ struct TcArgs {
   int taps, cblocks;  // K loop = taps * cblocks k-blocks
   int relu, has_res, stem;
   int m_tiles, n_tiles, stages;
+  int raster_m;      // 1: consecutive tiles walk m first (weights larger than activations: keep an n-tile's weights hot)
   int kb2, stride2;  // K-concatenated second operand: kb2 extra 1x1 k-blocks read from tmA2 at spatial stride2
 };
 
@@ -207,7 +208,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0, rchunk = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / a.n_tiles) * BM, n0 = (tile % a.n_tiles) * BN;
+        const int m0 = (a.raster_m ? tile % a.m_tiles : tile / a.n_tiles) * BM;
+        const int n0 = (a.raster_m ? tile / a.m_tiles : tile % a.n_tiles) * BN;
         const int wo0 = m0 % a.Wo;
         const int ho0 = (m0 / a.Wo) % a.Ho;
         const int b0 = m0 / (a.Wo * a.Ho);
@@ -285,7 +287,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int i = 0;
     int cur_n0 = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
-      const int m0 = (tile / a.n_tiles) * BM, n0 = (tile % a.n_tiles) * BN;
+      const int m0 = (a.raster_m ? tile % a.m_tiles : tile / a.n_tiles) * BM;
+        const int n0 = (a.raster_m ? tile / a.m_tiles : tile % a.n_tiles) * BN;
       const int buf = i & 1;
       if (n0 != cur_n0) {  // (re)stage the per-channel affine of this n-tile; the group's readers are past (d)
         for (int j = et; j < BN; j += 128) {
@@ -793,6 +796,7 @@ int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y,
   a.stem = 0;
   a.m_tiles = (M + BM - 1) / BM;
   a.n_tiles = L.Cout / L.wmap_bn;
+  a.raster_m = (double)L.Cout * L.K > (double)B * H * W * L.Cin ? 1 : 0;
   switch (L.wmap_bn) {
     case 256: return launch_tc<256, 128>(*tmA, L.wmap, *tmY, *tmR, *tmA, a, st);
     case 128: return launch_tc<128, 128>(*tmA, L.wmap, *tmY, *tmR, *tmA, a, st);
