@@ -18,7 +18,7 @@ import os
 import torch
 import torch.nn as nn
 
-from . import capi
+from . import assets, capi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _KEYS_JSON = os.path.join(_HERE, "state_dict_keys.json")
@@ -101,6 +101,13 @@ class DIR(nn.Module):
                 m.register_parameter(parts[-1], nn.Parameter(t, requires_grad=False))
         self._handle = None
         self._loaded_keys = None
+        # manolayer.py:62-101 reads MANO_{LEFT,RIGHT}.pkl at construction; the released checkpoint also embeds the
+        # same buffers, so the pickles are optional here: read them when they exist, else expect them in the state_dict
+        self._asset_keys = set()
+        if assets.has_mano_pickles(mano_path):
+            mano_state = assets.mano_state_from_dir(mano_path)
+            super().load_state_dict(mano_state, strict=False)
+            self._asset_keys = set(mano_state)
         self._packed = False
         self._workspace = {}
         self._graphs = {}
@@ -111,10 +118,17 @@ class DIR(nn.Module):
         """Same call as the reference (apps/eval.py:107-108 uses strict=False). Unlike nn.Module we do
         not let strict=False hide a key the kernels need: that raises unless allow_missing=True."""
         res = super().load_state_dict(state_dict, strict=strict, **kw)
-        self._loaded_keys = None if allow_missing else set(state_dict.keys())
+        self._loaded_keys = None if allow_missing else set(state_dict.keys()) | self._asset_keys
         self._packed = False
         self._graphs.clear()
         return res
+
+    def load_checkpoint(self, path, strict=False):
+        """apps/eval.py:107-108 in one call: torch.load(path)['net'] (DataParallel prefixes stripped) -> load_state_dict.
+        Returns the missing/unexpected key report."""
+        state, report = assets.read_checkpoint(path, expected_keys=reference_key_shapes().keys())
+        self.load_state_dict(state, strict=strict)
+        return report
 
     def _apply(self, fn, *a, **k):
         self._packed = False
