@@ -133,6 +133,8 @@ class DIR(nn.Module):
     def _apply(self, fn, *a, **k):
         self._packed = False
         self._graphs = {}
+        self._copy_stream = None  # staging ring and copy stream belong to the old device
+        self._staging = {}
         return super()._apply(fn, *a, **k)
 
     def _device(self):
@@ -228,22 +230,42 @@ class DIR(nn.Module):
 
     def _to_device(self, img):
         """models/dir.py:514 does `input['img'].cuda()` on the compute stream. Host tensors are uploaded on a
-        dedicated copy stream instead (pinned memory => truly asynchronous), so the H2D copy of call i+1 overlaps
-        the kernels of call i; the compute stream waits on an event, never the host."""
+        dedicated copy stream into a two-slot staging ring owned by the module (no allocator traffic, pinned
+        memory => truly asynchronous), so the H2D copy of call i+1 overlaps the kernels of call i; the compute
+        stream waits on an event, never the host. Returns (device tensor, ring slot or None)."""
         dev = self._device()
         dt = torch.uint8 if img.dtype == torch.uint8 else torch.float32
         if img.device.type == "cuda":
-            return img.to(device=dev, dtype=dt).contiguous()
+            return img.to(device=dev, dtype=dt).contiguous(), None
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staging = {}
+        key = (tuple(img.shape), dt)
+        ring = self._staging.get(key)
+        if ring is None:
+            if len(self._staging) >= 4:  # shapes seen long ago: let the allocator have the memory back
+                self._staging.clear()
+            ring = self._staging[key] = {"buf": [torch.empty(img.shape, dtype=dt, device=dev) for _ in range(2)],
+                                         "free": [None, None], "next": 0}
+        slot = ring["next"]
+        ring["next"] = slot ^ 1
+        buf = ring["buf"][slot]
         cur = torch.cuda.current_stream(dev)
         with torch.cuda.stream(self._copy_stream):
-            x = img.to(device=dev, dtype=dt, non_blocking=True).contiguous()
+            if ring["free"][slot] is not None:  # the forward that last read this slot must be done with it
+                self._copy_stream.wait_event(ring["free"][slot])
+            buf.copy_(img, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         cur.wait_event(ev)
-        x.record_stream(cur)
-        return x
+        return buf, (ring, slot)
+
+    def _release_staging(self, token):
+        if token is not None:
+            ring, slot = token
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self._device()))
+            ring["free"][slot] = ev
 
     def run_raw(self, img):
         """img (B,3,256,256) on the module's device -> dict of packed output buffers (record, mano_para, ...)."""
@@ -254,12 +276,15 @@ class DIR(nn.Module):
         if img.dim() != 4 or tuple(img.shape[1:]) != ((256, 256, 3) if u8 else (3, 256, 256)):
             raise ValueError("expected (B,3,256,256) float images (apps/eval.py:50-61) or raw (B,256,256,3) uint8 BGR "
                              f"frames, got {tuple(img.shape)} {img.dtype}")
-        x = self._to_device(img)
         with torch.cuda.device(self._device()):
-            if x.shape[0] <= self.max_batch:
-                return self._run_chunk(x)
-            parts = [self._run_chunk(x[i:i + self.max_batch]) for i in range(0, x.shape[0], self.max_batch)]
-            return {k: torch.cat([p[k] for p in parts], 0) for k in parts[0]}
+            x, token = self._to_device(img)
+            try:
+                if x.shape[0] <= self.max_batch:
+                    return self._run_chunk(x)
+                parts = [self._run_chunk(x[i:i + self.max_batch]) for i in range(0, x.shape[0], self.max_batch)]
+                return {k: torch.cat([p[k] for p in parts], 0) for k in parts[0]}
+            finally:
+                self._release_staging(token)
 
     @staticmethod
     def unpack_record(record, aux=None):
