@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdirb200.so")
+LIB_PATH = os.environ.get("DIRB200_LIB") or os.path.join(_HERE, "libdirb200.so")  # override: A/B of builds
 
 PRECISION = {"fp32": 0, "bf16": 1}
 DTYPE_F32, DTYPE_I64 = 0, 1

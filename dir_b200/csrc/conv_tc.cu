@@ -202,6 +202,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {  // ===================== TMA producer
@@ -402,6 +403,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // NCHW fp32 image -> zero-padded NHWC4 bf16: out[b][h][w + 3][c], row pitch (W + 8) pixels (stem operand)
 __global__ void stem_pack_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+  pdl_wait();
   const int Wp = W + 8;
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)B * H * Wp) return;
@@ -428,6 +430,7 @@ __global__ void stem_pack_kernel(const float* __restrict__ img, __nv_bfloat16* _
 // (apps/eval.py:56-61: BGR->RGB, /255, ImageNet mean/std)
 __global__ void stem_pack_u8_kernel(const unsigned char* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H,
                                     int W) {
+  pdl_wait();
   const int Wp = W + 8;
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)B * H * Wp) return;
@@ -553,7 +556,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_tc_kernel<BN, SW><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmY, tmR, tmA2, a);
+  launch_pdl(conv_tc_kernel<BN, SW>, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, tmY, tmR, tmA2, a);
   return DIRB200_OK;
 }
 
@@ -663,9 +666,9 @@ int launch_conv_tc_stem(const ConvLayer& L, const float* img, const unsigned cha
   const int Wp = W + 8, Ho = H / 2, Wo = W / 2;
   const int64_t n = (int64_t)B * H * Wp;
   if (img_u8)
-    stem_pack_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(img_u8, scratch, B, H, W);
+    launch_pdl(stem_pack_u8_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, img_u8, scratch, B, H, W);
   else
-    stem_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(img, scratch, B, H, W);
+    launch_pdl(stem_pack_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, img, scratch, B, H, W);
   typedef std::tuple<const void*, int, int, int> Key;
   static thread_local MapCache<Key> cache;
   Key key(scratch, B, H, W);

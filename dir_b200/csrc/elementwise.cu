@@ -47,6 +47,7 @@ struct Vec8<__nv_bfloat16> {
 // one thread = one output pixel x 8 channels; C/8 consecutive threads share a pixel (coalesced 16B accesses)
 template <typename T>
 __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo) {
+  pdl_wait();
   const int C8 = C >> 3;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned total = (unsigned)B * Ho * Wo * C8;
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(128) concat_preact_kernel(const T* __restrict_
                                                             const float* __restrict__ bns,
                                                             const float* __restrict__ bnb, T* __restrict__ raw,
                                                             T* __restrict__ act, int Ho, int Wo) {
+  pdl_wait();
   const int C = C0 + C1;
   const unsigned pix = blockIdx.x;
   const int wo = pix % Wo;
@@ -156,6 +158,7 @@ __device__ __forceinline__ float normalize_px(unsigned char v, int c) {
 }
 
 __global__ void preprocess_u8_kernel(const unsigned char* __restrict__ img, float* __restrict__ out, int B, int HW) {
+  pdl_wait();
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (unsigned)B * HW) return;
   const unsigned b = idx / HW, p = idx - b * HW;
@@ -203,6 +206,7 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
 template <typename T>
 __global__ void head3_kernel(const T* __restrict__ x, int Cx, int coff, int C, const float* __restrict__ w,
                              const float* __restrict__ bias, float* __restrict__ out, int B, int HW) {
+  pdl_wait();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= B * HW) return;
@@ -312,6 +316,7 @@ __global__ void gcn_adjacency_kernel(const float* __restrict__ e1, float* __rest
 template <typename T>
 __global__ void attn_logits_kernel(const T* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
                                    float* __restrict__ attn, int BP, int C) {
+  pdl_wait();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= BP * 2) return;
@@ -331,6 +336,7 @@ __global__ void attn_logits_kernel(const T* __restrict__ a, const float* __restr
 template <typename T>
 __global__ void attn_pool_kernel(const T* __restrict__ f, const float* __restrict__ attn, float* __restrict__ pooled,
                                  int P, int C) {
+  pdl_wait();
   extern __shared__ float sa[];  // [P][2]
   int b = blockIdx.x;
   for (int i = threadIdx.x; i < P * 2; i += blockDim.x) sa[i] = attn[(int64_t)b * P * 2 + i];
@@ -360,7 +366,7 @@ template <typename T>
 void launch_maxpool3x3s2(const T* x, T* y, int B, int H, int W, int C, cudaStream_t st) {
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   int64_t total = (int64_t)B * Ho * Wo * (C / 8);
-  maxpool_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(x, y, B, H, W, C, Ho, Wo);
+  launch_pdl(maxpool_kernel<T>, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, st, x, y, B, H, W, C, Ho, Wo);
 }
 
 template <typename T>
@@ -368,7 +374,7 @@ void launch_concat_preact(const T* s0, int C0, int up0, const T* s1, int C1, con
                           T* act, int B, int Ho, int Wo, cudaStream_t st) {
   const int C = C0 + C1;
   const int threads = C >= 1024 ? 128 : (C >= 512 ? 64 : 32);
-  concat_preact_kernel<T><<<(unsigned)(B * Ho * Wo), threads, 0, st>>>(s0, C0, up0, s1, C1, bns, bnb, raw, act, Ho, Wo);
+  launch_pdl(concat_preact_kernel<T>, dim3((unsigned)(B * Ho * Wo)), dim3(threads), 0, st, s0, C0, up0, s1, C1, bns, bnb, raw, act, Ho, Wo);
 }
 
 template <typename T>
@@ -387,11 +393,11 @@ template <typename T>
 void launch_head3(const T* x, int Cx, int coff, int C, const float* w, const float* bias, float* out, int B, int HW,
                   cudaStream_t st) {
   int warps = B * HW;
-  head3_kernel<T><<<ceil_div(warps * 32, 256), 256, 0, st>>>(x, Cx, coff, C, w, bias, out, B, HW);
+  launch_pdl(head3_kernel<T>, dim3(ceil_div(warps * 32, 256)), dim3(256), 0, st, x, Cx, coff, C, w, bias, out, B, HW);
 }
 
 void launch_preprocess_u8(const unsigned char* img, float* out, int B, int H, int W, cudaStream_t st) {
-  preprocess_u8_kernel<<<ceil_div(B * H * W, 256), 256, 0, st>>>(img, out, B, H * W);
+  launch_pdl(preprocess_u8_kernel, dim3(ceil_div(B * H * W, 256)), dim3(256), 0, st, img, out, B, H * W);
 }
 
 void launch_fold_affine(const float* cb, const float* g, const float* be, const float* mu, const float* var,
@@ -420,12 +426,12 @@ template <typename T>
 void launch_attn_logits(const T* a, const float* w, const float* bias, float* attn, int B, int P, int C,
                         cudaStream_t st) {
   int warps = B * P * 2;
-  attn_logits_kernel<T><<<ceil_div(warps * 32, 256), 256, 0, st>>>(a, w, bias, attn, B * P, C);
+  launch_pdl(attn_logits_kernel<T>, dim3(ceil_div(warps * 32, 256)), dim3(256), 0, st, a, w, bias, attn, B * P, C);
 }
 
 template <typename T>
 void launch_attn_pool(const T* f, const float* attn, float* pooled, int B, int P, int C, cudaStream_t st) {
-  attn_pool_kernel<T><<<B, 256, P * 2 * sizeof(float), st>>>(f, attn, pooled, P, C);
+  launch_pdl(attn_pool_kernel<T>, dim3(B), dim3(256), P * 2 * sizeof(float), st, f, attn, pooled, P, C);
 }
 
 #define INST(T)                                                                                                      \

@@ -7,6 +7,14 @@
 
 namespace dirb200 {
 
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DIRB200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 #define CK(expr)                                                                 \
   do {                                                                           \
     cudaError_t _e = (expr);                                                     \

@@ -82,6 +82,7 @@ __global__ void pack_fusion_weight_kernel(const float* __restrict__ w, float* __
 // grid (40, 9, ceil(2B/64)), 256 threads (n); 64 rows (b,role) per CTA.
 __global__ void __launch_bounds__(256) bone_coef_kernel(const float* __restrict__ jf, const float* __restrict__ wp,
                                                         float* __restrict__ P, int B) {
+  pdl_wait();
   extern __shared__ __align__(128) float dyn_smem[];  // weight stream: 2 x 32 x 128 floats + 2 mbarriers
   WStream ws;
   wstream_init(ws, dyn_smem, reinterpret_cast<uint64_t*>(dyn_smem + 2 * 32 * 128));
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(256) bone_fusion_kernel(const float* __restric
                                                           const float* __restrict__ P, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, T* __restrict__ out,
                                                           float distance) {
+  pdl_wait();
   constexpr int LOG2S = S == 32 ? 5 : 4;
   static_assert(S == 16 || S == 32, "feature map sizes of projecter_4 / projecter_3 (models/dir.py:395,401)");
   extern __shared__ __align__(16) uint8_t smraw[];
@@ -284,7 +286,7 @@ void launch_bone_coef(const float* jf, const float* wp, float* P, int B, cudaStr
     cudaFuncSetAttribute(bone_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr = true;
   }
-  bone_coef_kernel<<<dim3(40, 9, ceil_div(2 * B, 64)), 256, 2 * 32 * 128 * 4 + 16, st>>>(jf, wp, P, B);
+  launch_pdl(bone_coef_kernel, dim3(dim3(40, 9, ceil_div(2 * B, 64))), dim3(256), 2 * 32 * 128 * 4 + 16, st, jf, wp, P, B);
 }
 
 template <typename T>
@@ -297,11 +299,11 @@ void launch_bone_fusion(const float* rec, int rec_stride, const float* P, const 
   if (S == 32) {
     if (!attr[ti][si]) cudaFuncSetAttribute(bone_fusion_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr[ti][si] = true;
-    bone_fusion_kernel<T, 32><<<dim3(B, S), 256, smem, st>>>(rec, rec_stride, P, scale, shift, out, distance);
+    launch_pdl(bone_fusion_kernel<T, 32>, dim3(dim3(B, S)), dim3(256), smem, st, rec, rec_stride, P, scale, shift, out, distance);
   } else {
     if (!attr[ti][si]) cudaFuncSetAttribute(bone_fusion_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr[ti][si] = true;
-    bone_fusion_kernel<T, 16><<<dim3(B, S), 256, smem, st>>>(rec, rec_stride, P, scale, shift, out, distance);
+    launch_pdl(bone_fusion_kernel<T, 16>, dim3(dim3(B, S)), dim3(256), smem, st, rec, rec_stride, P, scale, shift, out, distance);
   }
 }
 template void launch_bone_fusion<float>(const float*, int, const float*, const float*, const float*, float*, int, int,

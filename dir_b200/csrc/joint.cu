@@ -17,6 +17,7 @@ constexpr int NJ = 21;
 // =================================================================== joint_embed
 template <typename T>
 __global__ void __launch_bounds__(128) joint_embed_kernel(EmbedArgs a) {
+  pdl_wait();
   extern __shared__ __align__(128) float dyn_smem[];  // weight stream: 2 x 32 x 128 floats + 2 mbarriers
   WStream ws;
   wstream_init(ws, dyn_smem, reinterpret_cast<uint64_t*>(dyn_smem + 2 * 32 * 128));
@@ -118,6 +119,7 @@ __device__ __forceinline__ float4 gcn_aggregate(const float* __restrict__ hin, c
 
 // grid (42 = k*21 + j, 2 hands, ceil(B/32)); 256 threads = 8 row groups (4 images) x 32 column groups
 __global__ void __launch_bounds__(256) gcn_gemm_kernel(GcnGemmArgs a) {
+  pdl_wait();
   extern __shared__ __align__(128) float dyn_smem[];  // weight stream: 2 x 32 x 128 floats + 2 mbarriers
   WStream ws;
   wstream_init(ws, dyn_smem, reinterpret_cast<uint64_t*>(dyn_smem + 2 * 32 * 128));
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(256) gcn_gemm_kernel(GcnGemmArgs a) {
 
 // grid (21 joints, 2 hands, ceil(B/32)); 256 threads
 __global__ void __launch_bounds__(256) gcn_finish_kernel(GcnFinishArgs a) {
+  pdl_wait();
   extern __shared__ __align__(128) float dyn_smem[];
   WStream ws;
   wstream_init(ws, dyn_smem, reinterpret_cast<uint64_t*>(dyn_smem + 2 * 32 * 128));
@@ -404,10 +407,11 @@ __global__ void __launch_bounds__(STE_THREADS) ste_kernel(const float* __restric
     segs[n++] = WSeg{w.head_t, 2 * 64, 4, 64};
   }
   __syncthreads();
-  if (tid >= STE_CONSUMERS) {  // producer warp
+  if (tid >= STE_CONSUMERS) {  // producer warp: weights only, so it starts before the previous kernel has finished
     ste_producer(segs, STE_NSEG, ring, full, empty);
     return;
   }
+  pdl_wait();
   WRing rg{ring, full, empty, 0};
   for (int i = tid; i < NT * 128; i += STE_CONSUMERS) x[i] = xin[(int64_t)b * NT * 128 + i] + w.pos[i];
   ste_bar();
@@ -515,6 +519,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) bone_raster_kernel(const float* __restrict__ rec, int rec_stride,
                                                           const float* __restrict__ jf, T* __restrict__ out, int S,
                                                           float distance) {
+  pdl_wait();
   __shared__ BoneGeom geo[40];
   __shared__ float uv[84];
   __shared__ __align__(16) float feat[2 * NJ * 64];
@@ -553,6 +558,7 @@ __global__ void __launch_bounds__(256) bone_vis_kernel(const float* __restrict__
                                                        int uv_stride, const float* __restrict__ f_l,
                                                        const float* __restrict__ f_r, int f_stride,
                                                        float* __restrict__ out, int S, float distance, int add_right) {
+  pdl_wait();
   __shared__ float uv[2][42];
   __shared__ float fe[2][2][64];  // [hand][a/b][c]
   __shared__ BoneGeom geo[2];
@@ -592,7 +598,7 @@ void launch_joint_embed(const EmbedArgs& a, cudaStream_t st) {
     cudaFuncSetAttribute(joint_embed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr = true;
   }
-  joint_embed_kernel<T><<<dim3(a.B, 2), 128, 2 * 32 * 128 * 4 + 16, st>>>(a);
+  launch_pdl(joint_embed_kernel<T>, dim3(dim3(a.B, 2)), dim3(128), 2 * 32 * 128 * 4 + 16, st, a);
 }
 template void launch_joint_embed<float>(const EmbedArgs&, cudaStream_t);
 template void launch_joint_embed<__nv_bfloat16>(const EmbedArgs&, cudaStream_t);
@@ -603,7 +609,7 @@ void launch_gcn_gemm(const GcnGemmArgs& a, cudaStream_t st) {
     cudaFuncSetAttribute(gcn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr = true;
   }
-  gcn_gemm_kernel<<<dim3(2 * NJ, 2, ceil_div(a.B, GBT)), 256, 2 * 32 * 128 * 4 + 16, st>>>(a);
+  launch_pdl(gcn_gemm_kernel, dim3(dim3(2 * NJ, 2, ceil_div(a.B, GBT))), dim3(256), 2 * 32 * 128 * 4 + 16, st, a);
 }
 
 void launch_gcn_finish(const GcnFinishArgs& a, cudaStream_t st) {
@@ -612,7 +618,7 @@ void launch_gcn_finish(const GcnFinishArgs& a, cudaStream_t st) {
     cudaFuncSetAttribute(gcn_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr = true;
   }
-  gcn_finish_kernel<<<dim3(NJ, 2, ceil_div(a.B, GBT)), 256, 2 * 32 * 128 * 4 + 16, st>>>(a);
+  launch_pdl(gcn_finish_kernel, dim3(dim3(NJ, 2, ceil_div(a.B, GBT))), dim3(256), 2 * 32 * 128 * 4 + 16, st, a);
 }
 
 void launch_ste(const float* x, float* y, const SteWeights& w, int B, cudaStream_t st) {
@@ -622,13 +628,13 @@ void launch_ste(const float* x, float* y, const SteWeights& w, int B, cudaStream
     cudaFuncSetAttribute(ste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_set = true;
   }
-  ste_kernel<<<B, STE_THREADS, smem, st>>>(x, y, w);
+  launch_pdl(ste_kernel, dim3(B), dim3(STE_THREADS), smem, st, x, y, w);
 }
 
 template <typename T>
 void launch_bone_raster(const float* rec, int rec_stride, const float* jf, T* out, int B, int S, float distance,
                         cudaStream_t st) {
-  bone_raster_kernel<T><<<dim3(B, S), 256, 0, st>>>(rec, rec_stride, jf, out, S, distance);
+  launch_pdl(bone_raster_kernel<T>, dim3(dim3(B, S)), dim3(256), 0, st, rec, rec_stride, jf, out, S, distance);
 }
 template void launch_bone_raster<float>(const float*, int, const float*, float*, int, int, float, cudaStream_t);
 template void launch_bone_raster<__nv_bfloat16>(const float*, int, const float*, __nv_bfloat16*, int, int, float,
@@ -636,7 +642,7 @@ template void launch_bone_raster<__nv_bfloat16>(const float*, int, const float*,
 
 void launch_bone_vis_nchw(const float* uv_l, const float* uv_r, int uv_stride, const float* f_l, const float* f_r,
                           int f_stride, float* out, int B, int S, float distance, int add_right, cudaStream_t st) {
-  bone_vis_kernel<<<dim3(B, 20), 256, 0, st>>>(uv_l, uv_r, uv_stride, f_l, f_r, f_stride, out, S, distance, add_right);
+  launch_pdl(bone_vis_kernel, dim3(dim3(B, 20)), dim3(256), 0, st, uv_l, uv_r, uv_stride, f_l, f_r, f_stride, out, S, distance, add_right);
 }
 
 }  // namespace dirb200

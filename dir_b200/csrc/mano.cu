@@ -254,6 +254,7 @@ __device__ __forceinline__ void warp_linear(const float* __restrict__ W, const f
 }
 
 __global__ void __launch_bounds__(THREADS) regress_mano_kernel(RegressArgs a) {
+  pdl_wait();
   __shared__ ManoSmem s;
   __shared__ __align__(16) float vin[VMAX];
   __shared__ float hid[21 * 64];
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(THREADS) mano_only_kernel(const float* __restr
 }  // namespace
 
 void launch_regress_mano(const RegressArgs& a, cudaStream_t st) {
-  regress_mano_kernel<<<dim3(a.B, 2), THREADS, 0, st>>>(a);
+  launch_pdl(regress_mano_kernel, dim3(dim3(a.B, 2)), dim3(THREADS), 0, st, a);
 }
 
 void launch_mano_only(const float* para, const ManoWeights mano[2], float* stage_record, int rec_stride, int B,
