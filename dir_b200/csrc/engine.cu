@@ -266,6 +266,19 @@ void Engine::build_stage(int s, const std::string& p) {
   st.ste.hnb = copy_of(q + "head.0.bias");
   st.ste.head_t = transposed_pairs(q + "head.1.weight", 64, 128);
   st.ste.head_b = copy_of(q + "head.1.bias");
+  if (bf16()) {  // operand tiles of the tcgen05 kernel, in consumption order
+    float* pk = dalloc(ste_tc_packed_bytes() / 4);
+    const char* names[4] = {"attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight"};
+    const std::vector<int64_t> shp[4] = {{384, 128}, {128, 128}, {256, 128}, {128, 256}};
+    for (int l = 0; l < 3; ++l)
+      for (int k = 0; k < 4; ++k) {
+        const float* src = W(q + "STEblocks." + std::to_string(l + 1) + "." + names[k], shp[k]);
+        if (!dry && src && pk) launch_pack_ste_tc(src, l, k, pk, fin_stream);
+      }
+    const float* hw = W(q + "head.1.weight", {64, 128});
+    if (!dry && hw && pk) launch_pack_ste_tc(hw, 3, 0, pk, fin_stream);
+    st.ste_packed = pk;
+  }
   st.fusion0 = make_conv(p + "fusion.0.weight", p + "fusion.0.bias", p + "fusion.1.", 1, 1, 1);
   st.fusion3 = make_conv(p + "fusion.3.weight", p + "fusion.3.bias", "", 1, 0, 0);
   {
@@ -709,7 +722,10 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
     launch_gcn_finish(f, st);
   }
   float* gin = jf1;
-  launch_ste(gin, tok, sw.ste, B, st);
+  if (std::is_same<T, __nv_bfloat16>::value && sw.ste_packed && !ste_simt)
+    launch_ste_tc(gin, tok, sw.ste, sw.ste_packed, B, st);
+  else
+    launch_ste(gin, tok, sw.ste, B, st);
   RegressArgs a{};
   for (int h = 0; h < 2; ++h) {
     a.in0[h] = VecSeg{tok + h * 1344, 1344, 2688};

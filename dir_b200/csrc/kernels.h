@@ -118,6 +118,11 @@ struct SteWeights {
   const float *snw, *snb, *hnw, *hnb, *head_t, *head_b;
 };
 void launch_ste(const float* x, float* y, const SteWeights& w, int B, cudaStream_t st);
+// tcgen05 version (ste_tc.cu, bf16 operands): `packed` = ste_tc_packed_bytes() of operand tiles filled at finalize by
+// launch_pack_ste_tc(weight, block l in 0..2, which: 0 qkv 1 proj 2 fc1 3 fc2; l = 3: head.1.weight)
+size_t ste_tc_packed_bytes();
+void launch_pack_ste_tc(const float* src, int l, int which, void* packed, cudaStream_t st);
+void launch_ste_tc(const float* x, float* y, const SteWeights& w, const void* packed, int B, cudaStream_t st);
 
 struct ManoWeights {
   const float* comps;       // (45,45)

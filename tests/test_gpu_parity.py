@@ -431,3 +431,41 @@ def test_pair_fused_convs_match_separate_launches(synth_sd, X, monkeypatch):
     n_fused = fused._handle.lib.dirb200_forward_launches(fused._handle.h, 2)
     n_sep = sep._handle.lib.dirb200_forward_launches(sep._handle.h, 2)
     assert n_fused == n_sep - 10  # 4 downsample + 6 skip convs disappear
+
+
+@pytest.mark.parametrize("stage,S,B", [(1, 16, 3), (2, 32, 8)])
+def test_ste_tcgen05_vs_cuda_core_kernel(synth_sd, monkeypatch, stage, S, B):
+    """bf16 configuration: mixSTE on tcgen05 (ste_tc.cu, bf16 operands / fp32 accumulate, residual stream in TMEM)
+    against the fp32 CUDA-core ste_kernel (DIRB200_STE_SIMT=1) through the joint2bone seam, same bf16 feature map.
+    Odd and even batches (two images per CTA: the last CTA of an odd batch has an empty slot). The joint features
+    (Linear over the STE tokens) and the refined MANO outputs must agree to bf16-operand accuracy; measured printed."""
+    from dir_b200 import seams
+
+    tc = _make(synth_sd, "bf16", max_batch=8)
+    monkeypatch.setenv("DIRB200_STE_SIMT", "1")
+    simt = _make(synth_sd, "bf16", max_batch=8)
+    simt._ensure_handle()  # handle reads the env var at creation
+    monkeypatch.delenv("DIRB200_STE_SIMT")
+    gen = torch.Generator().manual_seed(500 + stage)
+    prev = {"pd_joint_xyz_left": torch.randn(B, 21, 3, generator=gen) * 0.05,
+            "pd_joint_xyz_right": torch.randn(B, 21, 3, generator=gen) * 0.05,
+            "pd_joint_uv_left": (torch.rand(B, 21, 2, generator=gen) * 2 - 1) * 0.8,
+            "pd_joint_uv_right": (torch.rand(B, 21, 2, generator=gen) * 2 - 1) * 0.8,
+            "pd_mano_para_left": torch.randn(B, 64, generator=gen) * 0.3,
+            "pd_mano_para_right": torch.randn(B, 64, generator=gen) * 0.3,
+            "pd_offset": torch.randn(B, 3, generator=gen) * 0.5}
+    feat = torch.randn(B, 256, S, S, generator=gen).cuda()
+    prev = {k: v.cuda() for k, v in prev.items()}
+    ra, fa = seams.joint2bone(tc, stage, feat, prev)
+    rb, fb = seams.joint2bone(simt, stage, feat, prev)
+    worst = {}
+    for k in ("joint_feat_left", "joint_feat_right"):
+        worst[k] = rel(fa[k], fb[k])
+    for k in ("pd_mano_para_left", "pd_mano_para_right", "pd_mesh_xyz_left", "pd_mesh_xyz_right", "pd_joint_uv_left"):
+        worst[k] = rel(ra[k], rb[k])
+    print("tcgen05 STE vs fp32 STE:", {k: f"{v:.2e}" for k, v in worst.items()})
+    assert all(bool(torch.isfinite(v).all()) for v in ra.values() if v is not None)
+    assert max(worst.values()) < 3e-2
+    # per-image independence across the two slots of a CTA: image i alone == image i inside the batch
+    one, _ = seams.joint2bone(tc, stage, feat[1:2], {k: v[1:2] for k, v in prev.items()})
+    assert torch.equal(one["pd_mesh_xyz_left"], ra["pd_mesh_xyz_left"][1:2])
