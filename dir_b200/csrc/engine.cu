@@ -286,6 +286,11 @@ void Engine::build_stage(int s, const std::string& p) {
     float* wp = dalloc((size_t)40 * 64 * 9 * 256);
     if (!dry && fw && wp) launch_pack_fusion_weight(fw, wp, fin_stream);
     st.fus_wp = wp;
+    if (bf16()) {
+      float* wt = dalloc(bone_coef_tc_packed_bytes() / 4);
+      if (!dry && fw && wt) launch_pack_fusion_weight_tc(fw, wt, fin_stream);
+      st.fus_wp_tc = wt;
+    }
   }
 }
 
@@ -753,7 +758,10 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
     ++launches;
     conv<T>(sw.fusion0, bone, fus_mid, nullptr, B, S, S, st);
   } else {
-    launch_bone_coef(jfeat, sw.fus_wp, coef, B, st);
+    if (std::is_same<T, __nv_bfloat16>::value && sw.fus_wp_tc && !coef_simt)
+      launch_bone_coef_tc(jfeat, sw.fus_wp_tc, coef, B, st);
+    else
+      launch_bone_coef(jfeat, sw.fus_wp, coef, B, st);
     launch_bone_fusion<T>(stage_rec, rec_stride, coef, sw.fusion0.scale, sw.fusion0.shift, fus_mid, B, S, sw.distance,
                           st);
     launches += 2;

@@ -66,6 +66,7 @@ struct StageWeights {
   const float *Wm[2], *bm[2], *Wo, *bo;
   ConvLayer fusion0, fusion3;
   const float* fus_wp = nullptr;  // fusion.0 weights packed for the factored form [40][64][9][256]
+  const void* fus_wp_tc = nullptr;  // bf16 configuration: the same weights as tf32 operand tiles (fusion.cu)
 };
 
 struct Arena {
@@ -97,6 +98,7 @@ struct Engine {
   int last_forward_launches = 0;
   int tc_launches = 0;      // convs that went to the tcgen05 kernel since the last forward() start
   int sticky_rc = 0;        // first launch error inside a forward
+  bool coef_simt = false;     // DIRB200_COEF_SIMT=1: fp32 CUDA-core bone_coef also in the bf16 configuration
   bool ste_simt = false;      // DIRB200_STE_SIMT=1: fp32 CUDA-core mixSTE also in the bf16 configuration
   bool dense_fusion = false;  // DIRB200_DENSE_FUSION=1: materialise bone_proj and run the dense 2560-ch conv
   bool disable_pair_fusion = false;  // DIRB200_NO_PAIR_FUSION=1: keep conv3 and skip/downsample as separate launches

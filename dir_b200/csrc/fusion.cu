@@ -12,6 +12,7 @@
 #include "../../include/dirb200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace dirb200 {
 
@@ -110,6 +111,156 @@ __global__ void __launch_bounds__(256) bone_coef_kernel(const float* __restrict_
           make_float4(v[0], v[1], v[2], v[3]);
     });
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bone_coef on the tensor cores (bf16 configuration): the same grouped GEMM as tcgen05.mma kind::tf32 (fp32 operands
+// read as tf32, fp32 accumulation), i.e. 8x the operand precision of the bf16 dense conv it replaces.
+// CTA = (bone hb, 128 rows (b, role)): the 128x64 feature tile is staged once (K-major, 128B swizzle, 2 k-tiles of
+// 32 floats), then the 9 taps stream through a 2-deep ring of 64 KB weight tiles ([256 n][64 c], packed at finalize
+// in smem-image order: one cp.async.bulk each) into two alternating 256-column TMEM accumulators while 4 warps drain
+// the previous tap to P. Roles: warps 0-3 staging + epilogue, warp 4 weight producer, warp 5 TMEM + MMA issue.
+constexpr int CT_WTILE = 2 * 256 * 128;  // bytes of one (hb, tap) weight tile
+constexpr int CT_ATILE = 128 * 128;      // bytes of one k-tile of the feature operand
+constexpr int CT_PITCH = 68;             // floats per row of an epilogue transpose patch (64 + 4: conflict-free)
+constexpr int CT_OFF_A = 0, CT_OFF_W = 2 * CT_ATILE, CT_OFF_STAGE = CT_OFF_W + 2 * CT_WTILE;
+constexpr int CT_OFF_BAR = CT_OFF_STAGE + 4 * 32 * CT_PITCH * 4;
+constexpr int CT_SMEM = 1024 + CT_OFF_BAR + 128;
+
+struct CoefBars {
+  uint64_t full[2], empty[2], acc_full[2], acc_empty[2], a_ready;
+  uint32_t tmem_ptr;
+};
+
+__global__ void __launch_bounds__(192, 1)
+bone_coef_tc_kernel(const float* __restrict__ jf, const uint8_t* __restrict__ wpk, float* __restrict__ P, int B) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  CoefBars* bars = reinterpret_cast<CoefBars*>(smem + CT_OFF_BAR);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hb = blockIdx.x, r0 = blockIdx.y * 128;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->full[i], 1);
+      mbar_init(&bars->empty[i], 1);
+      mbar_init(&bars->acc_full[i], 1);
+      mbar_init(&bars->acc_empty[i], 128);
+    }
+    mbar_init(&bars->a_ready, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&bars->tmem_ptr)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = bars->tmem_ptr;
+
+  if (warp == 4) {  // ---- weight producer (finalize-time data: starts before the previous kernel has finished)
+    if (lane == 0) {
+      for (int tap = 0; tap < 9; ++tap) {
+        const int slot = tap & 1;
+        if (tap >= 2) mbar_wait(&bars->empty[slot], ((tap >> 1) - 1) & 1);
+        mbar_expect_tx(&bars->full[slot], CT_WTILE);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         s32(smem + CT_OFF_W + slot * CT_WTILE)),
+                     "l"(wpk + ((size_t)hb * 9 + tap) * CT_WTILE), "r"(CT_WTILE), "r"(s32(&bars->full[slot]))
+                     : "memory");
+      }
+    }
+  } else if (warp == 5) {  // ---- MMA issuer
+    if (lane == 0) {
+      const uint32_t sb = s32(smem);
+      mbar_wait(&bars->a_ready, 0);
+      fence_after();
+      for (int tap = 0; tap < 9; ++tap) {
+        const int slot = tap & 1;
+        mbar_wait(&bars->full[slot], (tap >> 1) & 1);
+        mbar_wait(&bars->acc_empty[slot], ((tap >> 1) & 1) ^ 1);
+        fence_after();
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+          const uint64_t da = desc128(sb + CT_OFF_A + kt * CT_ATILE);
+          const uint64_t db = desc128(sb + CT_OFF_W + slot * CT_WTILE + kt * (CT_WTILE / 2));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32(tmem + slot * 256, da + 2 * k, db + 2 * k, idesc(256, 2u), (kt | k) ? 1u : 0u);
+        }
+        umma_commit(&bars->empty[slot]);
+        umma_commit(&bars->acc_full[slot]);
+      }
+    }
+  } else {  // ---- stage the feature rows, then drain the accumulators: thread = row (b, role)
+    pdl_wait();
+    const int r = threadIdx.x, ri = r0 + r;
+    const int hand = hb / 20, bone = hb % 20;
+    const int pa = (bone % 4 == 0) ? 0 : bone, ch = bone + 1;
+    const bool valid = ri < 2 * B;
+    const int b = ri >> 1, role = ri & 1;
+    {
+      const float4* src = reinterpret_cast<const float4*>(jf + ((int64_t)(b * 2 + hand) * NJ + (role ? ch : pa)) * 64);
+      uint8_t* arow = smem + CT_OFF_A + r * 128;
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        const float4 v = valid ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(arow + (c4 >> 3) * CT_ATILE + (((c4 & 7) ^ (r & 7)) << 4)) = v;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive(&bars->a_ready);
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    // TMEM hands a thread one row; a row-per-lane global store would touch 32 lines per instruction (LSU-bound:
+    // measured 82 us). Each warp transposes 32 rows x 64 columns through its own padded smem patch instead, so one
+    // store instruction writes two 256-byte row segments.
+    float* patch = reinterpret_cast<float*>(smem + CT_OFF_STAGE) + warp * (32 * CT_PITCH);
+    const int prow_l = lane >> 4, pcol = (lane & 15) * 4;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int slot = tap & 1;
+      mbar_wait(&bars->acc_full[slot], (tap >> 1) & 1);
+      fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[64];
+        tmem_ld32(trow + slot * 256 + 64 * c, v);
+        tmem_ld32(trow + slot * 256 + 64 * c + 32, v + 32);
+        tmem_ld_wait();
+        float4* mine = reinterpret_cast<float4*>(patch + lane * CT_PITCH);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mine[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        __syncwarp();
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+          const int rr = 2 * it + prow_l, rj = r0 + warp * 32 + rr;
+          if (rj < 2 * B) {
+            const float4 o = *reinterpret_cast<const float4*>(patch + rr * CT_PITCH + pcol);
+            *reinterpret_cast<float4*>(P + ((((int64_t)(rj >> 1) * 40 + hb) * 2 + (rj & 1)) * 9 + tap) * 256 + 64 * c + pcol) = o;
+          }
+        }
+        __syncwarp();
+      }
+      fence_before();
+      mbar_arrive(&bars->acc_empty[slot]);
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// fusion.0.weight [256][2560][3][3] -> per (hb, tap): 2 k-tiles x [256 n][32 c] fp32 in 128B-swizzled smem-image order
+__global__ void pack_fusion_weight_tc_kernel(const float* __restrict__ w, float* __restrict__ wpk) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)40 * 9 * 256 * 64) return;
+  const int c = (int)(idx & 63);
+  const int n = (int)((idx >> 6) & 255);
+  const int t = (int)(idx >> 14);
+  const int tap = t % 9, hb = t / 9;
+  const int kt = c >> 5, cc = c & 31;
+  const int64_t off = (((int64_t)hb * 9 + tap) * 2 + kt) * 256 * 32 + n * 32 + ((((cc >> 2) ^ (n & 7)) << 2) | (cc & 3));
+  wpk[off] = w[((int64_t)n * 2560 + hb * 64 + c) * 9 + tap];
 }
 
 struct Entry {
@@ -278,6 +429,23 @@ __global__ void __launch_bounds__(256) bone_fusion_kernel(const float* __restric
 void launch_pack_fusion_weight(const float* w, float* wp, cudaStream_t st) {
   int64_t total = (int64_t)40 * 64 * 9 * 256;
   pack_fusion_weight_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(w, wp);
+}
+
+size_t bone_coef_tc_packed_bytes() { return (size_t)40 * 9 * CT_WTILE; }
+
+void launch_pack_fusion_weight_tc(const float* w, void* wpk, cudaStream_t st) {
+  int64_t total = (int64_t)40 * 9 * 256 * 64;
+  pack_fusion_weight_tc_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(w, reinterpret_cast<float*>(wpk));
+}
+
+void launch_bone_coef_tc(const float* jf, const void* wpk, float* P, int B, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(bone_coef_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM);
+    attr = true;
+  }
+  launch_pdl(bone_coef_tc_kernel, dim3(40, ceil_div(2 * B, 128)), dim3(192), CT_SMEM, st, jf,
+             reinterpret_cast<const uint8_t*>(wpk), P, B);
 }
 
 void launch_bone_coef(const float* jf, const float* wp, float* P, int B, cudaStream_t st) {

@@ -171,6 +171,10 @@ void launch_bone_raster(const float* stage_record, int rec_stride, const float* 
 // exact factored bone_proj -> conv3x3(2560->256) -> BN -> ReLU (fusion.cu)
 void launch_pack_fusion_weight(const float* w /*[256][2560][3][3]*/, float* wp /*[40][64][9][256]*/, cudaStream_t st);
 void launch_bone_coef(const float* joint_feat, const float* wp, float* P /*(B,40,2,9,256)*/, int B, cudaStream_t st);
+// tensor-core version (kind::tf32): wpk = bone_coef_tc_packed_bytes() filled by launch_pack_fusion_weight_tc
+size_t bone_coef_tc_packed_bytes();
+void launch_pack_fusion_weight_tc(const float* w /*fusion.0.weight*/, void* wpk, cudaStream_t st);
+void launch_bone_coef_tc(const float* jf, const void* wpk, float* P, int B, cudaStream_t st);
 template <typename T>
 void launch_bone_fusion(const float* stage_record, int rec_stride, const float* P, const float* scale,
                         const float* shift, T* out /*NHWC (B,S,S,256)*/, int B, int S, float distance, cudaStream_t st);

@@ -469,3 +469,36 @@ def test_ste_tcgen05_vs_cuda_core_kernel(synth_sd, monkeypatch, stage, S, B):
     # per-image independence across the two slots of a CTA: image i alone == image i inside the batch
     one, _ = seams.joint2bone(tc, stage, feat[1:2], {k: v[1:2] for k, v in prev.items()})
     assert torch.equal(one["pd_mesh_xyz_left"], ra["pd_mesh_xyz_left"][1:2])
+
+
+@pytest.mark.parametrize("stage,S,B", [(1, 16, 3), (2, 32, 70)])
+def test_bone_coef_tf32_tensor_core_vs_cuda_core(synth_sd, monkeypatch, stage, S, B):
+    """bf16 configuration: bone_coef as tcgen05 kind::tf32 GEMMs against the fp32 CUDA-core kernel
+    (DIRB200_COEF_SIMT=1). Only the fused stage feature map depends on it; tf32 operands (10-bit mantissa) under a
+    bf16 output: most pixels identical, the rest one bf16 ulp apart. B=70 -> 140 rows = one full + one ragged M tile."""
+    from dir_b200 import seams
+
+    tc = _make(synth_sd, "bf16", max_batch=128)
+    monkeypatch.setenv("DIRB200_COEF_SIMT", "1")
+    simt = _make(synth_sd, "bf16", max_batch=128)
+    simt._ensure_handle()
+    monkeypatch.delenv("DIRB200_COEF_SIMT")
+    gen = torch.Generator().manual_seed(700 + stage)
+    prev = {"pd_joint_xyz_left": torch.randn(B, 21, 3, generator=gen) * 0.05,
+            "pd_joint_xyz_right": torch.randn(B, 21, 3, generator=gen) * 0.05,
+            "pd_joint_uv_left": (torch.rand(B, 21, 2, generator=gen) * 2 - 1) * 0.8,
+            "pd_joint_uv_right": (torch.rand(B, 21, 2, generator=gen) * 2 - 1) * 0.8,
+            "pd_mano_para_left": torch.randn(B, 64, generator=gen) * 0.3,
+            "pd_mano_para_right": torch.randn(B, 64, generator=gen) * 0.3,
+            "pd_offset": torch.randn(B, 3, generator=gen) * 0.5}
+    feat = torch.randn(B, 256, S, S, generator=gen).cuda()
+    prev = {k: v.cuda() for k, v in prev.items()}
+    ra, fa = seams.joint2bone(tc, stage, feat, prev)
+    rb, fb = seams.joint2bone(simt, stage, feat, prev)
+    assert torch.equal(ra["pd_mesh_xyz_left"], rb["pd_mesh_xyz_left"])  # upstream of bone_coef: untouched
+    a, b = fa["img_feat"], fb["img_feat"]
+    assert bool(torch.isfinite(a).all()) and float(b.abs().max()) > 0
+    err = float((a - b).abs().max() / b.abs().max())
+    frac = float(((a - b).abs() > 0).float().mean())
+    print(f"tf32 bone_coef vs fp32: max rel err {err:.2e}, {100 * frac:.2f}% of outputs differ")
+    assert err < 1.5e-2  # a couple of bf16 ulps of the largest value
