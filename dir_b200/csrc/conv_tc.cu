@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <tuple>
 
@@ -86,6 +87,34 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 2-CTA variants (cute::SM100_TMA_2SM_LOAD_*): the data lands in THIS CTA's smem, the transaction bytes are counted
+// on the leader CTA's barrier (peer bit of the shared::cluster address cleared).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the leader CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(map)),
@@ -116,6 +145,23 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// cta_group::2: one instruction drives the tensor cores of both SMs of the pair (M = 256: rows 0-127 from the leader's
+// smem / into the leader's TMEM, rows 128-255 the peer's; each CTA supplies half of the N rows of B).
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {  // arrives on `bar` in both CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -131,14 +177,15 @@ __device__ __forceinline__ void epi_barrier(int group) {  // named barrier of on
   asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
 }
 
-template <int BN, int SW>
+template <int BN, int SW, int CG = 1>
 struct TcCfg {
   static constexpr int A_STAGE = BM * SW;
-  static constexpr int B_STAGE = BN * SW;
+  static constexpr int B_STAGE = (BN / CG) * SW;  // 2-CTA mode: each CTA of the pair holds half of the N rows
   static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
   static constexpr int KSTEPS = SW / 32;  // tcgen05.mma K=16 bf16 = 32 B per step
-  // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N=BN, M=128
-  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N=BN, M=128 per CTA
+  static constexpr uint32_t IDESC =
+      (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
   static constexpr uint32_t TMEM_COLS = 2 * BN;
   static constexpr int NCH = BN / 64;
   static int smem_bytes(int stages, int has_res) {
@@ -146,12 +193,16 @@ struct TcCfg {
   }
 };
 
-template <int BN, int SW>
+template <int BN, int SW, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ CUtensorMap tmA2, const TcArgs a) {
-  using Cfg = TcCfg<BN, SW>;
+  using Cfg = TcCfg<BN, SW, CG>;
+  // CG == 2: launched as clusters of two CTAs that share every MMA (tile = 256 output pixels x BN: this CTA owns rows
+  // 128*rank..+127 and loads its own A tile plus HALF of the weight tile, so the L2->SM bytes per FLOP drop by a third;
+  // the 3x3 / wide layers are bound by exactly that fabric). Only rank 0 issues tcgen05.mma.
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = a.stages;
@@ -170,7 +221,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty + RES_BUFS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = a.m_tiles * a.n_tiles;
+  const int m_units = a.m_tiles / CG;  // scheduling unit = CG adjacent M tiles (one per CTA of the pair)
+  const int total_tiles = m_units * a.n_tiles;
+  const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
   const int nkb1 = a.taps * a.cblocks;
   const int nkb = nkb1 + a.kb2;
 
@@ -184,7 +237,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 256);
+      mbar_init(&tmem_empty[i], 256 * CG);  // CG == 2: both CTAs' epilogues arrive on the leader's barrier
     }
     for (int i = 0; i < RES_BUFS; ++i) {
       mbar_init(&res_full[i], 1);
@@ -193,13 +246,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: two accumulator buffers of BN fp32 columns x 128 lanes
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"(Cfg::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"(Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"(Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();  // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail
@@ -208,9 +269,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {  // ===================== TMA producer
       int s = 0;
       uint32_t ph = 0, rchunk = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (a.raster_m ? tile % a.m_tiles : tile / a.n_tiles) * BM;
-        const int n0 = (a.raster_m ? tile / a.m_tiles : tile % a.n_tiles) * BN;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int m0 = ((a.raster_m ? tile % m_units : tile / a.n_tiles) * CG + (int)rank) * BM;
+        const int n0 = (a.raster_m ? tile / m_units : tile % a.n_tiles) * BN;
+        const int nb0 = n0 + (int)rank * (BN / CG);  // first weight row this CTA loads
         const int wo0 = m0 % a.Wo;
         const int ho0 = (m0 / a.Wo) % a.Ho;
         const int b0 = m0 / (a.Wo * a.Ho);
@@ -224,6 +286,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
+          if constexpr (CG == 2) {  // both CTAs' bytes are counted on the leader's full barrier
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+            if (kb >= nkb1) {
+              tma_load_4d_2sm(&tmA2, &full_bar[s], sA + s * Cfg::A_STAGE, (kb - nkb1) * 64, wo0 * a.stride2,
+                              ho0 * a.stride2, b0);
+            } else {
+              const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
+              const int ky = tap / a.kw, kx = tap - ky * a.kw;
+              tma_load_4d_2sm(&tmA, &full_bar[s], sA + s * Cfg::A_STAGE, cb * 64, wo0 * a.stride + kx - a.pad,
+                              ho0 * a.stride + ky - a.pad, b0);
+            }
+            tma_load_2d_2sm(&tmB, &full_bar[s], sB + s * Cfg::B_STAGE, kb * 64, nb0);
+          } else {
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           if (a.stem) {  // k-block = kernel row ky; overlapped view: {32 elems, wo (16 B apart), h, n}
             tma_load_4d(&tmA, &full_bar[s], sA + s * Cfg::A_STAGE, 0, wo0, ho0 * 2 + kb - 3, b0);
@@ -239,6 +314,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         ho0 * a.stride + ky - a.pad, b0);
             tma_load_2d(&tmB, &full_bar[s], sB + s * Cfg::B_STAGE, kb * 64, n0);
           }
+          }
           if (++s == stages) {
             s = 0;
             ph ^= 1;
@@ -247,11 +323,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===================== MMA issuer
+    if (lane == 0 && rank == 0) {  // ===================== MMA issuer (the leader CTA issues for the pair)
       int s = 0;
       uint32_t ph = 0;
       int i = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++i) {
         const int buf = i & 1;
         mbar_wait(&tmem_empty[buf], ((i >> 1) & 1) ^ 1);  // epilogue drained this accumulator buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -262,15 +338,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t da = umma_desc<SW>(smem_u32(sA + s * Cfg::A_STAGE));
           const uint64_t db = umma_desc<SW>(smem_u32(sB + s * Cfg::B_STAGE));
 #pragma unroll
-          for (int k = 0; k < Cfg::KSTEPS; ++k)  // +32 B per K=16 step inside the swizzle atom
-            umma_bf16(d, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) ? 1u : 0u);
-          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have consumed it
+          for (int k = 0; k < Cfg::KSTEPS; ++k) {  // +32 B per K=16 step inside the swizzle atom
+            if constexpr (CG == 2) umma_bf16_2sm(d, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) ? 1u : 0u);
+            else umma_bf16(d, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) ? 1u : 0u);
+          }
+          // frees the smem stage (in both CTAs) once these MMAs have consumed it
+          if constexpr (CG == 2) umma_commit_2sm(&empty_bar[s]);
+          else umma_commit(&empty_bar[s]);
           if (++s == stages) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(&tmem_full[buf]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (CG == 2) umma_commit_2sm(&tmem_full[buf]);
+        else umma_commit(&tmem_full[buf]);
       }
     }
   } else {
@@ -287,9 +369,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* sOutG = sOut + eg * CHUNK_BYTES;
     int i = 0;
     int cur_n0 = -1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
-      const int m0 = (a.raster_m ? tile % a.m_tiles : tile / a.n_tiles) * BM;
-        const int n0 = (a.raster_m ? tile / a.m_tiles : tile % a.n_tiles) * BN;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++i) {
+      const int m0 = ((a.raster_m ? tile % m_units : tile / a.n_tiles) * CG + (int)rank) * BM;
+      const int n0 = (a.raster_m ? tile / m_units : tile % a.n_tiles) * BN;
       const int buf = i & 1;
       if (n0 != cur_n0) {  // (re)stage the per-channel affine of this n-tile; the group's readers are past (d)
         for (int j = et; j < BN; j += 128) {
@@ -389,15 +471,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       // this thread has read everything it needs from accumulator buffer `buf` (256 arrivals hand it back to the MMA warp)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&tmem_empty[buf]);
+      if constexpr (CG == 2) mbar_arrive_leader(&tmem_empty[buf]);
+      else mbar_arrive(&tmem_empty[buf]);
     }
     if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output bytes written
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // neither CTA may exit while the pair's MMAs / remote arrivals are in flight
+  else __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS)
-                 : "memory");
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -537,27 +625,67 @@ bool make_rowmajor_map(CUtensorMap* tm, const void* ptr, int rows, int cols) {
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int SW>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
-              const CUtensorMap& tmA2, TcArgs a, cudaStream_t st) {
-  using Cfg = TcCfg<BN, SW>;
+bool cg2_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DIRB200_TC_CG2");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <int BN, int SW, int CG>
+int launch_tc_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
+                 const CUtensorMap& tmA2, TcArgs a, cudaStream_t st) {
+  using Cfg = TcCfg<BN, SW, CG>;
   static int attr_bytes = 0;
-  const int nkb = a.taps * a.cblocks + a.kb2;
-  int stages = MAX_STAGES;
+  int stages = MAX_STAGES;  // the ring runs ahead across tiles, so short K loops still want every stage that fits
   while (stages > 1 && Cfg::smem_bytes(stages, a.has_res) > 227 * 1024) --stages;
-  (void)nkb;  // the ring runs ahead across tiles, so short K loops still want every stage that fits
   a.stages = stages;
   const int smem = Cfg::smem_bytes(stages, a.has_res);
   if (smem > attr_bytes) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<BN, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN, SW, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess)
       return DIRB200_E_CUDA;
     attr_bytes = 227 * 1024;
   }
-  const int tiles = a.m_tiles * a.n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  launch_pdl(conv_tc_kernel<BN, SW>, dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, tmY, tmR, tmA2, a);
+  const int units = (a.m_tiles / CG) * a.n_tiles;        // scheduling units (one per CTA, or per CTA pair)
+  const int slots = num_sms() / CG;
+  const int grid = (units < slots ? units : slots) * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (CG == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  if (cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SW, CG>, tmA, tmB, tmY, tmR, tmA2, a) != cudaSuccess)
+    return DIRB200_E_CUDA;
   return DIRB200_OK;
+}
+
+// tmB2 = the weight map with BN/2-row boxes (null: 1-CTA kernel only)
+template <int BN, int SW>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmB2, const CUtensorMap& tmY,
+              const CUtensorMap& tmR, const CUtensorMap& tmA2, TcArgs a, cudaStream_t st) {
+  if constexpr (BN >= 128 && SW == 128) {
+    if (tmB2 && cg2_enabled() && !a.stem && a.m_tiles % 2 == 0)
+      return launch_tc_cg<BN, SW, 2>(tmA, *tmB2, tmY, tmR, tmA2, a, st);
+  }
+  return launch_tc_cg<BN, SW, 1>(tmA, tmB, tmY, tmR, tmA2, a, st);
 }
 
 template <typename Key>
@@ -612,6 +740,13 @@ int conv_tc_prepare_weights(ConvLayer& L) {
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return DIRB200_E_CUDA;
   L.wmap_bn = bn;
+  L.wmap2_ok = false;
+  if (bn >= 128) {  // 2-CTA mode: each CTA of a pair loads half of the N rows of a weight tile
+    cuuint32_t box2[2] = {64, (cuuint32_t)(bn / 2)};
+    L.wmap2_ok = enc(&L.wmap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, L.w16, dims, strides, box2, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
   return DIRB200_OK;
 }
 
@@ -709,7 +844,7 @@ int launch_conv_tc_stem(const ConvLayer& L, const float* img, const unsigned cha
   a.stem = 1;
   a.m_tiles = (M + BM - 1) / BM;
   a.n_tiles = 1;
-  return launch_tc<64, 64>(*tmA, L.wmap, *tmY, *tmY, *tmA, a, st);
+  return launch_tc<64, 64>(*tmA, L.wmap, nullptr, *tmY, *tmY, *tmA, a, st);
 }
 
 namespace {
@@ -766,9 +901,9 @@ int launch_conv_tc_dual(const ConvLayer& L, const __nv_bfloat16* x1, int C1, con
   a.m_tiles = (M + BM - 1) / BM;
   a.n_tiles = L.Cout / L.wmap_bn;
   switch (L.wmap_bn) {
-    case 256: return launch_tc<256, 128>(*tmA, L.wmap, *tmY, *tmY, *tmA2, a, st);
-    case 128: return launch_tc<128, 128>(*tmA, L.wmap, *tmY, *tmY, *tmA2, a, st);
-    default: return launch_tc<64, 128>(*tmA, L.wmap, *tmY, *tmY, *tmA2, a, st);
+    case 256: return launch_tc<256, 128>(*tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, *tmY, *tmY, *tmA2, a, st);
+    case 128: return launch_tc<128, 128>(*tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, *tmY, *tmY, *tmA2, a, st);
+    default: return launch_tc<64, 128>(*tmA, L.wmap, nullptr, *tmY, *tmY, *tmA2, a, st);
   }
 }
 
@@ -801,9 +936,9 @@ int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y,
   a.n_tiles = L.Cout / L.wmap_bn;
   a.raster_m = (double)L.Cout * L.K > (double)B * H * W * L.Cin ? 1 : 0;
   switch (L.wmap_bn) {
-    case 256: return launch_tc<256, 128>(*tmA, L.wmap, *tmY, *tmR, *tmA, a, st);
-    case 128: return launch_tc<128, 128>(*tmA, L.wmap, *tmY, *tmR, *tmA, a, st);
-    default: return launch_tc<64, 128>(*tmA, L.wmap, *tmY, *tmR, *tmA, a, st);
+    case 256: return launch_tc<256, 128>(*tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, *tmY, *tmR, *tmA, a, st);
+    case 128: return launch_tc<128, 128>(*tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, *tmY, *tmR, *tmA, a, st);
+    default: return launch_tc<64, 128>(*tmA, L.wmap, nullptr, *tmY, *tmR, *tmA, a, st);
   }
 }
 

@@ -33,6 +33,8 @@ struct ConvLayer {
   float* shift = nullptr;
   CUtensorMap wmap;  // bf16 weights [Cout][Kpad], box 64(k) x BN rows, 128B swizzle (tensor-core path)
   int wmap_bn = 0;   // rows per weight box (0: no tensor map)
+  CUtensorMap wmap2;  // same weights with wmap_bn/2-row boxes: operand halves of the 2-CTA (cta_group::2) kernel
+  bool wmap2_ok = false;
   int tc_bn_cap = 256;   // largest n-tile the tensor-core path may pick (128 for layers that add a residual)
   bool tc_stem = false;  // 7x7/s2/Cin=3 stem packed for the tensor-core stem variant
 };
