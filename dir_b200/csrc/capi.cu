@@ -66,6 +66,8 @@ extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
     h->e.disable_pair_fusion = nopair && nopair[0] == '1';
     const char* dense = getenv("DIRB200_DENSE_FUSION");
     h->e.dense_fusion = dense && dense[0] == '1';
+    const char* ssplit = getenv("DIRB200_STEM_SPLIT");
+    h->e.stem_split = ssplit && ssplit[0] == '1';
     const char* csimt = getenv("DIRB200_COEF_SIMT");
     h->e.coef_simt = csimt && csimt[0] == '1';
     const char* ssimt = getenv("DIRB200_STE_SIMT");

@@ -796,14 +796,20 @@ int conv_tc_prepare_stem(ConvLayer& L, const float* w_raw, __nv_bfloat16* w_pack
 
 size_t conv_tc_stem_scratch_bytes(int B, int H, int W) { return (size_t)B * H * (W + 8) * 4 * 2; }
 
-int launch_conv_tc_stem(const ConvLayer& L, const float* img, const unsigned char* img_u8, __nv_bfloat16* scratch,
-                        __nv_bfloat16* y, int B, int H, int W, cudaStream_t st) {
-  const int Wp = W + 8, Ho = H / 2, Wo = W / 2;
-  const int64_t n = (int64_t)B * H * Wp;
+// image (fp32 NCHW, or raw uint8 HWC BGR frames with the reference's preprocessing fused in) -> zero-padded NHWC4 bf16
+void launch_stem_pack(const float* img, const unsigned char* img_u8, __nv_bfloat16* scratch, int B, int H, int W,
+                      cudaStream_t st) {
+  const int64_t n = (int64_t)B * H * (W + 8);
   if (img_u8)
     launch_pdl(stem_pack_u8_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, img_u8, scratch, B, H, W);
   else
     launch_pdl(stem_pack_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, img, scratch, B, H, W);
+}
+
+int launch_conv_tc_stem(const ConvLayer& L, const float* img, const unsigned char* img_u8, __nv_bfloat16* scratch,
+                        __nv_bfloat16* y, int B, int H, int W, cudaStream_t st) {
+  const int Wp = W + 8, Ho = H / 2, Wo = W / 2;
+  launch_stem_pack(img, img_u8, scratch, B, H, W, st);
   typedef std::tuple<const void*, int, int, int> Key;
   static thread_local MapCache<Key> cache;
   Key key(scratch, B, H, W);

@@ -339,6 +339,9 @@ int Engine::build(cudaStream_t st) {
   if (!dry && bf16() && err.empty()) {
     __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(dalloc(64 * 224 / 2));
     if (wp) conv_tc_prepare_stem(stem, W("backbone.conv1.weight"), wp, st);
+    float* sp = dalloc(stem_pool_weight_bytes() / 4);
+    if (sp) launch_pack_stem_pool_weight(W("backbone.conv1.weight"), sp, st);
+    stem_pool_w = sp;
   }
   const int nblocks[4] = {3, 4, 6, 3};
   for (int l = 0; l < 4; ++l) {
@@ -557,7 +560,18 @@ int Engine::run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** 
     ++launches;
     img = u8_scratch;
   }
-  if (tc_stem) {
+  const bool fused_stem = tc_stem && stem_pool_w && !stem_split && H == 256 && W_ == 256;
+  if (fused_stem) {  // conv1 + bn1 + ReLU + maxpool in one kernel: the conv map never reaches HBM
+    launch_stem_pack(img, img_u8, stem_scratch, B, H, W_, st);
+    int rc = launch_stem_pool(stem_scratch, stem_pool_w, stem.scale, stem.shift, reinterpret_cast<__nv_bfloat16*>(pool_out),
+                              B, st);
+    if (rc && !sticky_rc) {
+      sticky_rc = rc;
+      err = "stem_pool launch failed";
+    }
+    launches += 2;
+    tc_launches += 1;
+  } else if (tc_stem) {
     int rc = launch_conv_tc_stem(stem, img, img_u8, stem_scratch, reinterpret_cast<__nv_bfloat16*>(stem_out), B, H, W_,
                                  st);
     if (rc && !sticky_rc) {
@@ -569,8 +583,10 @@ int Engine::run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** 
   } else {
     conv<T>(stem, reinterpret_cast<const T*>(img), stem_out, nullptr, B, H, W_, st, /*in_nchw=*/true);
   }
-  launch_maxpool3x3s2<T>(stem_out, pool_out, B, H2, W2, 64, st);
-  ++launches;
+  if (!fused_stem) {
+    launch_maxpool3x3s2<T>(stem_out, pool_out, B, H2, W2, 64, st);
+    ++launches;
+  }
   const T* x = pool_out;
   int xi = -1;  // index of the rotating buffer holding x (-1: none)
   int h = H4, w = W4;

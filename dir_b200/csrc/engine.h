@@ -101,6 +101,8 @@ struct Engine {
   int tc_launches = 0;      // convs that went to the tcgen05 kernel since the last forward() start
   int sticky_rc = 0;        // first launch error inside a forward
   bool coef_simt = false;     // DIRB200_COEF_SIMT=1: fp32 CUDA-core bone_coef also in the bf16 configuration
+  bool stem_split = false;    // DIRB200_STEM_SPLIT=1: stem conv and max-pool as two kernels (TMA implicit GEMM + pool)
+  const void* stem_pool_w = nullptr;  // conv1 weights packed for stem_pool_kernel
   bool ste_simt = false;      // DIRB200_STE_SIMT=1: fp32 CUDA-core mixSTE also in the bf16 configuration
   bool dense_fusion = false;  // DIRB200_DENSE_FUSION=1: materialise bone_proj and run the dense 2560-ch conv
   bool disable_pair_fusion = false;  // DIRB200_NO_PAIR_FUSION=1: keep conv3 and skip/downsample as separate launches
@@ -188,6 +190,13 @@ int launch_conv_tc_dual(const ConvLayer& L, const __nv_bfloat16* x1, int C1, con
                         int stride2, __nv_bfloat16* y, int B, int Ho, int Wo, cudaStream_t st);
 int conv_tc_prepare_stem(ConvLayer& L, const float* w_raw, __nv_bfloat16* w_packed, cudaStream_t st);
 size_t conv_tc_stem_scratch_bytes(int B, int H, int W);
+void launch_stem_pack(const float* img, const unsigned char* img_u8, __nv_bfloat16* scratch, int B, int H, int W,
+                      cudaStream_t st);
+// stem_pool.cu: conv1 + bn1 + ReLU + maxpool in one kernel, from the packed image
+size_t stem_pool_weight_bytes();
+void launch_pack_stem_pool_weight(const float* w, void* packed, cudaStream_t st);
+int launch_stem_pool(const void* in, const void* packed_w, const float* scale, const float* shift, __nv_bfloat16* y, int B,
+                     cudaStream_t st);
 int launch_conv_tc_stem(const ConvLayer& L, const float* img, const unsigned char* img_u8, __nv_bfloat16* scratch,
                         __nv_bfloat16* y, int B, int H, int W, cudaStream_t st);
 

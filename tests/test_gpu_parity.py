@@ -502,3 +502,29 @@ def test_bone_coef_tf32_tensor_core_vs_cuda_core(synth_sd, monkeypatch, stage, S
     frac = float(((a - b).abs() > 0).float().mean())
     print(f"tf32 bone_coef vs fp32: max rel err {err:.2e}, {100 * frac:.2f}% of outputs differ")
     assert err < 1.5e-2  # a couple of bf16 ulps of the largest value
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_fused_stem_pool_vs_split_kernels(synth_sd, monkeypatch, B):
+    """bf16 configuration: conv1+bn1+ReLU+maxpool as ONE kernel (stem_pool.cu: no-swizzle overlapping-window UMMA operand,
+    conv rows pooled out of a shared-memory ring) against the TMA implicit-GEMM stem + separate max-pool kernel
+    (DIRB200_STEM_SPLIT=1). Same bf16 operands and fp32 accumulation: the backbone outputs agree to bf16 rounding."""
+    from dir_b200 import seams
+
+    fused = _make(synth_sd, "bf16", max_batch=4)
+    monkeypatch.setenv("DIRB200_STEM_SPLIT", "1")
+    split = _make(synth_sd, "bf16", max_batch=4)
+    split._ensure_handle()
+    monkeypatch.delenv("DIRB200_STEM_SPLIT")
+    img = torch.randn(B, 3, 256, 256, generator=torch.Generator().manual_seed(40 + B)).cuda()
+    fa, fb = seams.backbone(fused, img), seams.backbone(split, img)
+    for name, a, b in zip(("c1", "c2", "c3", "c4"), fa, fb):
+        assert bool(torch.isfinite(a).all())
+        e = float((a - b).abs().max() / b.abs().max())
+        print(f"fused stem vs split, {name}: max rel err {e:.2e}")
+        assert e < 2e-2, name
+    ra, rb = fused.run_raw(img)["record"], split.run_raw(img)["record"]
+    assert rel(ra, rb) < 5e-2
+    n_f = fused._handle.lib.dirb200_forward_launches(fused._handle.h, B)
+    n_s = split._handle.lib.dirb200_forward_launches(split._handle.h, B)
+    assert n_f == n_s - 1  # the max-pool launch is gone
