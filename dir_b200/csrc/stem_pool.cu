@@ -10,8 +10,9 @@
 //    the tensor core reads overlapping windows straight out of the raw input row in shared memory. One bulk copy
 //    (2112 B) per input row per unit replaces 128 TMA requests per output row and kernel row;
 //  * a unit = (image, 8 pooled rows) = 17 conv rows (one halo row recomputed); conv rows go TMEM -> bn/ReLU -> bf16
-//    -> a 4-row smem ring, and every second row the 3x3/s2 max of the last three rows is written to HBM: the conv map
-//    never leaves the SM (HBM traffic 268+268+67 MB -> 67 MB).
+//    registers; a thread keeps its pixel's last two rows, so the vertical 3-max never touches memory; every second
+//    row that maximum goes through a double-buffered smem row for the horizontal stride-2 3-max and the pooled row
+//    is written to HBM: the conv map never leaves the SM (HBM traffic 268+268+67 MB -> 67 MB).
 // Roles (320 threads): warps 0-7 epilogue + pooling (two threads per output pixel), warp 8 input-row producer,
 // warp 9 TMEM alloc + MMA issue. 14 tcgen05.mma (M=128, N=64, K=16) per conv row.
 #include "../../include/dirb200.h"
@@ -27,15 +28,16 @@ using namespace tc;
 
 constexpr int SP_THREADS = 320;
 constexpr int ROW_BYTES = 264 * 8;   // one padded NHWC4 bf16 input row (W + 8 = 264 px)
-constexpr int IN_RING = 16;          // input-row slots
+constexpr int IN_RING = 16;          // input-row slots (7 live per conv row + prefetch)
 constexpr int W_BYTES = 7 * 4096;    // weights: 7 kernel rows x [64 n][32 k] bf16, no-swizzle core-matrix layout
 constexpr int CONV_ROW = 128 * 128;  // one conv output row in smem: 128 px x 64 ch bf16
-constexpr int CRING = 4;
+constexpr int CRING = 2;             // double-buffered row of vertical maxima
 constexpr int OFF_IN = 0;
 constexpr int OFF_W = OFF_IN + IN_RING * ROW_BYTES;  // 33792
 constexpr int OFF_C = OFF_W + W_BYTES;               // 62464
-constexpr int OFF_BARS = OFF_C + CRING * CONV_ROW;   // 128000
-constexpr int SP_SMEM = 1024 + OFF_BARS + 512;
+constexpr int OFF_AFF = OFF_C + CRING * CONV_ROW;    // bn1 scale | shift (2 x 64 floats)
+constexpr int OFF_BARS = OFF_AFF + 512;
+constexpr int SP_SMEM = 1024 + OFF_BARS + 512;       // ~104 KB: two CTAs per SM hide each other's epilogue latency
 constexpr int ACC_BUFS = 4;
 
 struct SpBars {
@@ -80,7 +82,7 @@ __device__ __forceinline__ UnitGeom unit_geom(int u) {
   return g;
 }
 
-__global__ void __launch_bounds__(SP_THREADS, 1)
+__global__ void __launch_bounds__(SP_THREADS, 2)
 stem_pool_kernel(const uint8_t* __restrict__ in /*[B][256][264][4] bf16*/, const uint8_t* __restrict__ wpk,
                  const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int B) {
   extern __shared__ uint8_t smem_raw[];
@@ -180,24 +182,28 @@ stem_pool_kernel(const uint8_t* __restrict__ in /*[B][256][264][4] bf16*/, const
     // ===================================================== epilogue + pooling: thread = (pixel, channel half)
     const int px = threadIdx.x & 127, half = threadIdx.x >> 7;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float sc[32], sh[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      sc[i] = __ldg(scale + 32 * half + i);
-      sh[i] = __ldg(shift + 32 * half + i);
+    float* aff = reinterpret_cast<float*>(smem + OFF_AFF);
+    if (threadIdx.x < 64) {
+      aff[threadIdx.x] = __ldg(scale + threadIdx.x);
+      aff[64 + threadIdx.x] = __ldg(shift + threadIdx.x);
     }
-    uint8_t* cring = smem + OFF_C;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float* sc = aff + 32 * half;
+    const float* sh = aff + 64 + 32 * half;
+    uint8_t* vbuf = smem + OFF_C;  // 2 x [128 px][128 B]: vertical 3-max of the conv rows of one pooled row
     const int ppx = threadIdx.x >> 2, quarter = threadIdx.x & 3;  // pooling role: pooled pixel, 16-channel quarter
-    uint32_t nrow = 0;
+    uint32_t nrow = 0, npool = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const UnitGeom g = unit_geom(u);
+      uint4 prev1[4], prev2[4];  // this pixel's 32 channels of conv rows j-1 and j-2 (post-ReLU: 0 == -inf padding)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) prev1[c] = prev2[c] = make_uint4(0u, 0u, 0u, 0u);
       for (int j = 0; j < 17; ++j) {
         const int ho = g.ho0 + j;
-        uint8_t* crow = cring + (j & (CRING - 1)) * CONV_ROW + px * 128;
-        uint4 packed[4];
+        uint4 cur[4];
         if (ho < 0) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) packed[c] = make_uint4(0u, 0u, 0u, 0u);  // post-ReLU values are >= 0: 0 == -inf pad
+          for (int c = 0; c < 4; ++c) cur[c] = make_uint4(0u, 0u, 0u, 0u);
         } else {
           const uint32_t buf = nrow % ACC_BUFS;
           mbar_wait(&bars->tfull[buf], (nrow / ACC_BUFS) & 1);
@@ -210,42 +216,46 @@ stem_pool_kernel(const uint8_t* __restrict__ in /*[B][256][264][4] bf16*/, const
           ++nrow;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            uint32_t w4[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int i = 8 * c + 2 * e;
-              const float a = fmaxf(fmaf(v[i], sc[i], sh[i]), 0.f), bq = fmaxf(fmaf(v[i + 1], sc[i + 1], sh[i + 1]), 0.f);
-              __nv_bfloat162 hh = __floats2bfloat162_rn(a, bq);
-              w4[e] = *reinterpret_cast<uint32_t*>(&hh);
-            }
-            packed[c] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            const float4 s0 = *reinterpret_cast<const float4*>(sc + 8 * c), s1 = *reinterpret_cast<const float4*>(sc + 8 * c + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(sh + 8 * c), h1 = *reinterpret_cast<const float4*>(sh + 8 * c + 4);
+            const float* vv = v + 8 * c;
+            __nv_bfloat162 q0 = __floats2bfloat162_rn(fmaxf(fmaf(vv[0], s0.x, h0.x), 0.f), fmaxf(fmaf(vv[1], s0.y, h0.y), 0.f));
+            __nv_bfloat162 q1 = __floats2bfloat162_rn(fmaxf(fmaf(vv[2], s0.z, h0.z), 0.f), fmaxf(fmaf(vv[3], s0.w, h0.w), 0.f));
+            __nv_bfloat162 q2 = __floats2bfloat162_rn(fmaxf(fmaf(vv[4], s1.x, h1.x), 0.f), fmaxf(fmaf(vv[5], s1.y, h1.y), 0.f));
+            __nv_bfloat162 q3 = __floats2bfloat162_rn(fmaxf(fmaf(vv[6], s1.z, h1.z), 0.f), fmaxf(fmaf(vv[7], s1.w, h1.w), 0.f));
+            cur[c] = make_uint4(*reinterpret_cast<uint32_t*>(&q0), *reinterpret_cast<uint32_t*>(&q1),
+                                *reinterpret_cast<uint32_t*>(&q2), *reinterpret_cast<uint32_t*>(&q3));
           }
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c)  // 16-byte chunk (4*half + c) of this pixel, XOR-swizzled against bank conflicts
-          *reinterpret_cast<uint4*>(crow + (((4 * half + c) ^ (px & 7)) << 4)) = packed[c];
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (j >= 2 && (j & 1) == 0) {  // conv rows j-2, j-1, j = 2po-1, 2po, 2po+1
+        if (j >= 2 && (j & 1) == 0) {  // conv rows j-2, j-1, j = 2po-1, 2po, 2po+1: vertical max stays in registers
           const int po = 8 * g.q + (j >> 1) - 1;
+          uint8_t* vb = vbuf + (npool & 1) * CONV_ROW;
+          uint8_t* vrow = vb + px * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)  // 16-byte chunk (4*half + c) of this pixel, XOR-swizzled against bank conflicts
+            *reinterpret_cast<uint4*>(vrow + (((4 * half + c) ^ (px & 7)) << 4)) =
+                max_bf16x8(max_bf16x8(prev2[c], prev1[c]), cur[c]);
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // (the buffer written two pooled rows ago is free again)
           uint4 m0 = make_uint4(0u, 0u, 0u, 0u), m1 = m0;
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const uint8_t* rrow = cring + ((j - 2 + dy) & (CRING - 1)) * CONV_ROW;
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-              const int p = 2 * ppx + dx;
-              if (p < 0) continue;
-              const uint8_t* pp = rrow + p * 128;
-              m0 = max_bf16x8(m0, *reinterpret_cast<const uint4*>(pp + (((2 * quarter) ^ (p & 7)) << 4)));
-              m1 = max_bf16x8(m1, *reinterpret_cast<const uint4*>(pp + (((2 * quarter + 1) ^ (p & 7)) << 4)));
-            }
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int p = 2 * ppx + dx;
+            if (p < 0) continue;
+            const uint8_t* pp = vb + p * 128;
+            m0 = max_bf16x8(m0, *reinterpret_cast<const uint4*>(pp + (((2 * quarter) ^ (p & 7)) << 4)));
+            m1 = max_bf16x8(m1, *reinterpret_cast<const uint4*>(pp + (((2 * quarter + 1) ^ (p & 7)) << 4)));
           }
           uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)g.b * 64 + po) * 64 + ppx) * 64 + 16 * quarter);
           dst[0] = m0;
           dst[1] = m1;
+          ++npool;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          prev2[c] = prev1[c];
+          prev1[c] = cur[c];
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the next unit's first rows reuse the slots the last pooling read
     }
   }
   fence_before();
@@ -285,7 +295,7 @@ int launch_stem_pool(const void* in, const void* packed_w, const float* scale, c
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int units = B * 8;
-  launch_pdl(stem_pool_kernel, dim3(units < sms ? units : sms), dim3(SP_THREADS), SP_SMEM, st,
+  launch_pdl(stem_pool_kernel, dim3(units < 2 * sms ? units : 2 * sms), dim3(SP_THREADS), SP_SMEM, st,
              reinterpret_cast<const uint8_t*>(in), reinterpret_cast<const uint8_t*>(packed_w), scale, shift, y, B);
   return DIRB200_OK;
 }
