@@ -66,6 +66,8 @@ extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
     h->e.disable_pair_fusion = nopair && nopair[0] == '1';
     const char* dense = getenv("DIRB200_DENSE_FUSION");
     h->e.dense_fusion = dense && dense[0] == '1';
+    const char* nov = getenv("DIRB200_NO_OVERLAP");
+    h->e.no_overlap = nov && nov[0] == '1';
     const char* ssplit = getenv("DIRB200_STEM_SPLIT");
     h->e.stem_split = ssplit && ssplit[0] == '1';
     const char* csimt = getenv("DIRB200_COEF_SIMT");
@@ -327,6 +329,7 @@ static int seam_stage(Engine& e, int s, const float* img_feat, const float* prev
   int rc = e.run_stage<T>(s, x, prev_rec, DIRB200_STAGE_FLOATS, prev_para, 128, B, rec, DIRB200_STAGE_FLOATS, para, 128,
                           &out, &jf, vis, ar, st);
   if (rc) return rc;
+  if (vis && e.side && !e.no_overlap) cudaStreamWaitEvent(st, e.ev_join[1], 0);  // rasteriser ran on the side stream
   launch_nhwc_to_nchw<T>(out, img_feat_out, B, 256, S, S, st);
   if (joint_feat)
     cudaMemcpyAsync(joint_feat, jf, (size_t)B * 42 * 64 * sizeof(float), cudaMemcpyDeviceToDevice, st);

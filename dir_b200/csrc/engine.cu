@@ -25,6 +25,11 @@ bool pdl_enabled() {
   } while (0)
 
 Engine::~Engine() {
+  if (side) cudaStreamDestroy(side);
+  for (int i = 0; i < 2; ++i) {
+    if (ev_fork[i]) cudaEventDestroy(ev_fork[i]);
+    if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+  }
   for (void* p : owned) cudaFree(p);
   for (auto& r : prof) {
     cudaEventDestroy(r.a);
@@ -334,6 +339,13 @@ static ConvLayer concat_convs(Engine& e, const std::string& w0, const std::strin
 int Engine::build(cudaStream_t st) {
   fin_stream = st;
   required.clear();
+  if (!dry && !side && !no_overlap) {
+    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) side = nullptr;
+    for (int i = 0; i < 2 && side; ++i) {
+      cudaEventCreateWithFlags(&ev_fork[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming);
+    }
+  }
   // ---- backbone (models/backbone/resnet.py)
   stem = make_conv("backbone.conv1.weight", "", "backbone.bn1.", 2, 3, 1);
   if (!dry && bf16() && err.empty()) {
@@ -769,6 +781,16 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
   a.B = B;
   launch_regress_mano(a, st);
   launches += 8;
+  const bool vis_on_side = vis_nchw && side && !no_overlap;
+  if (vis_on_side) {  // proj_feat (aux output) depends only on this stage's uv + joint features: HBM-bound, so it runs
+                      // on the side stream underneath the instruction-bound fusion kernels; forward() joins ev_join[1]
+    cudaEventRecord(ev_fork[1], st);
+    cudaStreamWaitEvent(side, ev_fork[1], 0);
+    launch_bone_vis_nchw(stage_rec + DIRB200_OFF_UV_L, stage_rec + DIRB200_OFF_UV_R, rec_stride, jfeat, jfeat + 21 * 64,
+                         42 * 64, vis_nchw, B, S, sw.distance, 1, side);
+    cudaEventRecord(ev_join[1], side);
+    ++launches;
+  }
   if (dense_fusion) {
     launch_bone_raster<T>(stage_rec, rec_stride, jfeat, bone, B, S, sw.distance, st);
     ++launches;
@@ -783,7 +805,7 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
     launches += 2;
   }
   conv<T>(sw.fusion3, fus_mid, out, nullptr, B, S, S, st);
-  if (vis_nchw) {
+  if (vis_nchw && !vis_on_side) {
     launch_bone_vis_nchw(stage_rec + DIRB200_OFF_UV_L, stage_rec + DIRB200_OFF_UV_R, rec_stride, jfeat, jfeat + 21 * 64,
                          42 * 64, vis_nchw, B, S, sw.distance, 1, st);
     ++launches;
@@ -825,6 +847,26 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   const ResidualBlock& fus4 = res["decoder.fusion_layer4."];
   concat(c4, 2048, 1, c3_skip, 256, fus4, 16, &raw, &act);
   T* fusion4 = run_residual<T>(fus4, raw, act, B, 16, 16, ar, st);
+  // skip_layer3 (models/dir.py:459) needs only c2: fork it onto the side stream here, so its convs fill the SMs that
+  // stage 1's small joint-space grids (SemGCN, mixSTE, MANO: 64-336 CTAs, latency-bound) leave idle
+  const ResidualBlock& skip3 = res["decoder.skip_layer3."];
+  const bool overlap = side && !no_overlap && !plan;
+  cudaStream_t st3 = overlap ? side : st;
+  if (overlap) {
+    cudaEventRecord(ev_fork[0], st);
+    cudaStreamWaitEvent(side, ev_fork[0], 0);
+  }
+  T *raw3 = nullptr, *act3 = nullptr;
+  {
+    const int64_t n = (int64_t)B * 32 * 32 * 512;
+    act3 = aalloc<T>(ar, n);
+    if (!plan && !ar.overflow) {
+      launch_concat_preact<T>(c2, 512, 0, (const T*)nullptr, 0, skip3.bn1s, skip3.bn1b, raw3, act3, B, 32, 32, st3);
+      ++launches;
+    }
+  }
+  T* c2_skip = run_residual<T>(skip3, c2, act3, B, 32, 32, ar, st3);
+  if (overlap) cudaEventRecord(ev_join[0], side);
   T* img_feat1 = nullptr;
   rc = run_stage<T>(0, fusion4, rec, RS, para, PS, B, plan ? nullptr : rec + DIRB200_STAGE_FLOATS, RS,
                     plan ? nullptr : para + 128, PS, &img_feat1, nullptr, nullptr, ar, st);
@@ -833,9 +875,7 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   concat(fusion4, 256, 0, img_feat1, 256, enh4, 16, &raw, &act);
   T* enhance4 = run_residual<T>(enh4, raw, act, B, 16, 16, ar, st);
   // ---- stage 2 @32x32 (models/dir.py:459-471)
-  const ResidualBlock& skip3 = res["decoder.skip_layer3."];
-  concat(c2, 512, 0, nullptr, 0, skip3, 32, &raw, &act);
-  T* c2_skip = run_residual<T>(skip3, c2, act, B, 32, 32, ar, st);
+  if (overlap) cudaStreamWaitEvent(st, ev_join[0], 0);
   const ResidualBlock& fus3 = res["decoder.fusion_layer3."];
   concat(enhance4, 256, 1, c2_skip, 256, fus3, 32, &raw, &act);
   T* fusion3 = run_residual<T>(fus3, raw, act, B, 32, 32, ar, st);
@@ -864,6 +904,7 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   }
   if (plan) return DIRB200_OK;
   if (ar.overflow) return DIRB200_E_WORKSPACE;
+  if (aux && side && !no_overlap) cudaStreamWaitEvent(st, ev_join[1], 0);  // proj_feat rasteriser (run_stage)
   last_forward_launches = launches;
   if (sticky_rc) return sticky_rc;
   CK(cudaPeekAtLastError());

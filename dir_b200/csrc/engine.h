@@ -100,6 +100,12 @@ struct Engine {
   int last_forward_launches = 0;
   int tc_launches = 0;      // convs that went to the tcgen05 kernel since the last forward() start
   int sticky_rc = 0;        // first launch error inside a forward
+  // Side stream for the two independent branches of the decoder (forked / joined with events relative to the
+  // caller's stream, so a forward stays one asynchronous, graph-capturable unit): skip_layer3 (needs only c2) runs
+  // under stage 1's latency-bound joint-space kernels, the HBM-bound proj_feat rasteriser under stage 2's fusion.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+  bool no_overlap = false;    // DIRB200_NO_OVERLAP=1: everything on the caller's stream
   bool coef_simt = false;     // DIRB200_COEF_SIMT=1: fp32 CUDA-core bone_coef also in the bf16 configuration
   bool stem_split = false;    // DIRB200_STEM_SPLIT=1: stem conv and max-pool as two kernels (TMA implicit GEMM + pool)
   const void* stem_pool_w = nullptr;  // conv1 weights packed for stem_pool_kernel
