@@ -81,6 +81,8 @@ __global__ void maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int B
 // ---------------------------------------------------------------- upsample(2x bilinear, align_corners=False) + concat + BN/ReLU
 // models/dir.py:442-444,455,459-461,470 and hourglass.py:60-61 (bn1+relu1 of the consuming Residual).
 // One CTA per output pixel (all index math once per CTA, 32-bit); threads stride over 8-channel vectors.
+// (Several pixels per CTA or several vectors per thread were measured and are not faster: the kernel writes 2-5x
+// more than it reads and sits at the ~3.9 TB/s every write-dominated kernel of this pipeline reaches.)
 template <typename T>
 __global__ void __launch_bounds__(128) concat_preact_kernel(const T* __restrict__ s0, int C0, int up0,
                                                             const T* __restrict__ s1, int C1,
@@ -333,30 +335,59 @@ __global__ void attn_logits_kernel(const T* __restrict__ a, const float* __restr
   if (lane == 0) attn[bp * 2 + hand] = 1.f / (1.f + expf(-(s + bias[hand])));
 }
 
+// grid (B, C/512), 256 threads = 64 groups of 8 channels x 4 pixel quarters: every thread streams 16-byte vectors of
+// P/4 pixels (independent loads), the quarters meet in shared memory. Accumulation order over the pixels differs from
+// a sequential sum only in association (fp32).
 template <typename T>
-__global__ void attn_pool_kernel(const T* __restrict__ f, const float* __restrict__ attn, float* __restrict__ pooled,
-                                 int P, int C) {
+__global__ void __launch_bounds__(256) attn_pool_kernel(const T* __restrict__ f, const float* __restrict__ attn,
+                                                        float* __restrict__ pooled, int P, int C) {
   pdl_wait();
-  extern __shared__ float sa[];  // [P][2]
-  int b = blockIdx.x;
+  extern __shared__ float sa[];  // [P][2] attention, then [4][3][512] partial sums
+  float* part = sa + P * 2;
+  const int b = blockIdx.x, c0 = blockIdx.y * 512;
   for (int i = threadIdx.x; i < P * 2; i += blockDim.x) sa[i] = attn[(int64_t)b * P * 2 + i];
+  __syncthreads();
+  const int g = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const int pq = P >> 2;
+  float al[8], ar[8], am[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) al[i] = ar[i] = am[i] = 0.f;
+  const T* base = f + ((int64_t)b * P + q * pq) * C + c0 + g * 8;
+#pragma unroll 4
+  for (int p = 0; p < pq; ++p) {
+    float v[8];
+    Vec8<T>::ld(base + (int64_t)p * C, v);
+    const float wl = sa[(q * pq + p) * 2], wr = sa[(q * pq + p) * 2 + 1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      al[i] = fmaf(v[i], wl, al[i]);
+      ar[i] = fmaf(v[i], wr, ar[i]);
+      am[i] += v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    part[(q * 3 + 0) * 512 + g * 8 + i] = al[i];
+    part[(q * 3 + 1) * 512 + g * 8 + i] = ar[i];
+    part[(q * 3 + 2) * 512 + g * 8 + i] = am[i];
+  }
   __syncthreads();
   float sl = 0.f, sr = 0.f;
   for (int p = 0; p < P; ++p) {
     sl += sa[p * 2];
     sr += sa[p * 2 + 1];
   }
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float al = 0.f, ar = 0.f, am = 0.f;
-    for (int p = 0; p < P; ++p) {
-      float v = ActIO<T>::ld(f + ((int64_t)b * P + p) * C + c);
-      al = fmaf(v, sa[p * 2], al);
-      ar = fmaf(v, sa[p * 2 + 1], ar);
-      am += v;
+  for (int c = threadIdx.x; c < 512; c += blockDim.x) {
+    float tl = 0.f, tr = 0.f, tm = 0.f;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      tl += part[(qq * 3 + 0) * 512 + c];
+      tr += part[(qq * 3 + 1) * 512 + c];
+      tm += part[(qq * 3 + 2) * 512 + c];
     }
-    pooled[((int64_t)b * 3 + 0) * C + c] = al / (sl + 1e-8f);
-    pooled[((int64_t)b * 3 + 1) * C + c] = ar / (sr + 1e-8f);
-    pooled[((int64_t)b * 3 + 2) * C + c] = am / (float)P;
+    pooled[((int64_t)b * 3 + 0) * C + c0 + c] = tl / (sl + 1e-8f);
+    pooled[((int64_t)b * 3 + 1) * C + c0 + c] = tr / (sr + 1e-8f);
+    pooled[((int64_t)b * 3 + 2) * C + c0 + c] = tm / (float)P;
   }
 }
 
@@ -374,7 +405,8 @@ void launch_concat_preact(const T* s0, int C0, int up0, const T* s1, int C1, con
                           T* act, int B, int Ho, int Wo, cudaStream_t st) {
   const int C = C0 + C1;
   const int threads = C >= 1024 ? 128 : (C >= 512 ? 64 : 32);
-  launch_pdl(concat_preact_kernel<T>, dim3((unsigned)(B * Ho * Wo)), dim3(threads), 0, st, s0, C0, up0, s1, C1, bns, bnb, raw, act, Ho, Wo);
+  launch_pdl(concat_preact_kernel<T>, dim3((unsigned)(B * Ho * Wo)), dim3(threads), 0, st, s0, C0, up0, s1, C1, bns, bnb,
+             raw, act, Ho, Wo);
 }
 
 template <typename T>
@@ -431,7 +463,9 @@ void launch_attn_logits(const T* a, const float* w, const float* bias, float* at
 
 template <typename T>
 void launch_attn_pool(const T* f, const float* attn, float* pooled, int B, int P, int C, cudaStream_t st) {
-  launch_pdl(attn_pool_kernel<T>, dim3(B), dim3(256), P * 2 * sizeof(float), st, f, attn, pooled, P, C);
+  // C is a multiple of 512 and P of 4 for every caller (2048 channels, 8x8 map; models/dir.py:263-268)
+  launch_pdl(attn_pool_kernel<T>, dim3(B, C / 512), dim3(256), (P * 2 + 4 * 3 * 512) * sizeof(float), st, f, attn, pooled,
+             P, C);
 }
 
 #define INST(T)                                                                                                      \
