@@ -230,6 +230,12 @@ void Engine::build_stage(int s, const std::string& p) {
     for (int l = 0; l < 4; ++l) {
       std::string q = p + "gcn_" + sd + ".gconv_layers." + std::to_string(l) + ".";
       st.gcn[l].W[h] = copy_of(q + "gconv.W");
+      if (bf16()) {
+        const float* gw = W(q + "gconv.W", {2, 21, 128, 128});
+        float* pk = dalloc(gcn_tc_packed_bytes() / 4);
+        if (!dry && gw && pk) launch_pack_gcn_weight_tc(gw, pk, fin_stream);
+        st.gcn[l].Wtc[h] = pk;
+      }
       const float* e1 = W(q + "gconv.e_1");
       float* A = dalloc(21 * 21);
       if (!dry && e1 && A) launch_gcn_adjacency(e1, A, fin_stream);
@@ -739,7 +745,10 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
     g.hout = hout;
     for (int h = 0; h < 2; ++h) g.W[h] = sw.gcn[l].W[h];
     g.B = B;
-    launch_gcn_gemm(g, st);
+    if (std::is_same<T, __nv_bfloat16>::value && sw.gcn[l].Wtc[0] && sw.gcn[l].Wtc[1] && !gcn_simt)
+      launch_gcn_gemm_tc(g, sw.gcn[l].Wtc[0], sw.gcn[l].Wtc[1], st);
+    else
+      launch_gcn_gemm(g, st);
     hin = hout;
     hout = (hout == gh0) ? gh1 : gh0;
   }

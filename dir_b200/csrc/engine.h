@@ -59,6 +59,7 @@ struct StageWeights {
   PointMlp filters[2], pos[2], gpos, proj_feat;
   struct Gcn {
     const float* W[2];
+    const void* Wtc[2] = {nullptr, nullptr};  // bf16 configuration: tf32 operand tiles of gcn_gemm_tc_kernel
     const float* A1[2];
     const float* scale[2];
     const float* shift[2];
@@ -106,6 +107,7 @@ struct Engine {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
   bool no_overlap = false;    // DIRB200_NO_OVERLAP=1: everything on the caller's stream
+  bool gcn_simt = false;      // DIRB200_GCN_SIMT=1: fp32 CUDA-core SemGCN GEMMs also in the bf16 configuration
   bool coef_simt = false;     // DIRB200_COEF_SIMT=1: fp32 CUDA-core bone_coef also in the bf16 configuration
   bool stem_split = false;    // DIRB200_STEM_SPLIT=1: stem conv and max-pool as two kernels (TMA implicit GEMM + pool)
   const void* stem_pool_w = nullptr;  // conv1 weights packed for stem_pool_kernel

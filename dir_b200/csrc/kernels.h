@@ -98,6 +98,10 @@ struct GcnGemmArgs {
   int B;
 };
 void launch_gcn_gemm(const GcnGemmArgs& a, cudaStream_t st);
+// tensor-core version (gcn_tc.cu, kind::tf32): per hand and layer a packed copy of gconv.W (gcn_tc_packed_bytes())
+size_t gcn_tc_packed_bytes();
+void launch_pack_gcn_weight_tc(const float* w /*(2,21,128,128)*/, void* wpk, cudaStream_t st);
+void launch_gcn_gemm_tc(const GcnGemmArgs& a, const void* wpk_left, const void* wpk_right, cudaStream_t st);
 struct GcnFinishArgs {  // tokens = relu(bn(agg(H))) + global_pos_emb(xyz/0.15 -/+ offset/2)   (models/dir.py:103-110)
   const float* hin;
   GcnAgg agg;

@@ -528,3 +528,38 @@ def test_fused_stem_pool_vs_split_kernels(synth_sd, monkeypatch, B):
     n_f = fused._handle.lib.dirb200_forward_launches(fused._handle.h, B)
     n_s = split._handle.lib.dirb200_forward_launches(split._handle.h, B)
     assert n_f == n_s - 1  # the max-pool launch is gone
+
+
+@pytest.mark.parametrize("stage,S,B", [(1, 16, 3), (2, 32, 130)])
+def test_gcn_tf32_tensor_core_vs_cuda_core(synth_sd, monkeypatch, stage, S, B):
+    """bf16 configuration: the SemGCN layer products as tcgen05 kind::tf32 GEMMs (gcn_tc.cu) against the fp32
+    CUDA-core kernel (DIRB200_GCN_SIMT=1), through the joint2bone seam; both sides use the fp32 mixSTE so that only
+    the GCN differs. B=130: one full 128-image tile plus a ragged one."""
+    from dir_b200 import seams
+
+    monkeypatch.setenv("DIRB200_STE_SIMT", "1")
+    tc = _make(synth_sd, "bf16", max_batch=130)
+    tc._ensure_handle()
+    monkeypatch.setenv("DIRB200_GCN_SIMT", "1")
+    simt = _make(synth_sd, "bf16", max_batch=130)
+    simt._ensure_handle()
+    monkeypatch.delenv("DIRB200_GCN_SIMT")
+    monkeypatch.delenv("DIRB200_STE_SIMT")
+    gen = torch.Generator().manual_seed(900 + stage)
+    prev = {"pd_joint_xyz_left": torch.randn(B, 21, 3, generator=gen) * 0.05,
+            "pd_joint_xyz_right": torch.randn(B, 21, 3, generator=gen) * 0.05,
+            "pd_joint_uv_left": (torch.rand(B, 21, 2, generator=gen) * 2 - 1) * 0.8,
+            "pd_joint_uv_right": (torch.rand(B, 21, 2, generator=gen) * 2 - 1) * 0.8,
+            "pd_mano_para_left": torch.randn(B, 64, generator=gen) * 0.3,
+            "pd_mano_para_right": torch.randn(B, 64, generator=gen) * 0.3,
+            "pd_offset": torch.randn(B, 3, generator=gen) * 0.5}
+    feat = torch.randn(B, 256, S, S, generator=gen).cuda()
+    prev = {k: v.cuda() for k, v in prev.items()}
+    ra, fa = seams.joint2bone(tc, stage, feat, prev)
+    rb, fb = seams.joint2bone(simt, stage, feat, prev)
+    worst = {k: rel(fa[k], fb[k]) for k in ("joint_feat_left", "joint_feat_right")}
+    worst.update({k: rel(ra[k], rb[k]) for k in ("pd_mano_para_left", "pd_mesh_xyz_left", "pd_mesh_xyz_right")})
+    print("tf32 SemGCN vs fp32:", {k: f"{v:.2e}" for k, v in worst.items()})
+    assert all(bool(torch.isfinite(v).all()) for v in ra.values() if v is not None)
+    assert max(worst["joint_feat_left"], worst["joint_feat_right"], worst["pd_mano_para_left"]) < 5e-3
+    assert max(worst.values()) < 3e-2  # the synthetic MANO heads amplify parameter noise ~5x into the mesh
