@@ -228,15 +228,24 @@ def main():
     # ---- end to end through the public API: pinned host input -> H2D -> forward -> D2H of the record
     e2e = None
     if not args.no_e2e:
-        out_host = torch.empty(B, capi.RECORD_FLOATS).pin_memory()
+        out_hosts = [torch.empty(B, capi.RECORD_FLOATS).pin_memory() for _ in range(2)]
+        d2h = torch.cuda.Stream(device=dev)  # the caller's download stream: result i leaves while forward i+1 runs
         Ke = max(3, min(K, 20))
+
+        def download(i, rec):
+            ev = torch.cuda.Event()
+            ev.record()
+            d2h.wait_event(ev)
+            with torch.cuda.stream(d2h):
+                out_hosts[i % 2].copy_(rec, non_blocking=True)
+            rec.record_stream(d2h)
 
         def e2e_step(i):
             outs, _ = net({"img": host[i % NBUF]}, None, None)  # forward() does the H2D copy (models/dir.py:514)
             rec = net_last_record(outs)
             if world > 1:
                 rec = net.allgather_records(rec)[rank * B:(rank + 1) * B]
-            out_host.copy_(rec, non_blocking=True)
+            download(i, rec)
 
         def net_last_record(outs):
             # the 3 stage dicts are views into one packed record; recover it without a copy
@@ -248,6 +257,7 @@ def main():
         e0.record()
         for i in range(Ke):
             e2e_step(i)
+        torch.cuda.current_stream().wait_stream(d2h)  # the last result must have reached the host inside the timed region
         e1.record()
         sync_all()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -268,7 +278,7 @@ def main():
             rec = outs[0]["pd_mesh_xyz_left"]._base
             if world > 1:
                 rec = net.allgather_records(rec)[rank * B:(rank + 1) * B]
-            out_host.copy_(rec, non_blocking=True)
+            download(i, rec)
 
         for i in range(3):
             u8_step(i)
@@ -276,6 +286,7 @@ def main():
         e0.record()
         for i in range(Ke):
             u8_step(i)
+        torch.cuda.current_stream().wait_stream(d2h)
         e1.record()
         sync_all()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev)
