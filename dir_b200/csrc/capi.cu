@@ -70,6 +70,8 @@ extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
     h->e.no_overlap = nov && nov[0] == '1';
     const char* ssplit = getenv("DIRB200_STEM_SPLIT");
     h->e.stem_split = ssplit && ssplit[0] == '1';
+    const char* fsimt = getenv("DIRB200_FUSION_SIMT");
+    h->e.fusion_simt = fsimt && fsimt[0] == '1';
     const char* gsimt = getenv("DIRB200_GCN_SIMT");
     h->e.gcn_simt = gsimt && gsimt[0] == '1';
     const char* csimt = getenv("DIRB200_COEF_SIMT");

@@ -809,8 +809,12 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
       launch_bone_coef_tc(jfeat, sw.fus_wp_tc, coef, B, st);
     else
       launch_bone_coef(jfeat, sw.fus_wp, coef, B, st);
-    launch_bone_fusion<T>(stage_rec, rec_stride, coef, sw.fusion0.scale, sw.fusion0.shift, fus_mid, B, S, sw.distance,
-                          st);
+    if (std::is_same<T, __nv_bfloat16>::value && !fusion_simt && (S == 16 || S == 32))
+      launch_bone_fusion_tc(stage_rec, rec_stride, coef, sw.fusion0.scale, sw.fusion0.shift,
+                            reinterpret_cast<__nv_bfloat16*>(fus_mid), B, S, sw.distance, st);
+    else
+      launch_bone_fusion<T>(stage_rec, rec_stride, coef, sw.fusion0.scale, sw.fusion0.shift, fus_mid, B, S, sw.distance,
+                            st);
     launches += 2;
   }
   conv<T>(sw.fusion3, fus_mid, out, nullptr, B, S, S, st);

@@ -107,6 +107,7 @@ struct Engine {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
   bool no_overlap = false;    // DIRB200_NO_OVERLAP=1: everything on the caller's stream
+  bool fusion_simt = false;   // DIRB200_FUSION_SIMT=1: CUDA-core sparse accumulate also in the bf16 configuration
   bool gcn_simt = false;      // DIRB200_GCN_SIMT=1: fp32 CUDA-core SemGCN GEMMs also in the bf16 configuration
   bool coef_simt = false;     // DIRB200_COEF_SIMT=1: fp32 CUDA-core bone_coef also in the bf16 configuration
   bool stem_split = false;    // DIRB200_STEM_SPLIT=1: stem conv and max-pool as two kernels (TMA implicit GEMM + pool)

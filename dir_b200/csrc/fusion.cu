@@ -424,6 +424,222 @@ __global__ void __launch_bounds__(256) bone_fusion_kernel(const float* __restric
   for (int x = 0; x < S; ++x) ActIO<T>::st(orow + x * 256, fmaxf(fmaf(s_out[x * 256 + n], sc, sh), 0.f));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// bone_fusion on the tensor cores (bf16 configuration). The sparse accumulate
+//     out[b, y, x, n] = sum_{bone, tap} mask(p) * ( wa(p) Pa[b,bone,tap,n] + wb(p) Pb[b,bone,tap,n] ),  p = (y,x) + tap - 1
+// is a GEMM per block of output rows:  out[m, n] = sum_k A[m, k] B[k, n],  m = (row, x) (128 output pixels per CTA),
+// k = (bone, endpoint role, tap):  A[m, k] = w_role(source pixel of m under tap) if that pixel lies on the bone else 0,
+// B[k, n] = P[b, bone, role, tap, n]. Every A element has exactly one possible source pixel, so A is written (never
+// accumulated) by the thread that evaluates that (pixel, bone) capsule test — no compaction, no lists, no atomics,
+// and the per-entry work is done ONCE instead of once per output channel (the CUDA-core kernel repeats it in 256
+// threads). K walks the image's ACTIVE bones (bounding box meets the row band) three at a time: 54 columns of a
+// 64-column bf16 chunk, double-buffered: 8 warps build chunk c+1 (capsule tests -> A; P rows -> B, bf16) while one
+// thread issues the 4 tcgen05.mma (M=128, N=256, K=16) of chunk c. Epilogue: TMEM -> bn/ReLU -> bf16 -> per-warp
+// padded patch -> coalesced stores (the 128 x 256 tile is one contiguous 64 KB block of the NHWC map).
+constexpr int FT_A = 128 * 128;  // bytes of one A chunk  [128 m][64 k] bf16
+constexpr int FT_B = 256 * 128;  // bytes of one B chunk  [256 n][64 k] bf16
+constexpr int FT_OFF_A = 0, FT_OFF_B = 2 * FT_A, FT_OFF_BAR = FT_OFF_B + 2 * FT_B;
+constexpr int FT_SMEM = 1024 + FT_OFF_BAR + 256;
+constexpr int FT_THREADS = 288;
+constexpr int FT_PATCH = 144;  // bytes per patch row: 64 bf16 + 16 pad
+
+struct FtBars {
+  uint64_t ready[2], free_[2], done;
+  uint32_t tmem_ptr;
+  int nact;
+  int act[40];
+};
+
+template <int S>
+__global__ void __launch_bounds__(FT_THREADS, 2)
+bone_fusion_tc_kernel(const float* __restrict__ rec, int rec_stride, const float* __restrict__ P,
+                      const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
+                      float distance) {
+  using namespace tc;
+  constexpr int R = 128 / S;            // output rows per CTA
+  constexpr int NPX = (R + 2) * S;      // source pixels a CTA looks at
+  constexpr int LOG2S = S == 32 ? 5 : 4;
+  static_assert(S == 16 || S == 32, "feature map sizes of projecter_4 / projecter_3 (models/dir.py:395,401)");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  FtBars* bars = reinterpret_cast<FtBars*>(smem + FT_OFF_BAR);
+  __shared__ BoneGeom geo[40];
+  __shared__ float uv[84];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x, y0 = blockIdx.y * R;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->ready[i], 256);
+      mbar_init(&bars->free_[i], 1);
+    }
+    mbar_init(&bars->done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&bars->tmem_ptr)), "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // zero both B chunks once: columns 54..63 are never written and must multiply A's zeros with finite values
+  for (int i = tid; i < 2 * FT_B / 16; i += FT_THREADS) reinterpret_cast<uint4*>(smem + FT_OFF_B)[i] = make_uint4(0u, 0u, 0u, 0u);
+  pdl_wait();
+  if (tid < 84) uv[tid] = rec[(int64_t)b * rec_stride + DIRB200_OFF_UV_L + tid];
+  __syncthreads();
+  if (tid < 40) geo[tid] = make_bone(uv + (tid / 20) * 42, tid % 20, S);
+  __syncthreads();
+  if (warp == 0) {  // active bones in ascending order: bounding box (+ distance) meets source rows y0-1 .. y0+R
+    int n = 0;
+    for (int base = 0; base < 40; base += 32) {
+      const int hb = base + lane;
+      bool on = false;
+      if (hb < 40) {
+        const BoneGeom g = geo[hb];
+        const float m = distance + 0.01f;
+        const float lo = fminf(g.ay, g.by) - m, hi = fmaxf(g.ay, g.by) + m;
+        // pixel centres of the band: y0 - 0.5 .. y0 + R + 0.5; NaN geometry (collapsed bone) compares false -> skipped,
+        // like the capsule test that can never pass for it
+        on = hi >= (float)y0 - 0.5f && lo <= (float)(y0 + R) + 0.5f;
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, on);
+      if (on) bars->act[n + __popc(mask & ((1u << lane) - 1))] = hb;
+      n += __popc(mask);
+    }
+    if (lane == 0) bars->nact = n;
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = bars->tmem_ptr;
+  const int nact = bars->nact, nchunks = (nact + 2) / 3;
+
+  if (warp == 8) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t sb = s32(smem);
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(&bars->ready[buf], (c >> 1) & 1);
+        fence_after();
+        const uint64_t da = desc128(sb + FT_OFF_A + buf * FT_A), db = desc128(sb + FT_OFF_B + buf * FT_B);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma(tmem, da + 2 * k, db + 2 * k, idesc(256), (c | k) ? 1u : 0u);
+        umma_commit(&bars->free_[buf]);
+      }
+      umma_commit(&bars->done);
+    }
+  } else {
+    // ===================================================== chunk builders (8 warps), then the epilogue
+    const float* Pimg = P + (int64_t)b * 40 * 2 * 9 * 256;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      uint8_t* At = smem + FT_OFF_A + buf * FT_A;
+      uint8_t* Bt = smem + FT_OFF_B + buf * FT_B;
+      if (c >= 2) mbar_wait(&bars->free_[buf], ((c >> 1) - 1) & 1);
+      for (int i = tid; i < FT_A / 16; i += 256) reinterpret_cast<uint4*>(At)[i] = make_uint4(0u, 0u, 0u, 0u);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // ---- A: capsule tests of this chunk's (up to) three bones over the band's source pixels
+      for (int id = tid; id < 3 * NPX; id += 256) {
+        const int s = id / NPX, pid = id - s * NPX;
+        if (3 * c + s >= nact) break;
+        const int hb = bars->act[3 * c + s];
+        const int ys = y0 - 1 + (pid >> LOG2S), xs = pid & (S - 1);
+        if (ys < 0 || ys >= S) continue;
+        float wa, wb;
+        if (bone_bbox_reject(geo[hb], xs + 0.5f, ys + 0.5f, distance)) continue;
+        if (!bone_weights(geo[hb], xs + 0.5f, ys + 0.5f, distance, wa, wb)) continue;
+        const __nv_bfloat16 ha = __float2bfloat16_rn(wa), hbq = __float2bfloat16_rn(wb);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int yl = ys - ky + 1 - y0;  // output row (local) fed through tap row ky
+          if (yl < 0 || yl >= R) continue;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int x = xs - kx + 1;
+            if (x < 0 || x >= S) continue;
+            const int m = yl * S + x, col = s * 18 + ky * 3 + kx;  // role a; role b = col + 9
+            __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(At + m * 128);
+            row[(((col >> 3) ^ (m & 7)) << 3) | (col & 7)] = ha;
+            row[((((col + 9) >> 3) ^ (m & 7)) << 3) | ((col + 9) & 7)] = hbq;
+          }
+        }
+      }
+      // ---- B: thread n gathers its channel of the chunk's 54 coefficient vectors (coalesced 1 KB rows of P)
+      {
+        const int n = tid;
+        __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(Bt + n * 128);
+#pragma unroll 1
+        for (int s = 0; s < 3; ++s) {
+          if (3 * c + s >= nact) {  // stale columns of an earlier chunk in this buffer: clear
+#pragma unroll
+            for (int t = 0; t < 18; ++t) {
+              const int col = s * 18 + t;
+              row[(((col >> 3) ^ (n & 7)) << 3) | (col & 7)] = __float2bfloat16_rn(0.f);
+            }
+            continue;
+          }
+          const float* src = Pimg + (int64_t)bars->act[3 * c + s] * (2 * 9 * 256) + n;
+          float v[18];
+#pragma unroll
+          for (int t = 0; t < 18; ++t) v[t] = __ldg(src + t * 256);  // t = role * 9 + tap
+#pragma unroll
+          for (int t = 0; t < 18; ++t) {
+            const int col = s * 18 + t;
+            row[(((col >> 3) ^ (n & 7)) << 3) | (col & 7)] = __float2bfloat16_rn(v[t]);
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&bars->ready[buf]);
+    }
+    mbar_wait(&bars->done, 0);
+    fence_after();
+    // ---- epilogue: warp = (TMEM lane quarter, 128-column half)
+    const int q = warp & 3, half = warp >> 2;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + 128 * half;
+    uint8_t* patch = smem + warp * (32 * FT_PATCH);  // aliases the A/B chunks: every MMA has completed
+    __nv_bfloat16* obase = out + ((int64_t)b * S * S + (int64_t)y0 * S) * 256;
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int col0 = 128 * half + 64 * cc;
+      float v[64];
+      if (nchunks > 0) {
+        tmem_ld32(trow + 64 * cc, v);
+        tmem_ld32(trow + 64 * cc + 32, v + 32);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = 0.f;
+      }
+      uint4* mine = reinterpret_cast<uint4*>(patch + lane * FT_PATCH);
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = 8 * g8 + 2 * e;
+          const float a0 = fmaxf(fmaf(v[i], __ldg(scale + col0 + i), __ldg(shift + col0 + i)), 0.f);
+          const float a1 = fmaxf(fmaf(v[i + 1], __ldg(scale + col0 + i + 1), __ldg(shift + col0 + i + 1)), 0.f);
+          __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
+          w4[e] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        mine[g8] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {  // 4 rows x 128 bytes per store instruction
+        const int rr = 4 * it + (lane >> 3), ch = lane & 7;
+        const uint4 o = *reinterpret_cast<const uint4*>(patch + rr * FT_PATCH + ch * 16);
+        *reinterpret_cast<uint4*>(obase + (int64_t)(q * 32 + rr) * 256 + col0 + ch * 8) = o;
+      }
+      __syncwarp();
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+}
+
 }  // namespace
 
 void launch_pack_fusion_weight(const float* w, float* wp, cudaStream_t st) {
@@ -474,6 +690,22 @@ void launch_bone_fusion(const float* rec, int rec_stride, const float* P, const 
     launch_pdl(bone_fusion_kernel<T, 16>, dim3(dim3(B, S)), dim3(256), smem, st, rec, rec_stride, P, scale, shift, out, distance);
   }
 }
+void launch_bone_fusion_tc(const float* rec, int rec_stride, const float* P, const float* scale, const float* shift,
+                           __nv_bfloat16* out, int B, int S, float distance, cudaStream_t st) {
+  static bool attr[2] = {false, false};
+  if (S == 32) {
+    if (!attr[0]) cudaFuncSetAttribute(bone_fusion_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
+    attr[0] = true;
+    launch_pdl(bone_fusion_tc_kernel<32>, dim3(B, 8), dim3(FT_THREADS), FT_SMEM, st, rec, rec_stride, P, scale, shift, out,
+               distance);
+  } else {
+    if (!attr[1]) cudaFuncSetAttribute(bone_fusion_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
+    attr[1] = true;
+    launch_pdl(bone_fusion_tc_kernel<16>, dim3(B, 2), dim3(FT_THREADS), FT_SMEM, st, rec, rec_stride, P, scale, shift, out,
+               distance);
+  }
+}
+
 template void launch_bone_fusion<float>(const float*, int, const float*, const float*, const float*, float*, int, int,
                                         float, cudaStream_t);
 template void launch_bone_fusion<__nv_bfloat16>(const float*, int, const float*, const float*, const float*,

@@ -563,3 +563,38 @@ def test_gcn_tf32_tensor_core_vs_cuda_core(synth_sd, monkeypatch, stage, S, B):
     assert all(bool(torch.isfinite(v).all()) for v in ra.values() if v is not None)
     assert max(worst["joint_feat_left"], worst["joint_feat_right"], worst["pd_mano_para_left"]) < 5e-3
     assert max(worst.values()) < 3e-2  # the synthetic MANO heads amplify parameter noise ~5x into the mesh
+
+
+@pytest.mark.parametrize("stage,S,B,uv_range", [(1, 16, 3, 0.8), (2, 32, 5, 0.8), (2, 32, 4, 3.0), (1, 16, 2, 0.0)])
+def test_bone_fusion_tensor_core_vs_cuda_core(synth_sd, monkeypatch, stage, S, B, uv_range):
+    """bf16 configuration: the sparse bone accumulate as a per-row-block tcgen05 GEMM (A = capsule weights written in
+    place, B = coefficient vectors, both bf16) against the fp32 CUDA-core accumulate (DIRB200_FUSION_SIMT=1).
+    uv_range 3.0: bones partly / fully off the map; 0.0: every bone collapsed (empty masks -> bias only)."""
+    from dir_b200 import seams
+
+    tc = _make(synth_sd, "bf16", max_batch=8)
+    monkeypatch.setenv("DIRB200_FUSION_SIMT", "1")
+    simt = _make(synth_sd, "bf16", max_batch=8)
+    simt._ensure_handle()
+    monkeypatch.delenv("DIRB200_FUSION_SIMT")
+    gen = torch.Generator().manual_seed(1100 + stage + int(uv_range * 10))
+    prev = {"pd_joint_xyz_left": torch.randn(B, 21, 3, generator=gen) * 0.05,
+            "pd_joint_xyz_right": torch.randn(B, 21, 3, generator=gen) * 0.05,
+            "pd_joint_uv_left": (torch.rand(B, 21, 2, generator=gen) * 2 - 1) * uv_range,
+            "pd_joint_uv_right": (torch.rand(B, 21, 2, generator=gen) * 2 - 1) * uv_range,
+            "pd_mano_para_left": torch.randn(B, 64, generator=gen) * 0.3,
+            "pd_mano_para_right": torch.randn(B, 64, generator=gen) * 0.3,
+            "pd_offset": torch.randn(B, 3, generator=gen) * 0.5}
+    feat = torch.randn(B, 256, S, S, generator=gen).cuda()
+    prev = {k: v.cuda() for k, v in prev.items()}
+    ra, fa = seams.joint2bone(tc, stage, feat, prev)
+    rb, fb = seams.joint2bone(simt, stage, feat, prev)
+    assert torch.equal(ra["pd_mesh_xyz_left"], rb["pd_mesh_xyz_left"])  # upstream of the fusion: untouched
+    a, b = fa["img_feat"], fb["img_feat"]
+    assert bool(torch.isfinite(a).all()) and float(b.abs().max()) > 0
+    err = float((a - b).abs().max() / b.abs().max())
+    mean = float((a - b).abs().mean() / b.abs().mean())
+    print(f"tcgen05 bone fusion vs fp32 accumulate: max rel err {err:.2e}, mean rel err {mean:.2e}")
+    assert err < 3e-2 and mean < 5e-3
+    one, fone = seams.joint2bone(tc, stage, feat[1:2], {k: v[1:2] for k, v in prev.items()})
+    assert torch.equal(fone["img_feat"], a[1:2])  # per-image independence, bit-exact
