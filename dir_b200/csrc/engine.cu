@@ -805,12 +805,15 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
     ++launches;
     conv<T>(sw.fusion0, bone, fus_mid, nullptr, B, S, S, st);
   } else {
-    if (std::is_same<T, __nv_bfloat16>::value && sw.fus_wp_tc && !coef_simt)
-      launch_bone_coef_tc(jfeat, sw.fus_wp_tc, coef, B, st);
+    const bool coef_tc = std::is_same<T, __nv_bfloat16>::value && sw.fus_wp_tc && !coef_simt;
+    const bool fus_tc = std::is_same<T, __nv_bfloat16>::value && !fusion_simt && (S == 16 || S == 32);
+    const int p_bf16 = coef_tc && fus_tc;  // both ends on the tensor cores: the coefficient tensor travels as bf16
+    if (coef_tc)
+      launch_bone_coef_tc(jfeat, sw.fus_wp_tc, coef, p_bf16, B, st);
     else
       launch_bone_coef(jfeat, sw.fus_wp, coef, B, st);
-    if (std::is_same<T, __nv_bfloat16>::value && !fusion_simt && (S == 16 || S == 32))
-      launch_bone_fusion_tc(stage_rec, rec_stride, coef, sw.fusion0.scale, sw.fusion0.shift,
+    if (fus_tc)
+      launch_bone_fusion_tc(stage_rec, rec_stride, coef, p_bf16, sw.fusion0.scale, sw.fusion0.shift,
                             reinterpret_cast<__nv_bfloat16*>(fus_mid), B, S, sw.distance, st);
     else
       launch_bone_fusion<T>(stage_rec, rec_stride, coef, sw.fusion0.scale, sw.fusion0.shift, fus_mid, B, S, sw.distance,

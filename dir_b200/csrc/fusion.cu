@@ -132,8 +132,9 @@ struct CoefBars {
   uint32_t tmem_ptr;
 };
 
+template <typename PT>  // PT = float, or __nv_bfloat16 when the consumer is bone_fusion_tc_kernel (which rounds P to bf16 anyway)
 __global__ void __launch_bounds__(192, 1)
-bone_coef_tc_kernel(const float* __restrict__ jf, const uint8_t* __restrict__ wpk, float* __restrict__ P, int B) {
+bone_coef_tc_kernel(const float* __restrict__ jf, const uint8_t* __restrict__ wpk, PT* __restrict__ P, int B) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -227,16 +228,38 @@ bone_coef_tc_kernel(const float* __restrict__ jf, const uint8_t* __restrict__ wp
         tmem_ld32(trow + slot * 256 + 64 * c, v);
         tmem_ld32(trow + slot * 256 + 64 * c + 32, v + 32);
         tmem_ld_wait();
-        float4* mine = reinterpret_cast<float4*>(patch + lane * CT_PITCH);
+        if constexpr (sizeof(PT) == 4) {
+          float4* mine = reinterpret_cast<float4*>(patch + lane * CT_PITCH);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) mine[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        __syncwarp();
+          for (int i = 0; i < 16; ++i) mine[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          __syncwarp();
 #pragma unroll 4
-        for (int it = 0; it < 16; ++it) {
-          const int rr = 2 * it + prow_l, rj = r0 + warp * 32 + rr;
-          if (rj < 2 * B) {
-            const float4 o = *reinterpret_cast<const float4*>(patch + rr * CT_PITCH + pcol);
-            *reinterpret_cast<float4*>(P + ((((int64_t)(rj >> 1) * 40 + hb) * 2 + (rj & 1)) * 9 + tap) * 256 + 64 * c + pcol) = o;
+          for (int it = 0; it < 16; ++it) {
+            const int rr = 2 * it + prow_l, rj = r0 + warp * 32 + rr;
+            if (rj < 2 * B) {
+              const float4 o = *reinterpret_cast<const float4*>(patch + rr * CT_PITCH + pcol);
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(P) +
+                                         ((((int64_t)(rj >> 1) * 40 + hb) * 2 + (rj & 1)) * 9 + tap) * 256 + 64 * c + pcol) = o;
+            }
+          }
+        } else {  // bf16: a row of the patch is 64 values = 128 bytes (+16 pad); a store instruction writes 4 rows
+          uint4* mine = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(patch) + lane * 144);
+#pragma unroll
+          for (int g8 = 0; g8 < 8; ++g8) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * g8], v[8 * g8 + 1]), h1 = __floats2bfloat162_rn(v[8 * g8 + 2], v[8 * g8 + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * g8 + 4], v[8 * g8 + 5]), h3 = __floats2bfloat162_rn(v[8 * g8 + 6], v[8 * g8 + 7]);
+            mine[g8] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                  *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = 4 * it + (lane >> 3), rj = r0 + warp * 32 + rr, ch = lane & 7;
+            if (rj < 2 * B) {
+              const uint4 o = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(patch) + rr * 144 + ch * 16);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P) +
+                                        ((((int64_t)(rj >> 1) * 40 + hb) * 2 + (rj & 1)) * 9 + tap) * 256 + 64 * c + ch * 8) = o;
+            }
           }
         }
         __syncwarp();
@@ -450,9 +473,9 @@ struct FtBars {
   int act[40];
 };
 
-template <int S>
+template <int S, typename PT>
 __global__ void __launch_bounds__(FT_THREADS, 2)
-bone_fusion_tc_kernel(const float* __restrict__ rec, int rec_stride, const float* __restrict__ P,
+bone_fusion_tc_kernel(const float* __restrict__ rec, int rec_stride, const PT* __restrict__ P,
                       const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
                       float distance) {
   using namespace tc;
@@ -530,7 +553,7 @@ bone_fusion_tc_kernel(const float* __restrict__ rec, int rec_stride, const float
     }
   } else {
     // ===================================================== chunk builders (8 warps), then the epilogue
-    const float* Pimg = P + (int64_t)b * 40 * 2 * 9 * 256;
+    const PT* Pimg = P + (int64_t)b * 40 * 2 * 9 * 256;
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c & 1;
       uint8_t* At = smem + FT_OFF_A + buf * FT_A;
@@ -564,29 +587,23 @@ bone_fusion_tc_kernel(const float* __restrict__ rec, int rec_stride, const float
           }
         }
       }
-      // ---- B: thread n gathers its channel of the chunk's 54 coefficient vectors (coalesced 1 KB rows of P)
+      // ---- B: thread n gathers its channel of the chunk's 54 coefficient vectors (coalesced rows of P). All loads
+      // are issued before the first store: one L2 round trip per chunk instead of three.
       {
         const int n = tid;
         __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(Bt + n * 128);
-#pragma unroll 1
+        PT v[54];
+#pragma unroll
         for (int s = 0; s < 3; ++s) {
-          if (3 * c + s >= nact) {  // stale columns of an earlier chunk in this buffer: clear
+          const bool on = 3 * c + s < nact;
+          const PT* src = Pimg + (int64_t)(on ? bars->act[3 * c + s] : 0) * (2 * 9 * 256) + n;
 #pragma unroll
-            for (int t = 0; t < 18; ++t) {
-              const int col = s * 18 + t;
-              row[(((col >> 3) ^ (n & 7)) << 3) | (col & 7)] = __float2bfloat16_rn(0.f);
-            }
-            continue;
-          }
-          const float* src = Pimg + (int64_t)bars->act[3 * c + s] * (2 * 9 * 256) + n;
-          float v[18];
+          for (int t = 0; t < 18; ++t) v[s * 18 + t] = on ? __ldg(src + t * 256) : PT(0.f);  // t = role * 9 + tap
+        }
 #pragma unroll
-          for (int t = 0; t < 18; ++t) v[t] = __ldg(src + t * 256);  // t = role * 9 + tap
-#pragma unroll
-          for (int t = 0; t < 18; ++t) {
-            const int col = s * 18 + t;
-            row[(((col >> 3) ^ (n & 7)) << 3) | (col & 7)] = __float2bfloat16_rn(v[t]);
-          }
+        for (int col = 0; col < 54; ++col) {
+          if constexpr (sizeof(PT) == 4) row[(((col >> 3) ^ (n & 7)) << 3) | (col & 7)] = __float2bfloat16_rn(v[col]);
+          else row[(((col >> 3) ^ (n & 7)) << 3) | (col & 7)] = v[col];
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -654,14 +671,19 @@ void launch_pack_fusion_weight_tc(const float* w, void* wpk, cudaStream_t st) {
   pack_fusion_weight_tc_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(w, reinterpret_cast<float*>(wpk));
 }
 
-void launch_bone_coef_tc(const float* jf, const void* wpk, float* P, int B, cudaStream_t st) {
+void launch_bone_coef_tc(const float* jf, const void* wpk, void* P, int p_bf16, int B, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(bone_coef_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM);
+    cudaFuncSetAttribute(bone_coef_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM);
+    cudaFuncSetAttribute(bone_coef_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM);
     attr = true;
   }
-  launch_pdl(bone_coef_tc_kernel, dim3(40, ceil_div(2 * B, 128)), dim3(192), CT_SMEM, st, jf,
-             reinterpret_cast<const uint8_t*>(wpk), P, B);
+  if (p_bf16)
+    launch_pdl(bone_coef_tc_kernel<__nv_bfloat16>, dim3(40, ceil_div(2 * B, 128)), dim3(192), CT_SMEM, st, jf,
+               reinterpret_cast<const uint8_t*>(wpk), reinterpret_cast<__nv_bfloat16*>(P), B);
+  else
+    launch_pdl(bone_coef_tc_kernel<float>, dim3(40, ceil_div(2 * B, 128)), dim3(192), CT_SMEM, st, jf,
+               reinterpret_cast<const uint8_t*>(wpk), reinterpret_cast<float*>(P), B);
 }
 
 void launch_bone_coef(const float* jf, const float* wp, float* P, int B, cudaStream_t st) {
@@ -690,20 +712,29 @@ void launch_bone_fusion(const float* rec, int rec_stride, const float* P, const 
     launch_pdl(bone_fusion_kernel<T, 16>, dim3(dim3(B, S)), dim3(256), smem, st, rec, rec_stride, P, scale, shift, out, distance);
   }
 }
-void launch_bone_fusion_tc(const float* rec, int rec_stride, const float* P, const float* scale, const float* shift,
-                           __nv_bfloat16* out, int B, int S, float distance, cudaStream_t st) {
+template <typename PT>
+static void launch_bone_fusion_tc_t(const float* rec, int rec_stride, const PT* P, const float* scale, const float* shift,
+                                    __nv_bfloat16* out, int B, int S, float distance, cudaStream_t st) {
   static bool attr[2] = {false, false};
   if (S == 32) {
-    if (!attr[0]) cudaFuncSetAttribute(bone_fusion_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
+    if (!attr[0]) cudaFuncSetAttribute(bone_fusion_tc_kernel<32, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
     attr[0] = true;
-    launch_pdl(bone_fusion_tc_kernel<32>, dim3(B, 8), dim3(FT_THREADS), FT_SMEM, st, rec, rec_stride, P, scale, shift, out,
-               distance);
+    launch_pdl(bone_fusion_tc_kernel<32, PT>, dim3(B, 8), dim3(FT_THREADS), FT_SMEM, st, rec, rec_stride, P, scale, shift,
+               out, distance);
   } else {
-    if (!attr[1]) cudaFuncSetAttribute(bone_fusion_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
+    if (!attr[1]) cudaFuncSetAttribute(bone_fusion_tc_kernel<16, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
     attr[1] = true;
-    launch_pdl(bone_fusion_tc_kernel<16>, dim3(B, 2), dim3(FT_THREADS), FT_SMEM, st, rec, rec_stride, P, scale, shift, out,
-               distance);
+    launch_pdl(bone_fusion_tc_kernel<16, PT>, dim3(B, 2), dim3(FT_THREADS), FT_SMEM, st, rec, rec_stride, P, scale, shift,
+               out, distance);
   }
+}
+
+void launch_bone_fusion_tc(const float* rec, int rec_stride, const void* P, int p_bf16, const float* scale,
+                           const float* shift, __nv_bfloat16* out, int B, int S, float distance, cudaStream_t st) {
+  if (p_bf16)
+    launch_bone_fusion_tc_t(rec, rec_stride, reinterpret_cast<const __nv_bfloat16*>(P), scale, shift, out, B, S, distance, st);
+  else
+    launch_bone_fusion_tc_t(rec, rec_stride, reinterpret_cast<const float*>(P), scale, shift, out, B, S, distance, st);
 }
 
 template void launch_bone_fusion<float>(const float*, int, const float*, const float*, const float*, float*, int, int,

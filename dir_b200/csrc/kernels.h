@@ -178,9 +178,10 @@ void launch_bone_coef(const float* joint_feat, const float* wp, float* P /*(B,40
 // tensor-core version (kind::tf32): wpk = bone_coef_tc_packed_bytes() filled by launch_pack_fusion_weight_tc
 size_t bone_coef_tc_packed_bytes();
 void launch_pack_fusion_weight_tc(const float* w /*fusion.0.weight*/, void* wpk, cudaStream_t st);
-void launch_bone_coef_tc(const float* jf, const void* wpk, float* P, int B, cudaStream_t st);
+void launch_bone_coef_tc(const float* jf, const void* wpk, void* P, int p_bf16 /*P element type: 0 fp32, 1 bf16*/, int B,
+                         cudaStream_t st);
 // tensor-core version of the sparse accumulate (bf16 configuration; fusion.cu), S in {16, 32}
-void launch_bone_fusion_tc(const float* stage_record, int rec_stride, const float* P, const float* scale,
+void launch_bone_fusion_tc(const float* stage_record, int rec_stride, const void* P, int p_bf16, const float* scale,
                            const float* shift, __nv_bfloat16* out, int B, int S, float distance, cudaStream_t st);
 template <typename T>
 void launch_bone_fusion(const float* stage_record, int rec_stride, const float* P, const float* scale,
