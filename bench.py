@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 
 GF_PER_IMAGE = 36.80  # dense-contraction GFLOP per image, ResNet-50, 3 stages, incl. heads (measured)
 # dominant kernel = largest single launch of the step: the two InitRegressor attention convs, run as one
-# conv3x3 2048->2048 @8x8 (models/dir.py:227-241), 4.83 GFLOP/img, on conv_tc_kernel<256,128>
+# conv3x3 2048->2048 @8x8 (models/dir.py:227-241), 4.83 GFLOP/img, on conv_tc_kernel<256,128,2> (2-CTA tcgen05)
 DOMINANT_LAYER = "init_regressor.attention_left.0"
 DOMINANT_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
 
@@ -312,7 +312,7 @@ def main():
                 t = json.load(f)
             if t.get("batch") == B and t.get("precision") == args.precision:
                 traffic = t.get("dram_bytes_per_launch")
-        roof = {"bound": "tensor", "kernel": f"conv_tc_kernel<256,128> ({DOMINANT_LAYER}: conv3x3 2048->2x1024 @8x8, "
+        roof = {"bound": "tensor", "kernel": f"conv_tc_kernel<256,128,2> cta_group::2 ({DOMINANT_LAYER}: conv3x3 2048->2x1024 @8x8, "
                                              f"{prof_flops / prof_n / 1e9:.1f} GFLOP/launch algorithmic = 2*M*N*K)",
                 "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
                 "traffic": traffic, "peak_source": pk["source"], "launches_timed": prof_n,
