@@ -48,6 +48,7 @@ struct TcArgs {
   int m_tiles, n_tiles, stages;
   int raster_m;      // 1: consecutive tiles walk m first (weights larger than activations: keep an n-tile's weights hot)
   int kb2, stride2;  // K-concatenated second operand: kb2 extra 1x1 k-blocks read from tmA2 at spatial stride2
+  int b_resident;    // 1: the whole weight matrix (one n-tile, all k-blocks) is loaded once per CTA and stays in smem
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -188,8 +189,10 @@ struct TcCfg {
       (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
   static constexpr uint32_t TMEM_COLS = 2 * BN;
   static constexpr int NCH = BN / 64;
-  static int smem_bytes(int stages, int has_res) {
-    return 1024 + stages * STAGE_BYTES + 2 * CHUNK_BYTES + (has_res ? RES_BUFS * CHUNK_BYTES : 0) + 4 * BN * 4 + 256;
+  // bslots = weight tiles held in smem: one per stage, or (resident mode) one per k-block
+  static int smem_bytes(int stages, int has_res, int bslots) {
+    return 1024 + stages * A_STAGE + bslots * B_STAGE + 2 * CHUNK_BYTES + (has_res ? RES_BUFS * CHUNK_BYTES : 0) +
+           4 * BN * 4 + 256;
   }
 };
 
@@ -208,7 +211,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int stages = a.stages;
   uint8_t* sA = smem;
   uint8_t* sB = sA + stages * Cfg::A_STAGE;
-  uint8_t* sOut = sB + stages * Cfg::B_STAGE;             // 2 x 16 KB output staging (128B-swizzled boxes)
+  const int bres = a.b_resident;  // weights resident: B slot = k-block (loaded once), stages carry only A
+  const int nkb_all = a.taps * a.cblocks + a.kb2;
+  uint8_t* sOut = sB + (bres ? nkb_all : stages) * Cfg::B_STAGE;  // 2 x 16 KB output staging (128B-swizzled boxes)
   uint8_t* sRes = sOut + 2 * CHUNK_BYTES;                 // RES_BUFS x 16 KB residual ring (only if has_res)
   float* s_affine = reinterpret_cast<float*>(sRes + (a.has_res ? RES_BUFS * CHUNK_BYTES : 0));  // [2 groups][2][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_affine + 4 * BN);
@@ -218,7 +223,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_full = tmem_empty + 2;
   uint64_t* res_empty = res_full + RES_BUFS;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty + RES_BUFS);
+  uint64_t* bres_bar = res_empty + RES_BUFS;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_units = a.m_tiles / CG;  // scheduling unit = CG adjacent M tiles (one per CTA of the pair)
@@ -243,6 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&res_full[i], 1);
       mbar_init(&res_empty[i], 1);
     }
+    mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: two accumulator buffers of BN fp32 columns x 128 lanes
@@ -269,6 +276,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {  // ===================== TMA producer
       int s = 0;
       uint32_t ph = 0, rchunk = 0;
+      if (bres && first_tile < total_tiles) {  // weights: finalize-time data, one load per CTA for all its tiles
+        mbar_expect_tx(bres_bar, (uint32_t)nkb * Cfg::B_STAGE);
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(&tmB, bres_bar, sB + kb * Cfg::B_STAGE, kb * 64, 0);
+      }
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int m0 = ((a.raster_m ? tile % m_units : tile / a.n_tiles) * CG + (int)rank) * BM;
         const int n0 = (a.raster_m ? tile / m_units : tile % a.n_tiles) * BN;
@@ -298,6 +309,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                               ho0 * a.stride + ky - a.pad, b0);
             }
             tma_load_2d_2sm(&tmB, &full_bar[s], sB + s * Cfg::B_STAGE, kb * 64, nb0);
+          } else if (bres) {  // A only (1-CTA, non-stem layers)
+            mbar_expect_tx(&full_bar[s], Cfg::A_STAGE);
+            if (kb >= nkb1) {
+              tma_load_4d(&tmA2, &full_bar[s], sA + s * Cfg::A_STAGE, (kb - nkb1) * 64, wo0 * a.stride2, ho0 * a.stride2,
+                          b0);
+            } else {
+              const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
+              const int ky = tap / a.kw, kx = tap - ky * a.kw;
+              tma_load_4d(&tmA, &full_bar[s], sA + s * Cfg::A_STAGE, cb * 64, wo0 * a.stride + kx - a.pad,
+                          ho0 * a.stride + ky - a.pad, b0);
+            }
           } else {
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           if (a.stem) {  // k-block = kernel row ky; overlapped view: {32 elems, wo (16 B apart), h, n}
@@ -327,6 +349,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       int i = 0;
+      if (bres && first_tile < total_tiles) mbar_wait(bres_bar, 0);
       for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++i) {
         const int buf = i & 1;
         mbar_wait(&tmem_empty[buf], ((i >> 1) & 1) ^ 1);  // epilogue drained this accumulator buffer
@@ -336,7 +359,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&full_bar[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t da = umma_desc<SW>(smem_u32(sA + s * Cfg::A_STAGE));
-          const uint64_t db = umma_desc<SW>(smem_u32(sB + s * Cfg::B_STAGE));
+          const uint64_t db = umma_desc<SW>(smem_u32(sB + (bres ? kb : s) * Cfg::B_STAGE));
 #pragma unroll
           for (int k = 0; k < Cfg::KSTEPS; ++k) {  // +32 B per K=16 step inside the swizzle atom
             if constexpr (CG == 2) umma_bf16_2sm(d, da + 2 * k, db + 2 * k, Cfg::IDESC, (kb | k) ? 1u : 0u);
@@ -633,15 +656,28 @@ bool cg2_enabled() {
   return on;
 }
 
+bool resident_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DIRB200_TC_RESIDENT");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 template <int BN, int SW, int CG>
 int launch_tc_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                  const CUtensorMap& tmA2, TcArgs a, cudaStream_t st) {
   using Cfg = TcCfg<BN, SW, CG>;
   static int attr_bytes = 0;
+  const int nkb = a.taps * a.cblocks + a.kb2;
+  // resident weights: one n-tile whose whole K extent fits next to a useful A ring (layer1: <= 72 KB); the TMA engine
+  // then only fetches activations (it retires ~one 128-byte box row per 3-5 cycles, the limit of these layers)
+  a.b_resident = (CG == 1 && SW == 128 && !a.stem && a.n_tiles == 1 && nkb * Cfg::B_STAGE <= 80 * 1024 && resident_enabled())
+                     ? 1 : 0;
   int stages = MAX_STAGES;  // the ring runs ahead across tiles, so short K loops still want every stage that fits
-  while (stages > 1 && Cfg::smem_bytes(stages, a.has_res) > 227 * 1024) --stages;
+  while (stages > 1 && Cfg::smem_bytes(stages, a.has_res, a.b_resident ? nkb : stages) > 227 * 1024) --stages;
   a.stages = stages;
-  const int smem = Cfg::smem_bytes(stages, a.has_res);
+  const int smem = Cfg::smem_bytes(stages, a.has_res, a.b_resident ? nkb : stages);
   if (smem > attr_bytes) {
     if (cudaFuncSetAttribute(conv_tc_kernel<BN, SW, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess)
