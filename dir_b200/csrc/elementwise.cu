@@ -229,6 +229,35 @@ __global__ void head3_kernel(const T* __restrict__ x, int Cx, int coff, int C, c
   }
 }
 
+// Both 128->3 heads of the shared seg|dense feature map (models/dir.py:404-420,474-476) in one pass: a warp per
+// pixel reads its 256 channels once (16 bytes per lane); lanes 0-15 hold the seg half, 16-31 the dense half.
+template <typename T>
+__global__ void head3x2_kernel(const T* __restrict__ x, const float* __restrict__ w0, const float* __restrict__ b0,
+                               const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ out0,
+                               float* __restrict__ out1, int B, int HW) {
+  pdl_wait();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * HW) return;
+  const int b = warp / HW, p = warp - b * HW;
+  float v[8];
+  Vec8<T>::ld(x + (int64_t)warp * 256 + lane * 8, v);
+  const float* w = (lane < 16 ? w0 : w1) + (lane & 15) * 8;
+  float a[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float4 u0 = __ldg(reinterpret_cast<const float4*>(w + k * 128)), u1 = __ldg(reinterpret_cast<const float4*>(w + k * 128) + 1);
+    a[k] = v[0] * u0.x + v[1] * u0.y + v[2] * u0.z + v[3] * u0.w + v[4] * u1.x + v[5] * u1.y + v[6] * u1.z + v[7] * u1.w;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);  // within each half-warp
+  }
+  if ((lane & 15) == 0) {
+    float* out = lane ? out1 : out0;
+    const float* bias = lane ? b1 : b0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[((int64_t)b * 3 + k) * HW + p] = a[k] + bias[k];
+  }
+}
+
 // ---------------------------------------------------------------- finalize-time packing
 __global__ void fold_affine_kernel(const float* cb, const float* g, const float* be, const float* mu, const float* var,
                                    float* scale, float* shift, int n) {
@@ -428,6 +457,12 @@ void launch_head3(const T* x, int Cx, int coff, int C, const float* w, const flo
   launch_pdl(head3_kernel<T>, dim3(ceil_div(warps * 32, 256)), dim3(256), 0, st, x, Cx, coff, C, w, bias, out, B, HW);
 }
 
+template <typename T>
+void launch_head3x2(const T* x, const float* w0, const float* b0, const float* w1, const float* b1, float* out0,
+                    float* out1, int B, int HW, cudaStream_t st) {
+  launch_pdl(head3x2_kernel<T>, dim3(ceil_div(B * HW * 32, 256)), dim3(256), 0, st, x, w0, b0, w1, b1, out0, out1, B, HW);
+}
+
 void launch_preprocess_u8(const unsigned char* img, float* out, int B, int H, int W, cudaStream_t st) {
   launch_pdl(preprocess_u8_kernel, dim3(ceil_div(B * H * W, 256)), dim3(256), 0, st, img, out, B, H * W);
 }
@@ -475,6 +510,8 @@ void launch_attn_pool(const T* f, const float* attn, float* pooled, int B, int P
   template void launch_nchw_to_nhwc<T>(const float*, T*, int, int, int, int, cudaStream_t);                          \
   template void launch_nhwc_to_nchw<T>(const T*, float*, int, int, int, int, cudaStream_t);                          \
   template void launch_head3<T>(const T*, int, int, int, const float*, const float*, float*, int, int, cudaStream_t); \
+  template void launch_head3x2<T>(const T*, const float*, const float*, const float*, const float*, float*, float*,  \
+                                  int, int, cudaStream_t);                                                           \
   template void launch_attn_logits<T>(const T*, const float*, const float*, float*, int, int, int, cudaStream_t);    \
   template void launch_attn_pool<T>(const T*, const float*, float*, int, int, int, cudaStream_t);
 INST(float)

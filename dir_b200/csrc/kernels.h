@@ -37,6 +37,11 @@ template <typename T>
 void launch_head3(const T* x, int Cx, int coff, int C, const float* w, const float* bias, float* out, int B, int HW,
                   cudaStream_t st);
 
+// the two 128->3 heads over the halves of one 256-channel map in a single pass (seg: channels 0..127, dense: 128..255)
+template <typename T>
+void launch_head3x2(const T* x, const float* w0, const float* b0, const float* w1, const float* b1, float* out0,
+                    float* out1, int B, int HW, cudaStream_t st);
+
 // uint8 (B,H,W,3) BGR -> normalised fp32 NCHW RGB (apps/eval.py:56-61)
 void launch_preprocess_u8(const unsigned char* img, float* out, int B, int H, int W, cudaStream_t st);
 
