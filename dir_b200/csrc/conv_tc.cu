@@ -48,6 +48,7 @@ struct TcArgs {
   int m_tiles, n_tiles, stages;
   int raster_m;      // 1: consecutive tiles walk m first (weights larger than activations: keep an n-tile's weights hot)
   int kb2, stride2;  // K-concatenated second operand: kb2 extra 1x1 k-blocks read from tmA2 at spatial stride2
+  int kb2a;          // ... of which the first kb2a come from tmA2 and the rest from tmA3 (a channel concat never built)
   int b_resident;    // 1: the whole weight matrix (one n-tile, all k-blocks) is loaded once per CTA and stays in smem
 };
 
@@ -200,7 +201,7 @@ template <int BN, int SW, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
-               const __grid_constant__ CUtensorMap tmA2, const TcArgs a) {
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3, const TcArgs a) {
   using Cfg = TcCfg<BN, SW, CG>;
   // CG == 2: launched as clusters of two CTAs that share every MMA (tile = 256 output pixels x BN: this CTA owns rows
   // 128*rank..+127 and loads its own A tile plus HALF of the weight tile, so the L2->SM bytes per FLOP drop by a third;
@@ -300,8 +301,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if constexpr (CG == 2) {  // both CTAs' bytes are counted on the leader's full barrier
             if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
             if (kb >= nkb1) {
-              tma_load_4d_2sm(&tmA2, &full_bar[s], sA + s * Cfg::A_STAGE, (kb - nkb1) * 64, wo0 * a.stride2,
-                              ho0 * a.stride2, b0);
+              const int k2 = kb - nkb1;
+              tma_load_4d_2sm(k2 < a.kb2a ? &tmA2 : &tmA3, &full_bar[s], sA + s * Cfg::A_STAGE,
+                              (k2 < a.kb2a ? k2 : k2 - a.kb2a) * 64, wo0 * a.stride2, ho0 * a.stride2, b0);
             } else {
               const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
               const int ky = tap / a.kw, kx = tap - ky * a.kw;
@@ -312,8 +314,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else if (bres) {  // A only (1-CTA, non-stem layers)
             mbar_expect_tx(&full_bar[s], Cfg::A_STAGE);
             if (kb >= nkb1) {
-              tma_load_4d(&tmA2, &full_bar[s], sA + s * Cfg::A_STAGE, (kb - nkb1) * 64, wo0 * a.stride2, ho0 * a.stride2,
-                          b0);
+              const int k2 = kb - nkb1;
+              tma_load_4d(k2 < a.kb2a ? &tmA2 : &tmA3, &full_bar[s], sA + s * Cfg::A_STAGE,
+                          (k2 < a.kb2a ? k2 : k2 - a.kb2a) * 64, wo0 * a.stride2, ho0 * a.stride2, b0);
             } else {
               const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
               const int ky = tap / a.kw, kx = tap - ky * a.kw;
@@ -326,8 +329,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_4d(&tmA, &full_bar[s], sA + s * Cfg::A_STAGE, 0, wo0, ho0 * 2 + kb - 3, b0);
             tma_load_2d(&tmB, &full_bar[s], sB + s * Cfg::B_STAGE, kb * 32, n0);
           } else if (kb >= nkb1) {  // second operand of a K-concatenated pair (1x1, own stride): skip / downsample conv
-            tma_load_4d(&tmA2, &full_bar[s], sA + s * Cfg::A_STAGE, (kb - nkb1) * 64, wo0 * a.stride2, ho0 * a.stride2,
-                        b0);
+            const int k2 = kb - nkb1;
+            tma_load_4d(k2 < a.kb2a ? &tmA2 : &tmA3, &full_bar[s], sA + s * Cfg::A_STAGE,
+                        (k2 < a.kb2a ? k2 : k2 - a.kb2a) * 64, wo0 * a.stride2, ho0 * a.stride2, b0);
             tma_load_2d(&tmB, &full_bar[s], sB + s * Cfg::B_STAGE, kb * 64, n0);
           } else {
             const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
@@ -666,7 +670,7 @@ bool resident_enabled() {
 
 template <int BN, int SW, int CG>
 int launch_tc_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
-                 const CUtensorMap& tmA2, TcArgs a, cudaStream_t st) {
+                 const CUtensorMap& tmA2, const CUtensorMap& tmA3, TcArgs a, cudaStream_t st) {
   using Cfg = TcCfg<BN, SW, CG>;
   static int attr_bytes = 0;
   const int nkb = a.taps * a.cblocks + a.kb2;
@@ -708,7 +712,8 @@ int launch_tc_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SW, CG>, tmA, tmB, tmY, tmR, tmA2, a) != cudaSuccess)
+  if (a.kb2a == 0) a.kb2a = a.kb2;  // no third operand
+  if (cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SW, CG>, tmA, tmB, tmY, tmR, tmA2, tmA3, a) != cudaSuccess)
     return DIRB200_E_CUDA;
   return DIRB200_OK;
 }
@@ -716,12 +721,14 @@ int launch_tc_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
 // tmB2 = the weight map with BN/2-row boxes (null: 1-CTA kernel only)
 template <int BN, int SW>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmB2, const CUtensorMap& tmY,
-              const CUtensorMap& tmR, const CUtensorMap& tmA2, TcArgs a, cudaStream_t st) {
+              const CUtensorMap& tmR, const CUtensorMap& tmA2, TcArgs a, cudaStream_t st,
+              const CUtensorMap* tmA3 = nullptr) {
+  const CUtensorMap& t3 = tmA3 ? *tmA3 : tmA2;
   if constexpr (BN >= 128 && SW == 128) {
     if (tmB2 && cg2_enabled() && !a.stem && a.m_tiles % 2 == 0)
-      return launch_tc_cg<BN, SW, 2>(tmA, *tmB2, tmY, tmR, tmA2, a, st);
+      return launch_tc_cg<BN, SW, 2>(tmA, *tmB2, tmY, tmR, tmA2, t3, a, st);
   }
-  return launch_tc_cg<BN, SW, 1>(tmA, tmB, tmY, tmR, tmA2, a, st);
+  return launch_tc_cg<BN, SW, 1>(tmA, tmB, tmY, tmR, tmA2, t3, a, st);
 }
 
 template <typename Key>
@@ -918,13 +925,18 @@ const CUtensorMap* act_map_cached(const __nv_bfloat16* x, int B, int H, int W, i
 // with a 1x1 stride-`stride2` conv over x2 (the ResNet downsample / hourglass skip branch). L holds the concatenated,
 // BN-scale-folded weights [Cout][C1 + C2].
 int launch_conv_tc_dual(const ConvLayer& L, const __nv_bfloat16* x1, int C1, const __nv_bfloat16* x2, int C2,
-                        int stride2, __nv_bfloat16* y, int B, int Ho, int Wo, cudaStream_t st) {
+                        int stride2, __nv_bfloat16* y, int B, int Ho, int Wo, cudaStream_t st, const __nv_bfloat16* x2b,
+                        int C2b) {
+  // x2b != null: the second operand is the channel concat [x2 (C2 - C2b channels) | x2b (C2b channels)], read from its
+  // two sources (the concatenated tensor is never materialised)
   const Boxes bx = pick_boxes(Ho, Wo);
+  const int C2a = x2b ? C2 - C2b : C2;
   const CUtensorMap* tmA = act_map_cached(x1, B, Ho, Wo, C1, 1, bx, L.name.c_str());
-  const CUtensorMap* tmA2 = act_map_cached(x2, B, Ho * stride2, Wo * stride2, C2, stride2, bx, L.name.c_str());
+  const CUtensorMap* tmA2 = act_map_cached(x2, B, Ho * stride2, Wo * stride2, C2a, stride2, bx, L.name.c_str());
+  const CUtensorMap* tmA3 = x2b ? act_map_cached(x2b, B, Ho * stride2, Wo * stride2, C2b, stride2, bx, L.name.c_str()) : nullptr;
   const int M = B * Ho * Wo;
   const CUtensorMap* tmY = rowmajor_map_cached(y, M, L.Cout);
-  if (!tmA || !tmA2 || !tmY) return DIRB200_E_CUDA;
+  if (!tmA || !tmA2 || !tmY || (x2b && !tmA3) || C2a % 64 || (x2b && C2b % 64)) return DIRB200_E_CUDA;
   TcArgs a{};
   a.scale = L.scale;
   a.shift = L.shift;
@@ -938,14 +950,15 @@ int launch_conv_tc_dual(const ConvLayer& L, const __nv_bfloat16* x1, int C1, con
   a.taps = 1;
   a.cblocks = C1 / 64;
   a.kb2 = C2 / 64;
+  a.kb2a = C2a / 64;
   a.stride2 = stride2;
   a.relu = L.relu;
   a.m_tiles = (M + BM - 1) / BM;
   a.n_tiles = L.Cout / L.wmap_bn;
   switch (L.wmap_bn) {
-    case 256: return launch_tc<256, 128>(*tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, *tmY, *tmY, *tmA2, a, st);
-    case 128: return launch_tc<128, 128>(*tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, *tmY, *tmY, *tmA2, a, st);
-    default: return launch_tc<64, 128>(*tmA, L.wmap, nullptr, *tmY, *tmY, *tmA2, a, st);
+    case 256: return launch_tc<256, 128>(*tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, *tmY, *tmY, *tmA2, a, st, tmA3);
+    case 128: return launch_tc<128, 128>(*tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, *tmY, *tmY, *tmA2, a, st, tmA3);
+    default: return launch_tc<64, 128>(*tmA, L.wmap, nullptr, *tmY, *tmY, *tmA2, a, st, tmA3);
   }
 }
 

@@ -510,7 +510,7 @@ void Engine::conv(const ConvLayer& L, const T* x, T* y, const T* resid, int B, i
 // conv3 + (downsample | skip) as one K-concatenated tensor-core GEMM; returns false if the pair must run separately
 template <typename T>
 bool Engine::conv_pair(const ConvLayer& F, const ConvLayer& main, const ConvLayer& second, const T* x1, const T* x2,
-                       T* y, int B, int Ho, int Wo, cudaStream_t st) {
+                       T* y, int B, int Ho, int Wo, cudaStream_t st, const T* x2b, int C2b) {
   if (sizeof(T) != 2 || disable_tc || disable_pair_fusion || F.wmap_bn == 0) return false;
   ConvLayer probe = F;  // same geometry checks as a 1x1 stride-1 conv on the output grid
   probe.kh = probe.kw = 1;
@@ -537,7 +537,8 @@ bool Engine::conv_pair(const ConvLayer& F, const ConvLayer& main, const ConvLaye
   }
   int rc = launch_conv_tc_dual(F, reinterpret_cast<const __nv_bfloat16*>(x1), main.Cin,
                                reinterpret_cast<const __nv_bfloat16*>(x2), second.Cin, second.stride,
-                               reinterpret_cast<__nv_bfloat16*>(y), B, Ho, Wo, st);
+                               reinterpret_cast<__nv_bfloat16*>(y), B, Ho, Wo, st,
+                               reinterpret_cast<const __nv_bfloat16*>(x2b), C2b);
   if (pr) cudaEventRecord(pr->b, st);
   if (rc && !sticky_rc) {
     sticky_rc = rc;
@@ -642,8 +643,18 @@ int Engine::run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** 
 }
 
 template <typename T>
+bool Engine::virtual_concat_ok(const ResidualBlock& r, int B, int H, int W_) const {
+  if (sizeof(T) != 2 || disable_tc || disable_pair_fusion || !r.need_skip || r.c3skip.wmap_bn == 0) return false;
+  ConvLayer probe = r.c3skip;
+  probe.kh = probe.kw = 1;
+  probe.stride = 1;
+  probe.pad = 0;
+  return conv_tc_supported(probe, B, H, W_);
+}
+
+template <typename T>
 T* Engine::run_residual(const ResidualBlock& r, const T* rawx, const T* act, int B, int H, int W_, Arena& ar,
-                        cudaStream_t st) {
+                        cudaStream_t st, const T* raw2, int c2) {
   const int64_t px = (int64_t)B * H * W_;
   T* t1 = aalloc<T>(ar, px * r.c1.Cout);
   T* t2 = aalloc<T>(ar, px * r.c2.Cout);
@@ -652,7 +663,14 @@ T* Engine::run_residual(const ResidualBlock& r, const T* rawx, const T* act, int
   if (!ar.base || ar.overflow) return nullptr;
   conv<T>(r.c1, act, t1, nullptr, B, H, W_, st);
   conv<T>(r.c2, t1, t2, nullptr, B, H, W_, st);
-  if (r.need_skip && conv_pair<T>(r.c3skip, r.c3, r.skip, t2, rawx, out, B, H, W_, st)) return out;
+  if (r.need_skip && conv_pair<T>(r.c3skip, r.c3, r.skip, t2, rawx, out, B, H, W_, st, raw2, c2)) return out;
+  if (raw2) {  // callers check virtual_concat_ok() first
+    if (!sticky_rc) {
+      sticky_rc = DIRB200_E_STATE;
+      err = "virtual concat needs the tensor-core pair GEMM";
+    }
+    return out;
+  }
   const T* resid = rawx;
   if (r.need_skip) {
     conv<T>(r.skip, rawx, sk, nullptr, B, H, W_, st);
@@ -887,9 +905,23 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   rc = run_stage<T>(0, fusion4, rec, RS, para, PS, B, plan ? nullptr : rec + DIRB200_STAGE_FLOATS, RS,
                     plan ? nullptr : para + 128, PS, &img_feat1, nullptr, nullptr, ar, st);
   if (rc) return rc;
+  // enhance_layer{4,3}: the block input cat(fusion, img_feat) is only pre-activated (act); its raw copy is never
+  // written: the skip half of the pair GEMM reads the two sources directly (third A operand of conv_tc_kernel)
+  auto enhance = [&](const ResidualBlock& r, const T* a0, const T* a1, int S) -> T* {
+    if (virtual_concat_ok<T>(r, B, S, S)) {
+      T* acto = aalloc<T>(ar, (int64_t)B * S * S * 512);
+      if (!plan && !ar.overflow) {
+        launch_concat_preact<T>(a0, 256, 0, a1, 256, r.bn1s, r.bn1b, (T*)nullptr, acto, B, S, S, st);
+        ++launches;
+      }
+      return run_residual<T>(r, a0, acto, B, S, S, ar, st, a1, 256);
+    }
+    T *rw = nullptr, *ac = nullptr;
+    concat(a0, 256, 0, a1, 256, r, S, &rw, &ac);
+    return run_residual<T>(r, rw, ac, B, S, S, ar, st);
+  };
   const ResidualBlock& enh4 = res["decoder.enhance_layer4."];
-  concat(fusion4, 256, 0, img_feat1, 256, enh4, 16, &raw, &act);
-  T* enhance4 = run_residual<T>(enh4, raw, act, B, 16, 16, ar, st);
+  T* enhance4 = enhance(enh4, fusion4, img_feat1, 16);
   // ---- stage 2 @32x32 (models/dir.py:459-471)
   if (overlap) cudaStreamWaitEvent(st, ev_join[0], 0);
   const ResidualBlock& fus3 = res["decoder.fusion_layer3."];
@@ -903,8 +935,7 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   if (rc) return rc;
   if (aux) {  // models/dir.py:470-476: only the seg/dense heads consume enhance_layer3
     const ResidualBlock& enh3 = res["decoder.enhance_layer3."];
-    concat(fusion3, 256, 0, img_feat2, 256, enh3, 32, &raw, &act);
-    T* enhance3 = run_residual<T>(enh3, raw, act, B, 32, 32, ar, st);
+    T* enhance3 = enhance(enh3, fusion3, img_feat2, 32);
     const int64_t px = (int64_t)B * 32 * 32;
     T* fmid = aalloc<T>(ar, px * 256);
     T* feat = aalloc<T>(ar, px * 256);
@@ -937,9 +968,10 @@ template int Engine::run_backbone<float>(const float*, int, int, int, Arena&, fl
 template int Engine::run_backbone<__nv_bfloat16>(const float*, int, int, int, Arena&, __nv_bfloat16**,
                                                  __nv_bfloat16**, __nv_bfloat16**, __nv_bfloat16**, cudaStream_t);
 template float* Engine::run_residual<float>(const ResidualBlock&, const float*, const float*, int, int, int, Arena&,
-                                            cudaStream_t);
+                                            cudaStream_t, const float*, int);
 template __nv_bfloat16* Engine::run_residual<__nv_bfloat16>(const ResidualBlock&, const __nv_bfloat16*,
-                                                            const __nv_bfloat16*, int, int, int, Arena&, cudaStream_t);
+                                                            const __nv_bfloat16*, int, int, int, Arena&, cudaStream_t,
+                                                            const __nv_bfloat16*, int);
 template int Engine::run_init<float>(const float*, int, float*, int, float*, int, Arena&, cudaStream_t);
 template int Engine::run_init<__nv_bfloat16>(const __nv_bfloat16*, int, float*, int, float*, int, Arena&,
                                              cudaStream_t);

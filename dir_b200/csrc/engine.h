@@ -172,11 +172,16 @@ struct Engine {
   void make_dual(ConvLayer& F, const ConvLayer& main, const ConvLayer& second);
   template <typename T>
   bool conv_pair(const ConvLayer& F, const ConvLayer& main, const ConvLayer& second, const T* x1, const T* x2, T* y,
-                 int B, int Ho, int Wo, cudaStream_t st);
+                 int B, int Ho, int Wo, cudaStream_t st, const T* x2b = nullptr, int C2b = 0);
   template <typename T>
   int run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** c1, T** c2, T** c3, T** c4, cudaStream_t st);
   template <typename T>
-  T* run_residual(const ResidualBlock& r, const T* raw, const T* act, int B, int H, int W_, Arena& ar, cudaStream_t st);
+  // raw2 != null: the block input is the channel concat [raw (cin - c2 channels) | raw2 (c2 channels)], never built
+  T* run_residual(const ResidualBlock& r, const T* raw, const T* act, int B, int H, int W_, Arena& ar, cudaStream_t st,
+                  const T* raw2 = nullptr, int c2 = 0);
+  // true if run_residual can take the skip operand of `r` from two sources (tensor-core pair GEMM available)
+  template <typename T>
+  bool virtual_concat_ok(const ResidualBlock& r, int B, int H, int W_) const;
   template <typename T>
   int run_init(const T* c4, int B, float* stage_rec, int rec_stride, float* para, int para_stride, Arena& ar,
                cudaStream_t st);
@@ -195,8 +200,9 @@ int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y,
                    int H, int W, cudaStream_t st);
 int conv_tc_prepare_dual(ConvLayer& F, const ConvLayer& main, const ConvLayer& second, __nv_bfloat16* w16, float* scale,
                          float* shift, cudaStream_t st);
-int launch_conv_tc_dual(const ConvLayer& L, const __nv_bfloat16* x1, int C1, const __nv_bfloat16* x2, int C2,
-                        int stride2, __nv_bfloat16* y, int B, int Ho, int Wo, cudaStream_t st);
+int launch_conv_tc_dual(const ConvLayer& L, const __nv_bfloat16* x1, int C1, const __nv_bfloat16* x2, int C2, int stride2,
+                        __nv_bfloat16* y, int B, int Ho, int Wo, cudaStream_t st, const __nv_bfloat16* x2b = nullptr,
+                        int C2b = 0);
 int conv_tc_prepare_stem(ConvLayer& L, const float* w_raw, __nv_bfloat16* w_packed, cudaStream_t st);
 size_t conv_tc_stem_scratch_bytes(int B, int H, int W);
 void launch_stem_pack(const float* img, const unsigned char* img_u8, __nv_bfloat16* scratch, int B, int H, int W,
