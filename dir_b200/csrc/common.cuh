@@ -262,6 +262,9 @@ __device__ __forceinline__ void pdl_trigger() {
 #endif
 
 bool pdl_enabled();  // engine.cu
+// Opt a kernel in to more than 48 KB of (static + dynamic) shared memory. The attribute is per (function, device), so
+// it is remembered per pair (a process-wide "done" flag would leave a second device of the process without it).
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes);  // engine.cu
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -276,6 +279,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  if (smem > 0) {
+    const cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem);
+    if (e != cudaSuccess) return e;
+  }
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -672,7 +672,6 @@ template <int BN, int SW, int CG>
 int launch_tc_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                  const CUtensorMap& tmA2, const CUtensorMap& tmA3, TcArgs a, cudaStream_t st) {
   using Cfg = TcCfg<BN, SW, CG>;
-  static int attr_bytes = 0;
   const int nkb = a.taps * a.cblocks + a.kb2;
   // resident weights: one n-tile whose whole K extent fits next to a useful A ring (layer1: <= 72 KB); the TMA engine
   // then only fetches activations (it retires ~one 128-byte box row per 3-5 cycles, the limit of these layers)
@@ -682,12 +681,8 @@ int launch_tc_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   while (stages > 1 && Cfg::smem_bytes(stages, a.has_res, a.b_resident ? nkb : stages) > 227 * 1024) --stages;
   a.stages = stages;
   const int smem = Cfg::smem_bytes(stages, a.has_res, a.b_resident ? nkb : stages);
-  if (smem > attr_bytes) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<BN, SW, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-        cudaSuccess)
-      return DIRB200_E_CUDA;
-    attr_bytes = 227 * 1024;
-  }
+  if (ensure_dynamic_smem(reinterpret_cast<const void*>(conv_tc_kernel<BN, SW, CG>), 227 * 1024) != cudaSuccess)
+    return DIRB200_E_CUDA;
   const int units = (a.m_tiles / CG) * a.n_tiles;        // scheduling units (one per CTA, or per CTA pair)
   const int slots = num_sms() / CG;
   const int grid = (units < slots ? units : slots) * CG;

@@ -4,8 +4,27 @@
 
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace dirb200 {
+
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
+  if (bytes == 0) return cudaSuccess;
+  // static + dynamic above 48 KB needs the opt-in too (the joint-space kernels pair ~32 KB of each): ask for >= 64 KB
+  if (bytes < 64 * 1024) bytes = 64 * 1024;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& cur = done[std::make_pair(func, dev)];
+  if (cur >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
 
 bool pdl_enabled() {
   static const bool on = [] {

@@ -672,12 +672,6 @@ void launch_pack_fusion_weight_tc(const float* w, void* wpk, cudaStream_t st) {
 }
 
 void launch_bone_coef_tc(const float* jf, const void* wpk, void* P, int p_bf16, int B, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(bone_coef_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM);
-    cudaFuncSetAttribute(bone_coef_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM);
-    attr = true;
-  }
   if (p_bf16)
     launch_pdl(bone_coef_tc_kernel<__nv_bfloat16>, dim3(40, ceil_div(2 * B, 128)), dim3(192), CT_SMEM, st, jf,
                reinterpret_cast<const uint8_t*>(wpk), reinterpret_cast<__nv_bfloat16*>(P), B);
@@ -687,11 +681,6 @@ void launch_bone_coef_tc(const float* jf, const void* wpk, void* P, int p_bf16, 
 }
 
 void launch_bone_coef(const float* jf, const float* wp, float* P, int B, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(bone_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr = true;
-  }
   launch_pdl(bone_coef_kernel, dim3(dim3(40, 9, ceil_div(2 * B, 64))), dim3(256), 2 * 32 * 128 * 4 + 16, st, jf, wp, P, B);
 }
 
@@ -700,30 +689,19 @@ void launch_bone_fusion(const float* rec, int rec_stride, const float* P, const 
                         int B, int S, float distance, cudaStream_t st) {
   const int nchunks = (3 * S * 40 + 31) / 32;
   const size_t smem = (size_t)S * 256 * 4 + (size_t)3 * S * 40 * sizeof(Entry) + (nchunks + 1) * 4 + 128 * 4;
-  static bool attr[2][2] = {{false, false}, {false, false}};
-  const int ti = sizeof(T) == 4 ? 0 : 1, si = S == 32 ? 1 : 0;
   if (S == 32) {
-    if (!attr[ti][si]) cudaFuncSetAttribute(bone_fusion_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr[ti][si] = true;
     launch_pdl(bone_fusion_kernel<T, 32>, dim3(dim3(B, S)), dim3(256), smem, st, rec, rec_stride, P, scale, shift, out, distance);
   } else {
-    if (!attr[ti][si]) cudaFuncSetAttribute(bone_fusion_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr[ti][si] = true;
     launch_pdl(bone_fusion_kernel<T, 16>, dim3(dim3(B, S)), dim3(256), smem, st, rec, rec_stride, P, scale, shift, out, distance);
   }
 }
 template <typename PT>
 static void launch_bone_fusion_tc_t(const float* rec, int rec_stride, const PT* P, const float* scale, const float* shift,
                                     __nv_bfloat16* out, int B, int S, float distance, cudaStream_t st) {
-  static bool attr[2] = {false, false};
   if (S == 32) {
-    if (!attr[0]) cudaFuncSetAttribute(bone_fusion_tc_kernel<32, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
-    attr[0] = true;
     launch_pdl(bone_fusion_tc_kernel<32, PT>, dim3(B, 8), dim3(FT_THREADS), FT_SMEM, st, rec, rec_stride, P, scale, shift,
                out, distance);
   } else {
-    if (!attr[1]) cudaFuncSetAttribute(bone_fusion_tc_kernel<16, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
-    attr[1] = true;
     launch_pdl(bone_fusion_tc_kernel<16, PT>, dim3(B, 2), dim3(FT_THREADS), FT_SMEM, st, rec, rec_stride, P, scale, shift,
                out, distance);
   }

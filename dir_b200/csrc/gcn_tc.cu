@@ -198,11 +198,6 @@ void launch_pack_gcn_weight_tc(const float* w, void* wpk, cudaStream_t st) {
 }
 
 void launch_gcn_gemm_tc(const GcnGemmArgs& a, const void* wpk_left, const void* wpk_right, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(gcn_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
-    attr = true;
-  }
   launch_pdl(gcn_gemm_tc_kernel, dim3(NJ, 2, ceil_div(a.B, 128)), dim3(G_THREADS), G_SMEM, st, a,
              reinterpret_cast<const uint8_t*>(wpk_left), reinterpret_cast<const uint8_t*>(wpk_right));
 }

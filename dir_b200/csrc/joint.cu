@@ -593,41 +593,21 @@ __global__ void __launch_bounds__(256) bone_vis_kernel(const float* __restrict__
 
 template <typename T>
 void launch_joint_embed(const EmbedArgs& a, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(joint_embed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr = true;
-  }
   launch_pdl(joint_embed_kernel<T>, dim3(dim3(a.B, 2)), dim3(128), 2 * 32 * 128 * 4 + 16, st, a);
 }
 template void launch_joint_embed<float>(const EmbedArgs&, cudaStream_t);
 template void launch_joint_embed<__nv_bfloat16>(const EmbedArgs&, cudaStream_t);
 
 void launch_gcn_gemm(const GcnGemmArgs& a, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(gcn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr = true;
-  }
   launch_pdl(gcn_gemm_kernel, dim3(dim3(2 * NJ, 2, ceil_div(a.B, GBT))), dim3(256), 2 * 32 * 128 * 4 + 16, st, a);
 }
 
 void launch_gcn_finish(const GcnFinishArgs& a, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(gcn_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr = true;
-  }
   launch_pdl(gcn_finish_kernel, dim3(dim3(NJ, 2, ceil_div(a.B, GBT))), dim3(256), 2 * 32 * 128 * 4 + 16, st, a);
 }
 
 void launch_ste(const float* x, float* y, const SteWeights& w, int B, cudaStream_t st) {
-  static bool attr_set = false;
   const int smem = STE_SMEM_BYTES;
-  if (!attr_set) {
-    cudaFuncSetAttribute(ste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_set = true;
-  }
   launch_pdl(ste_kernel, dim3(B), dim3(STE_THREADS), smem, st, x, y, w);
 }
 

@@ -474,11 +474,6 @@ void launch_pack_ste_tc(const float* src, int l, int which, void* packed, cudaSt
 }
 
 void launch_ste_tc(const float* x, float* y, const SteWeights& w, const void* packed, int B, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(ste_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    attr = true;
-  }
   launch_pdl(ste_tc_kernel, dim3((B + 1) / 2), dim3(TC_THREADS), SMEM_BYTES, st, x, y, w,
              reinterpret_cast<const uint8_t*>(packed), B);
 }

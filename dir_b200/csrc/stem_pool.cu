@@ -285,12 +285,6 @@ void launch_pack_stem_pool_weight(const float* w, void* packed, cudaStream_t st)
 // in: the padded NHWC4 bf16 image (B,256,264,4) of stem_pack_kernel; y: (B,64,64,64) NHWC bf16
 int launch_stem_pool(const void* in, const void* packed_w, const float* scale, const float* shift, __nv_bfloat16* y, int B,
                      cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM) != cudaSuccess)
-      return DIRB200_E_CUDA;
-    attr = true;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
