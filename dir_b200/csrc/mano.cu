@@ -253,6 +253,32 @@ __device__ __forceinline__ void warp_linear(const float* __restrict__ W, const f
   }
 }
 
+// The 64-output MANO head: warp w owns outputs w, w+8, ..., w+56 and runs the eight dot products CONCURRENTLY (eight
+// independent coalesced weight-row loads in flight per lane instead of one); per-output sums are unchanged.
+__device__ __forceinline__ void warp_linear64(const float* __restrict__ W, const float* __restrict__ bias,
+                                              const float* vec, int K, float* out) {
+  constexpr int NW = THREADS / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float a[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) a[u] = 0.f;
+  const float* wr = W + (int64_t)warp * K;
+  const int64_t ostride = (int64_t)NW * K;
+  for (int k = lane; k < K; k += 32) {
+    const float x = vec[k];
+    float wv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) wv[u] = __ldg(wr + u * ostride + k);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = fmaf(wv[u], x, a[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float r = warp_sum(a[u]);
+    if (lane == 0) out[warp + u * NW] = r + bias[warp + u * NW];
+  }
+}
+
 __global__ void __launch_bounds__(THREADS) regress_mano_kernel(RegressArgs a) {
   pdl_wait();
   __shared__ ManoSmem s;
@@ -264,7 +290,8 @@ __global__ void __launch_bounds__(THREADS) regress_mano_kernel(RegressArgs a) {
   load_vec(vin, a.in0[hand], a.in1[hand], b);
   __syncthreads();
   const int K = a.in0[hand].n + (a.in1[hand].p ? a.in1[hand].n : 0);
-  warp_linear(a.Wm[hand], a.bm[hand], vin, K, 64, s.para);
+  static_assert(THREADS == 256, "warp_linear64 assumes 8 warps x 8 outputs");
+  warp_linear64(a.Wm[hand], a.bm[hand], vin, K, s.para);
   __syncthreads();
   if (tid < 64) a.mano_para[(int64_t)b * a.para_stride + hand * 64 + tid] = s.para[tid];
 
