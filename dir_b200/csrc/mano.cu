@@ -107,13 +107,22 @@ __device__ void mano_forward(ManoSmem& s, const ManoWeights& w, float* __restric
   __syncthreads();
   // 4. J = J_regressor . v_shaped (manolayer.py:177): 48 dot products of length 778, one warp each
   {
+    // warp w owns joints 2w, 2w+1 (all three coordinates): six concurrent dot products, each regressor weight
+    // loaded once for its three coordinates (per-output sums unchanged)
     const int warp = tid >> 5, lane = tid & 31;
-    for (int o = warp; o < 48; o += THREADS / 32) {
-      int j = o / 3, c = o % 3;
-      float a = 0.f;
-      for (int v = lane; v < NV; v += 32) a = fmaf(__ldg(w.jreg + j * NV + v), s.vs[v * 3 + c], a);
-      a = warp_sum(a);
-      if (lane == 0) s.J[j][c] = a;
+    const int ja = 2 * warp, jb = 2 * warp + 1;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    for (int v = lane; v < NV; v += 32) {
+      const float wa = __ldg(w.jreg + ja * NV + v), wb = __ldg(w.jreg + jb * NV + v);
+      const float x = s.vs[v * 3], y = s.vs[v * 3 + 1], z = s.vs[v * 3 + 2];
+      a0 = fmaf(wa, x, a0); a1 = fmaf(wa, y, a1); a2 = fmaf(wa, z, a2);
+      b0 = fmaf(wb, x, b0); b1 = fmaf(wb, y, b1); b2 = fmaf(wb, z, b2);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    b0 = warp_sum(b0); b1 = warp_sum(b1); b2 = warp_sum(b2);
+    if (lane == 0) {
+      s.J[ja][0] = a0; s.J[ja][1] = a1; s.J[ja][2] = a2;
+      s.J[jb][0] = b0; s.J[jb][1] = b1; s.J[jb][2] = b2;
     }
   }
   __syncthreads();
