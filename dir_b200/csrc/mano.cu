@@ -127,25 +127,26 @@ __device__ void mano_forward(ManoSmem& s, const ManoWeights& w, float* __restric
   }
   __syncthreads();
   // 5. v_posed = v_shaped + posedirs . pose_map (manolayer.py:180-181); each thread owns elements tid + 256*e of vs.
-  //    The 1.26 MB posedirs matrix streams from L2: 10 independent accumulators x 3 k-steps = 30 loads in flight.
+  //    The 1.26 MB posedirs matrix streams from L2: 10 independent accumulators x 5 k-steps = 50 loads in flight.
   {
     constexpr int NE = (NV3 + THREADS - 1) / THREADS;  // 10
     float pv[NE];
 #pragma unroll
     for (int e = 0; e < NE; ++e) pv[e] = 0.f;
     const float* pd = w.posedirs_t + tid;
-    for (int k = 0; k < 135; k += 3) {
-      const float m0 = s.pose_map[k], m1 = s.pose_map[k + 1], m2 = s.pose_map[k + 2];
-      float l0[NE], l1[NE], l2[NE];
+    for (int k = 0; k < 135; k += 5) {  // 135 = 27 x 5: 50 independent loads in flight per thread
+      float m[5], l[5][NE];
 #pragma unroll
-      for (int e = 0; e < NE; ++e) {
-        const bool ok = tid + e * THREADS < NV3;
-        l0[e] = ok ? __ldg(pd + (size_t)k * NV3 + e * THREADS) : 0.f;
-        l1[e] = ok ? __ldg(pd + (size_t)(k + 1) * NV3 + e * THREADS) : 0.f;
-        l2[e] = ok ? __ldg(pd + (size_t)(k + 2) * NV3 + e * THREADS) : 0.f;
-      }
+      for (int q = 0; q < 5; ++q) m[q] = s.pose_map[k + q];
 #pragma unroll
-      for (int e = 0; e < NE; ++e) pv[e] = fmaf(l2[e], m2, fmaf(l1[e], m1, fmaf(l0[e], m0, pv[e])));
+      for (int q = 0; q < 5; ++q)
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+          l[q][e] = (tid + e * THREADS < NV3) ? __ldg(pd + (size_t)(k + q) * NV3 + e * THREADS) : 0.f;
+#pragma unroll
+      for (int q = 0; q < 5; ++q)  // ascending k: the per-element summation order is unchanged
+#pragma unroll
+        for (int e = 0; e < NE; ++e) pv[e] = fmaf(l[q][e], m[q], pv[e]);
     }
 #pragma unroll
     for (int e = 0; e < NE; ++e)
