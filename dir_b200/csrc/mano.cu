@@ -326,7 +326,27 @@ __global__ void __launch_bounds__(THREADS) regress_mano_kernel(RegressArgs a) {
     load_vec(vin, a.off0, a.off1, b);
     __syncthreads();
     const int Ko = a.off0.n + (a.off1.p ? a.off1.n : 0);
-    warp_linear(a.Wo, a.bo, vin, Ko, 3, rec + DIRB200_OFF_OFFSET);
+    // three outputs over K ~ 2.7k: all 8 warps split K (one warp per output left 5 warps idle behind an 84-iteration
+    // load chain); partial sums meet in smem (fp32, association differs from the sequential sum only)
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+      for (int k = tid; k < Ko; k += THREADS) {
+        const float x = vin[k];
+        o0 = fmaf(__ldg(a.Wo + k), x, o0);
+        o1 = fmaf(__ldg(a.Wo + Ko + k), x, o1);
+        o2 = fmaf(__ldg(a.Wo + 2 * (int64_t)Ko + k), x, o2);
+      }
+      o0 = warp_sum(o0); o1 = warp_sum(o1); o2 = warp_sum(o2);
+      if (lane == 0) { hid[warp * 3] = o0; hid[warp * 3 + 1] = o1; hid[warp * 3 + 2] = o2; }
+      __syncthreads();
+      if (tid < 3) {
+        float r = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < THREADS / 32; ++wv) r += hid[wv * 3 + tid];
+        rec[DIRB200_OFF_OFFSET + tid] = r + a.bo[tid];
+      }
+    }
   }
   mano_forward(s, a.mano[hand], rec, hand);
 }
