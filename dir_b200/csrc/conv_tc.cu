@@ -13,11 +13,19 @@
 //   zero-padded NHWC4 bf16 buffer; a k-block is one kernel row (8 px x 4 ch = 32 elements = 64 B, SWIZZLE_64B)
 //   and the A box is taken from an OVERLAPPING-stride view of that buffer (consecutive wo are 2 px = 16 B apart),
 //   so the 7x7 window gather is again pure TMA.
-// Persistent schedule (grid = min(tiles, SMs)), roles per CTA (192 threads):
-//   warp 0   : TMA producer over a `stages`-deep smem ring (runs ahead across tiles)
+// Persistent schedule (grid = min(tiles, SMs)), roles per CTA (320 threads):
+//   warp 0   : TMA producer over a `stages`-deep smem ring (runs ahead across tiles; also feeds the residual ring)
 //   warp 1   : TMEM alloc (2 accumulator buffers of BN fp32 columns) + single-thread tcgen05.mma issue
-//   warps 2-5: epilogue of tile i overlapped with the main loop of tile i+1: tcgen05.ld -> affine/residual/ReLU ->
-//              bf16 -> 128B-swizzled smem staging -> TMA store (coalesced, asynchronous); residual tiles arrive by TMA.
+//   warps 2-9: two epilogue groups of 4 warps taking alternate 64-column chunks; the epilogue of tile i overlaps the
+//              main loop of tile i+1: tcgen05.ld -> affine/residual/ReLU -> bf16 -> 128B-swizzled smem staging ->
+//              TMA store (coalesced, asynchronous); residual tiles arrive by TMA.
+// Variants selected per layer at launch:
+//   CG = 2       : clusters of two CTAs share every MMA (tcgen05.mma.cta_group::2, M = 256); each CTA loads its own A
+//                  tile and half of the weight tile (every layer with BN >= 128 and an even number of M tiles)
+//   b_resident   : single-n-tile layers whose whole weight matrix fits next to the A ring load it once per CTA
+//   kb2 / kb2a   : K-concatenated second (and third) 1x1 operand: conv3 + downsample/skip as one GEMM, the skip operand
+//                  optionally read from the two sources of a channel concat that is never materialised
+//   stem         : legacy TMA stem (DIRB200_STEM_SPLIT=1); the default stem is stem_pool.cu
 #include <cuda.h>
 
 #include <cstdio>
