@@ -27,4 +27,7 @@ def main(path, per_forward):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]))
+    try:
+        main(sys.argv[1], int(sys.argv[2]))
+    except BrokenPipeError:  # piped into head
+        pass
