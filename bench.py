@@ -93,7 +93,7 @@ def cpu_forward_rate(batch, min_seconds, max_iters):
     unmodified reference by tests/golden) with all host threads. Returns (images/s, cores, seconds, iters)."""
     import torch
 
-    from dir_b200.synth import make_state_dict
+    from oracle.synth import make_state_dict
     from oracle import dir_oracle as O
 
     cores = os.cpu_count() or 1
@@ -115,7 +115,7 @@ def run_reference(args, rank):
         return
     import torch
 
-    from dir_b200.synth import make_state_dict
+    from oracle.synth import make_state_dict
     from oracle import dir_oracle as O
 
     cores = os.cpu_count() or 1
@@ -156,7 +156,7 @@ def main():
 
     import dir_b200
     from dir_b200 import capi
-    from dir_b200.synth import make_state_dict
+    from oracle.synth import make_state_dict
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")

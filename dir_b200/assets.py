@@ -66,11 +66,26 @@ def _value(v):
     return np.asarray(v)
 
 
+# A MANO pickle only needs ndarrays, scipy sparse matrices and (stand-ins for) chumpy objects: every other global is
+# refused, so loading a third-party pickle cannot run arbitrary code.
+_ALLOWED_GLOBAL_ROOTS = ("numpy", "scipy.sparse")
+_ALLOWED_GLOBALS = {("builtins", n) for n in ("dict", "list", "tuple", "set", "frozenset", "int", "float", "complex",
+                                              "bool", "str", "bytes", "bytearray", "slice", "range", "object")}
+_ALLOWED_GLOBALS |= {("__builtin__", n) for _, n in list(_ALLOWED_GLOBALS)} | {("copy_reg", "_reconstructor"),
+                                                                               ("copyreg", "_reconstructor"),
+                                                                               ("collections", "OrderedDict"),
+                                                                               ("_codecs", "encode")}  # numpy's py2 bytes
+
+
 class _ManoUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module == "chumpy" or module.startswith("chumpy."):
             return _ChStandIn
-        return super().find_class(module, name)
+        if (module, name) in _ALLOWED_GLOBALS or any(module == r or module.startswith(r + ".")
+                                                     for r in _ALLOWED_GLOBAL_ROOTS):
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"MANO pickle references {module}.{name}, which is not on the allow-list "
+                                     "(numpy, scipy.sparse, chumpy stand-in, plain containers)")
 
 
 def read_mano_pickle(path_or_bytes):
@@ -158,13 +173,21 @@ def has_mano_pickles(mano_root):
         os.path.isfile(os.path.join(mano_root, f"MANO_{s}.pkl")) for s in ("LEFT", "RIGHT"))
 
 
-def read_checkpoint(path_or_obj, expected_keys=None):
+def read_checkpoint(path_or_obj, expected_keys=None, trusted=False):
     """`torch.load(path, map_location='cpu')['net']` (apps/eval.py:107) made tolerant of the variants in the wild:
     a bare state_dict, a `module.` (DataParallel) prefix. Returns (state_dict, report) where report lists the
-    keys of `expected_keys` that are absent and the checkpoint keys that are not expected."""
+    keys of `expected_keys` that are absent and the checkpoint keys that are not expected.
+    The file is read with `weights_only=True` (tensors and plain containers only: nothing in it can execute);
+    `trusted=True` is the explicit opt-in to the reference's unrestricted `torch.load` for checkpoints that carry
+    arbitrary pickled objects (e.g. an optimizer with custom classes)."""
     obj = path_or_obj
     if isinstance(obj, (str, os.PathLike)):
-        obj = torch.load(obj, map_location="cpu", weights_only=False)
+        try:
+            obj = torch.load(obj, map_location="cpu", weights_only=True)
+        except pickle.UnpicklingError:
+            if not trusted:
+                raise
+            obj = torch.load(obj, map_location="cpu", weights_only=False)
     if isinstance(obj, dict) and "net" in obj and isinstance(obj["net"], dict):
         obj = obj["net"]
     if not isinstance(obj, dict) or not all(isinstance(k, str) for k in obj):

@@ -91,7 +91,7 @@ def load_library():
 class Handle:
     """Owns one dirb200_handle*. All methods raise DirB200Error on a non-zero return code."""
 
-    def __init__(self, precision="bf16", max_batch=128, aux_outputs=True, device=0):
+    def __init__(self, precision="fp32", max_batch=128, aux_outputs=True, device=0):
         self.lib = load_library()
         cfg = Config(PRECISION[precision], int(max_batch), int(bool(aux_outputs)), int(device))
         h = C.c_void_p()
@@ -99,6 +99,7 @@ class Handle:
         if rc != 0:
             raise DirB200Error(f"dirb200_create failed ({rc}): {self.lib.dirb200_last_error(None).decode()}")
         self.h = h
+        self.device = int(device)
         self.precision = precision
         self.aux_outputs = bool(aux_outputs)
         self.max_batch = int(max_batch)

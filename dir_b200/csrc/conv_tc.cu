@@ -734,28 +734,31 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap*
   return launch_tc_cg<BN, SW, 1>(tmA, tmB, tmY, tmR, tmA2, t3, a, st);
 }
 
+// Tensor maps are cached per (pointer, geometry). Lookups hand out COPIES: an insertion may evict (clear) the cache, so a
+// pointer into it could dangle while the same launch is still collecting its other maps.
 template <typename Key>
 struct MapCache {
   std::map<Key, CUtensorMap> m;
-  CUtensorMap* find(const Key& k) {
+  bool find(const Key& k, CUtensorMap* out) const {
     auto it = m.find(k);
-    return it == m.end() ? nullptr : &it->second;
+    if (it == m.end()) return false;
+    *out = it->second;
+    return true;
   }
-  CUtensorMap* put(const Key& k, const CUtensorMap& v) {
+  void put(const Key& k, const CUtensorMap& v) {
     if (m.size() > 8192) m.clear();
-    return &m.emplace(k, v).first->second;
+    m.emplace(k, v);
   }
 };
 
-const CUtensorMap* rowmajor_map_cached(const void* ptr, int rows, int cols) {
+bool rowmajor_map_cached(const void* ptr, int rows, int cols, CUtensorMap* out) {
   typedef std::tuple<const void*, int, int> Key;
   static thread_local MapCache<Key> cache;
   Key k(ptr, rows, cols);
-  CUtensorMap* p = cache.find(k);
-  if (p) return p;
-  CUtensorMap tm;
-  if (!make_rowmajor_map(&tm, ptr, rows, cols)) return nullptr;
-  return cache.put(k, tm);
+  if (cache.find(k, out)) return true;
+  if (!make_rowmajor_map(out, ptr, rows, cols)) return false;
+  cache.put(k, *out);
+  return true;
 }
 
 }  // namespace
@@ -859,10 +862,9 @@ int launch_conv_tc_stem(const ConvLayer& L, const float* img, const unsigned cha
   typedef std::tuple<const void*, int, int, int> Key;
   static thread_local MapCache<Key> cache;
   Key key(scratch, B, H, W);
-  CUtensorMap* tmA = cache.find(key);
-  if (!tmA) {
+  CUtensorMap tm;
+  if (!cache.find(key, &tm)) {
     // overlapping view of the padded NHWC4 buffer: window wo starts at padded pixel 2*wo (= pixel 2*wo-3)
-    CUtensorMap tm;
     cuuint64_t dims[4] = {32, (cuuint64_t)Wo, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {16, (cuuint64_t)Wp * 8, (cuuint64_t)H * Wp * 8};
     cuuint32_t box[4] = {32, (cuuint32_t)BM, 1, 1};
@@ -874,11 +876,11 @@ int launch_conv_tc_stem(const ConvLayer& L, const float* img, const unsigned cha
       fprintf(stderr, "dirb200: cuTensorMapEncodeTiled(stem A, overlapping strides) failed: %d\n", (int)r);
       return DIRB200_E_CUDA;
     }
-    tmA = cache.put(key, tm);
+    cache.put(key, tm);
   }
   const int M = B * Ho * Wo;
-  const CUtensorMap* tmY = rowmajor_map_cached(y, M, 64);
-  if (!tmY) return DIRB200_E_CUDA;
+  CUtensorMap tmY;
+  if (!rowmajor_map_cached(y, M, 64, &tmY)) return DIRB200_E_CUDA;
   TcArgs a{};
   a.scale = L.scale;
   a.shift = L.shift;
@@ -896,19 +898,18 @@ int launch_conv_tc_stem(const ConvLayer& L, const float* img, const unsigned cha
   a.stem = 1;
   a.m_tiles = (M + BM - 1) / BM;
   a.n_tiles = 1;
-  return launch_tc<64, 64>(*tmA, L.wmap, nullptr, *tmY, *tmY, *tmA, a, st);
+  return launch_tc<64, 64>(tm, L.wmap, nullptr, tmY, tmY, tm, a, st);
 }
 
 namespace {
 // activation tensor map {C, W, H, N} with box {64, wbox*s, hbox*s, nbox}, cached per (pointer, geometry)
-const CUtensorMap* act_map_cached(const __nv_bfloat16* x, int B, int H, int W, int C, int stride, const Boxes& bx,
-                                  const char* name) {
+bool act_map_cached(const __nv_bfloat16* x, int B, int H, int W, int C, int stride, const Boxes& bx, const char* name,
+                    CUtensorMap* out) {
   typedef std::tuple<const void*, int, int, int, int, int, int, int, int> Key;
   static thread_local MapCache<Key> cache;
   Key key(x, B, H, W, C, stride, bx.wbox, bx.hbox, bx.nbox);
-  CUtensorMap* tm = cache.find(key);
-  if (tm) return tm;
-  CUtensorMap t;
+  if (cache.find(key, out)) return true;
+  CUtensorMap& t = *out;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   cuuint32_t box[4] = {64, (cuuint32_t)(bx.wbox * stride), (cuuint32_t)(bx.hbox * stride), (cuuint32_t)bx.nbox};
@@ -918,9 +919,10 @@ const CUtensorMap* act_map_cached(const __nv_bfloat16* x, int B, int H, int W, i
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     fprintf(stderr, "dirb200: cuTensorMapEncodeTiled(A) failed: %d (layer %s)\n", (int)r, name);
-    return nullptr;
+    return false;
   }
-  return cache.put(key, t);
+  cache.put(key, t);
+  return true;
 }
 }  // namespace
 
@@ -934,12 +936,15 @@ int launch_conv_tc_dual(const ConvLayer& L, const __nv_bfloat16* x1, int C1, con
   // two sources (the concatenated tensor is never materialised)
   const Boxes bx = pick_boxes(Ho, Wo);
   const int C2a = x2b ? C2 - C2b : C2;
-  const CUtensorMap* tmA = act_map_cached(x1, B, Ho, Wo, C1, 1, bx, L.name.c_str());
-  const CUtensorMap* tmA2 = act_map_cached(x2, B, Ho * stride2, Wo * stride2, C2a, stride2, bx, L.name.c_str());
-  const CUtensorMap* tmA3 = x2b ? act_map_cached(x2b, B, Ho * stride2, Wo * stride2, C2b, stride2, bx, L.name.c_str()) : nullptr;
+  if (C2a % 64 || (x2b && C2b % 64)) return DIRB200_E_CUDA;
+  CUtensorMap tmA, tmA2, tmA3s, tmY;
   const int M = B * Ho * Wo;
-  const CUtensorMap* tmY = rowmajor_map_cached(y, M, L.Cout);
-  if (!tmA || !tmA2 || !tmY || (x2b && !tmA3) || C2a % 64 || (x2b && C2b % 64)) return DIRB200_E_CUDA;
+  if (!act_map_cached(x1, B, Ho, Wo, C1, 1, bx, L.name.c_str(), &tmA) ||
+      !act_map_cached(x2, B, Ho * stride2, Wo * stride2, C2a, stride2, bx, L.name.c_str(), &tmA2) ||
+      (x2b && !act_map_cached(x2b, B, Ho * stride2, Wo * stride2, C2b, stride2, bx, L.name.c_str(), &tmA3s)) ||
+      !rowmajor_map_cached(y, M, L.Cout, &tmY))
+    return DIRB200_E_CUDA;
+  const CUtensorMap* tmA3 = x2b ? &tmA3s : nullptr;
   TcArgs a{};
   a.scale = L.scale;
   a.shift = L.shift;
@@ -959,9 +964,9 @@ int launch_conv_tc_dual(const ConvLayer& L, const __nv_bfloat16* x1, int C1, con
   a.m_tiles = (M + BM - 1) / BM;
   a.n_tiles = L.Cout / L.wmap_bn;
   switch (L.wmap_bn) {
-    case 256: return launch_tc<256, 128>(*tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, *tmY, *tmY, *tmA2, a, st, tmA3);
-    case 128: return launch_tc<128, 128>(*tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, *tmY, *tmY, *tmA2, a, st, tmA3);
-    default: return launch_tc<64, 128>(*tmA, L.wmap, nullptr, *tmY, *tmY, *tmA2, a, st, tmA3);
+    case 256: return launch_tc<256, 128>(tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, tmY, tmY, tmA2, a, st, tmA3);
+    case 128: return launch_tc<128, 128>(tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, tmY, tmY, tmA2, a, st, tmA3);
+    default: return launch_tc<64, 128>(tmA, L.wmap, nullptr, tmY, tmY, tmA2, a, st, tmA3);
   }
 }
 
@@ -969,12 +974,13 @@ int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y,
                    int H, int W, cudaStream_t st) {
   const int Ho = (H + 2 * L.pad - L.kh) / L.stride + 1, Wo = (W + 2 * L.pad - L.kw) / L.stride + 1;
   const Boxes bx = pick_boxes(Ho, Wo);
-  const CUtensorMap* tmA = act_map_cached(x, B, H, W, L.Cin, L.stride, bx, L.name.c_str());
-  if (!tmA) return DIRB200_E_CUDA;
+  CUtensorMap tmA, tmY, tmR;
   const int M = B * Ho * Wo;
-  const CUtensorMap* tmY = rowmajor_map_cached(y, M, L.Cout);
-  const CUtensorMap* tmR = res ? rowmajor_map_cached(res, M, L.Cout) : tmY;
-  if (!tmY || !tmR) return DIRB200_E_CUDA;
+  if (!act_map_cached(x, B, H, W, L.Cin, L.stride, bx, L.name.c_str(), &tmA) ||
+      !rowmajor_map_cached(y, M, L.Cout, &tmY))
+    return DIRB200_E_CUDA;
+  if (!res) tmR = tmY;
+  else if (!rowmajor_map_cached(res, M, L.Cout, &tmR)) return DIRB200_E_CUDA;
   TcArgs a{};
   a.scale = L.scale;
   a.shift = L.shift;
@@ -994,9 +1000,9 @@ int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y,
   a.n_tiles = L.Cout / L.wmap_bn;
   a.raster_m = (double)L.Cout * L.K > (double)B * H * W * L.Cin ? 1 : 0;
   switch (L.wmap_bn) {
-    case 256: return launch_tc<256, 128>(*tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, *tmY, *tmR, *tmA, a, st);
-    case 128: return launch_tc<128, 128>(*tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, *tmY, *tmR, *tmA, a, st);
-    default: return launch_tc<64, 128>(*tmA, L.wmap, nullptr, *tmY, *tmR, *tmA, a, st);
+    case 256: return launch_tc<256, 128>(tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, tmY, tmR, tmA, a, st);
+    case 128: return launch_tc<128, 128>(tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, tmY, tmR, tmA, a, st);
+    default: return launch_tc<64, 128>(tmA, L.wmap, nullptr, tmY, tmR, tmA, a, st);
   }
 }
 

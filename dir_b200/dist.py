@@ -47,7 +47,11 @@ def forward_sharded(model, img_global: torch.Tensor):
     n = img_global.shape[0]
     lo, hi = shard_bounds(n, rank, world)
     pad = padded_shard(n, world)
-    local = model.run_raw(img_global[lo:hi])["record"]
+    if hi > lo:
+        local = model.run_raw(img_global[lo:hi])["record"]
+    else:  # fewer images than ranks: this rank has no work but must still enter the all-gather
+        from . import capi
+        local = torch.zeros(0, capi.RECORD_FLOATS, device=model._device())
     if local.shape[0] < pad:
         local = torch.cat([local, local.new_zeros(pad - local.shape[0], local.shape[1])], 0)
     full = assemble(model.allgather_records(local.contiguous()), n, world)

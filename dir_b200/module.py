@@ -71,10 +71,12 @@ def reference_key_shapes():
 
 class DIR(nn.Module):
     """B200-native DIR. Extra keyword arguments (all optional, defaults keep the reference call valid):
-    precision 'bf16' | 'fp32'; aux_outputs: also return seg/dense/proj_feat (outs_list[3]);
+    precision 'fp32' (default: the reference's numerics, <=1e-4 relative; error-compensated 3xTF32 tcgen05 convs) |
+    'bf16' (explicit opt-in: bf16 feature maps, fastest; drifts like the reference under bf16 autocast, DESIGN.md 2);
+    aux_outputs: also return seg/dense/proj_feat (outs_list[3]);
     max_batch: larger batches are processed in chunks; use_cuda_graph: capture one graph per batch size."""
 
-    def __init__(self, joint_num, mano_path, root_joint=0, precision="bf16", aux_outputs=True, max_batch=128,
+    def __init__(self, joint_num, mano_path, root_joint=0, precision="fp32", aux_outputs=True, max_batch=128,
                  use_cuda_graph=False):
         super().__init__()
         if joint_num != 21:
@@ -133,6 +135,7 @@ class DIR(nn.Module):
     def _apply(self, fn, *a, **k):
         self._packed = False
         self._graphs = {}
+        self._workspace = {}  # belongs to the old device; the handle is re-created in _ensure_handle if the GPU changed
         self._copy_stream = None  # staging ring and copy stream belong to the old device
         self._staging = {}
         return super()._apply(fn, *a, **k)
@@ -144,8 +147,14 @@ class DIR(nn.Module):
         dev = self._device()
         if dev.type != "cuda":
             raise capi.DirB200Error("DIR runs on an sm_100a CUDA device only (call .cuda()); there is no CPU fallback")
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        if self._handle is not None and self._handle.device != index:  # the module moved to another GPU
+            self._handle.close()
+            self._handle = None
+            self._packed = False
+            self._workspace = {}
         if self._handle is None:
-            self._handle = capi.Handle(self.precision, self.max_batch, self.aux_outputs, dev.index or 0)
+            self._handle = capi.Handle(self.precision, self.max_batch, self.aux_outputs, index)
         return self._handle
 
     def required_keys(self):

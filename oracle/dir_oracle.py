@@ -91,11 +91,11 @@ def upsample2x(x):
     B, C, H, W = x.shape
 
     def idx(n):
-        o = torch.arange(2 * n, dtype=torch.float32)
+        o = torch.arange(2 * n, dtype=x.dtype, device=x.device)
         s = torch.clamp((o + 0.5) * 0.5 - 0.5, min=0.0)
         i0 = s.floor().long()
         i1 = torch.clamp(i0 + 1, max=n - 1)
-        w1 = s - i0.float()
+        w1 = s - i0.to(x.dtype)
         return i0, i1, w1
 
     y0, y1, wy = idx(H)
@@ -151,7 +151,7 @@ def mano_layer(sd, p, pose, betas, side, center_idx=0):
 
     aa = mean + pose[:, 6:51] @ comps  # :124-133
     R = rodrigues(aa.reshape(-1, 3)).view(B, 15, 3, 3)  # tensutils.py:6-12
-    pose_map = (R - torch.eye(3)).reshape(B, 135)
+    pose_map = (R - torch.eye(3, dtype=pose.dtype, device=pose.device)).reshape(B, 135)
     R_root = rot6d_robust(pose[:, :6])
 
     v_shaped = torch.einsum("vck,bk->bvc", shapedirs, betas) + v_template  # :173-176
@@ -224,8 +224,8 @@ def grid_sample_joints(feat, uv):
     x = ((uv[..., 0] + 1) * W - 1) * 0.5
     y = ((uv[..., 1] + 1) * H - 1) * 0.5
     x0, y0 = torch.floor(x), torch.floor(y)
-    out = torch.zeros(B, C, uv.shape[1])
-    bidx = torch.arange(B).view(B, 1).expand(B, uv.shape[1])
+    out = torch.zeros(B, C, uv.shape[1], dtype=feat.dtype, device=feat.device)
+    bidx = torch.arange(B, device=feat.device).view(B, 1).expand(B, uv.shape[1])
     for dy in (0, 1):
         for dx in (0, 1):
             xi, yi = x0 + dx, y0 + dy
@@ -263,7 +263,7 @@ def gcn_softmax_adjacency(e1):
     """A_1 = softmax over each row of the 40 learned edge logits, -9e15 elsewhere
     (SemGCN/p_graph_conv.py:43-50). A_0 = softmax(diag logits) == I exactly."""
     nz = gcn_adjacency_logits_index()
-    A = torch.full((21, 21), -9e15)
+    A = torch.full((21, 21), -9e15, dtype=e1.dtype, device=e1.device)
     A[nz[:, 0], nz[:, 1]] = e1.flatten()
     return torch.softmax(A, dim=1)
 
@@ -337,14 +337,15 @@ def bone_proj(uv, feat, S, distance):
     p = (uv + 1) / 2 * S
     a = p[:, BONE_PARENT].unsqueeze(1)  # (B,1,20,2)
     b = p[:, BONE_CHILD].unsqueeze(1)
-    r = torch.arange(S, dtype=torch.float32) + 0.5
+    r = torch.arange(S, dtype=uv.dtype, device=uv.device) + 0.5
     gy, gx = torch.meshgrid(r, r, indexing="ij")  # pixel (row, col) -> P = (col+.5, row+.5)
+    zero = torch.zeros((), dtype=uv.dtype, device=uv.device)
     P = torch.stack((gx, gy), -1).reshape(1, S * S, 1, 2)
     dba = b - a
     d = dba / torch.hypot(dba[..., 0], dba[..., 1]).unsqueeze(-1)  # NaN when a == b
     s = ((a - P) * d).sum(-1)
     t = ((P - b) * d).sum(-1)
-    h = torch.maximum(torch.maximum(s, t), torch.zeros(()))
+    h = torch.maximum(torch.maximum(s, t), zero)
     dpa = P - a
     c = dpa[..., 0] * d[..., 1] - dpa[..., 1] * d[..., 0]
     mask = torch.hypot(h, c) < distance  # NaN -> False
@@ -355,7 +356,7 @@ def bone_proj(uv, feat, S, distance):
     fa = feat[:, BONE_PARENT].unsqueeze(1)  # (B,1,20,C)
     fb = feat[:, BONE_CHILD].unsqueeze(1)
     img = fa * wa.unsqueeze(-1) + fb * wb.unsqueeze(-1)
-    img = torch.where(mask.unsqueeze(-1), img, torch.zeros(()))
+    img = torch.where(mask.unsqueeze(-1), img, zero)
     return img.reshape(B, S, S, 20 * C).permute(0, 3, 1, 2)
 
 
@@ -429,7 +430,7 @@ def dir_forward(sd, img):
 def eval_jregressor(jreg16):
     """apps/eval.py:27-41 (class Jr): 16-joint MANO regressor -> 21 joints (5 tip vertices appended, reordered).
     Note: the reference uses tip vertex 444 for BOTH hands here (unlike manopth's 445 for the left hand)."""
-    tips = torch.zeros(5, jreg16.shape[1])
+    tips = torch.zeros(5, jreg16.shape[1], dtype=jreg16.dtype, device=jreg16.device)
     for i, v in enumerate([745, 317, 444, 556, 673]):
         tips[i, v] = 1.0
     return torch.cat([jreg16, tips], 0)[JOINT_REORDER].contiguous()

@@ -2,7 +2,7 @@
 
 Run ONLY in the build container (needs /root/reference):   python -m oracle.gen_golden
 It (1) dumps the reference's state_dict key/shape inventory, (2) loads the synthetic
-weights of oracle/synth_weights.py into the reference modules with strict=True,
+weights of oracle/synth.py into the reference modules with strict=True,
 (3) executes the reference on seeded inputs at every seam of SURVEY.md 8(b-2) and for the
 whole forward, and (4) stores inputs-by-seed + reference outputs as small fixtures.
 It also prints the oracle-vs-reference deviation so the restatement is checked at
@@ -17,7 +17,7 @@ import torch
 
 from oracle import dir_oracle as O
 from oracle.ref_shims import load_reference
-from oracle.synth_weights import fingerprint, make_state_dict
+from oracle.synth import fingerprint, make_state_dict
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
 warnings.filterwarnings("ignore")
@@ -73,7 +73,7 @@ def eval_metric_inputs():
     cam = torch.tensor([[1400.0, 0, 128.0], [0, 1400.0, 128.0], [0, 0, 1.0]]).repeat(B, 1, 1)
     gv2d = {s: rnd(44 + i, B, 778, 2, scale=30.0) + 128 for i, s in enumerate(("left", "right"))}
     off = rnd(46, B, 3, scale=0.5)
-    jreg16 = {s: torch.from_numpy(__import__("dir_b200.synth", fromlist=["mano_buffers"]).mano_buffers(s)["th_J_regressor"])
+    jreg16 = {s: torch.from_numpy(__import__("oracle.synth", fromlist=["mano_buffers"]).mano_buffers(s)["th_J_regressor"])
               for s in ("left", "right")}
     return {"gt_verts": gv, "pred_verts": pv, "cam": cam, "gt_verts2d": gv2d, "pred_offset": off, "jreg16": jreg16}
 

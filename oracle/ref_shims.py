@@ -85,7 +85,7 @@ def _install_stub_modules():
 
 
 def _fake_ready_arguments(path, *_a, **_k):
-    from oracle.synthetic_mano import make_mano_arrays
+    from oracle.synth import make_mano_arrays
 
     side = "left" if "LEFT" in str(path).upper() else "right"
     a = make_mano_arrays(side)

@@ -120,7 +120,7 @@ def mano_buffers(side: str) -> dict:
 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-KEYS_JSON = os.path.join(_HERE, "state_dict_keys.json")
+KEYS_JSON = os.path.join(os.path.dirname(_HERE), "dir_b200", "state_dict_keys.json")  # shipped with the product module
 
 
 def load_key_shapes(path: str = KEYS_JSON) -> dict:

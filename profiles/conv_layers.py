@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 import dir_b200  # noqa: E402
-from dir_b200.synth import make_state_dict  # noqa: E402
+from oracle.synth import make_state_dict  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=128)

@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import dir_b200  # noqa: E402
-from dir_b200.synth import make_state_dict  # noqa: E402
+from oracle.synth import make_state_dict  # noqa: E402
 
 precision = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 net = dir_b200.DIR(21, "./misc/mano", precision=precision, max_batch=4).cuda()

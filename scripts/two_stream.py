@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import dir_b200
-from dir_b200.synth import make_state_dict
+from oracle.synth import make_state_dict
 
 dev = torch.device("cuda:0")
 net = dir_b200.DIR(21, "./misc/mano", precision="bf16", aux_outputs=True, max_batch=128).to(dev)

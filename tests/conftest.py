@@ -14,8 +14,8 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def synth_sd():
-    """Synthetic fp32 state_dict with the reference's 963 keys (oracle/synth_weights.py)."""
-    from oracle.synth_weights import make_state_dict
+    """Synthetic fp32 state_dict with the reference's 963 keys (oracle/synth.py)."""
+    from oracle.synth import make_state_dict
 
     return make_state_dict(0)
 

@@ -14,7 +14,8 @@ import pytest
 import scipy.sparse as sp
 import torch
 
-from dir_b200 import assets, synth
+from dir_b200 import assets
+from oracle import synth
 
 
 def _write_mano_pickles(root, same_shapedirs_x=False):

@@ -13,7 +13,7 @@ def _worker(rank, world, port, q):
 
     import dir_b200
     from dir_b200.dist import forward_sharded, init_nccl
-    from dir_b200.synth import make_state_dict
+    from oracle.synth import make_state_dict
 
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,

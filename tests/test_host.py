@@ -77,7 +77,7 @@ def test_module_contract(golden_dir):
     with pytest.raises(NotImplementedError):
         m({"img": torch.zeros(1, 3, 256, 256)}, None, None)
     # strict load of a synthetic checkpoint, like apps/eval.py:107-108
-    from dir_b200.synth import make_state_dict
+    from oracle.synth import make_state_dict
 
     res = m.load_state_dict(make_state_dict(0, prefix="decoder.projecter_4.interaction."), strict=False)
     assert len(res.unexpected_keys) == 0
