@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DIRB200_LIB") or os.path.join(_HERE, "libdirb200.so")  # override: A/B of builds
 
-PRECISION = {"fp32": 0, "bf16": 1}
+PRECISION = {"fp32": 0, "bf16": 1, "tf32": 2}
 DTYPE_F32, DTYPE_I64 = 0, 1
 STAGE_FLOATS = 4887
 RECORD_FLOATS = 3 * STAGE_FLOATS

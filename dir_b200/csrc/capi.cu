@@ -31,7 +31,8 @@ extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
     g_create_err = "null argument";
     return DIRB200_E_INVALID;
   }
-  if (cfg->precision != DIRB200_PRECISION_FP32 && cfg->precision != DIRB200_PRECISION_BF16) {
+  if (cfg->precision != DIRB200_PRECISION_FP32 && cfg->precision != DIRB200_PRECISION_BF16 &&
+      cfg->precision != DIRB200_PRECISION_TF32) {
     g_create_err = "unknown precision";
     return DIRB200_E_INVALID;
   }
@@ -62,6 +63,8 @@ extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
   {
     const char* dis = getenv("DIRB200_DISABLE_TC");
     h->e.disable_tc = dis && dis[0] == '1';
+    const char* f32s = getenv("DIRB200_FP32_SIMT");
+    h->e.fp32_simt = f32s && f32s[0] == '1';
     const char* nopair = getenv("DIRB200_NO_PAIR_FUSION");
     h->e.disable_pair_fusion = nopair && nopair[0] == '1';
     const char* dense = getenv("DIRB200_DENSE_FUSION");
@@ -471,9 +474,14 @@ extern "C" int dirb200_nccl_init(dirb200_handle* h, const char id[128], int rank
   cudaSetDevice(e.cfg.device);
   NcclId nid;
   memcpy(nid.internal, id, 128);
+  if (e.nccl_comm) {  // re-initialisation: the previous communicator is released first
+    g_nccl.destroy(e.nccl_comm);
+    e.nccl_comm = nullptr;
+  }
   void* comm = nullptr;
   if (g_nccl.init_rank(&comm, world, nid, rank) != 0) return fail(e, DIRB200_E_CUDA, "ncclCommInitRank failed");
   e.nccl_comm = comm;
+  e.nccl_destroy = [](void* c) { g_nccl.destroy(c); };
   return DIRB200_OK;
 }
 

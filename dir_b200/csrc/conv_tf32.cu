@@ -1,0 +1,432 @@
+// fp32-grade implicit-GEMM convolution on the tcgen05 tensor cores (precision = fp32): error-compensated 3xTF32 with
+// the accumulation promoted to round-to-nearest fp32 registers every few MMAs. NHWC fp32 activations, weights
+// [Cout][(ky,kx,ci)] pre-split into tf32 hi / lo parts at finalize. Replaces conv_simt.cu for every tensor-core shaped
+// layer of the parity configuration (models/backbone/resnet.py:120-140, models/backbone/hourglass.py:55-70,
+// models/dir.py:57-62,227-241,404-420).
+//
+// Why it is built this way (measured on B200, profiles/mma_probe_r2.txt):
+//  * kind::tf32 TRUNCATES its fp32 operands to 10 mantissa bits, so the hardware itself forms A_hi = trunc(A) from the
+//    raw activation tile; only A_lo = rn_tf32(A - trunc(A)) has to be produced in software (an elementwise pass over
+//    the 16 KB tile by four "splitter" warps, position for position, so the 128B swizzle never has to be decoded).
+//  * D += A_hi*W_hi is accumulated in one TMEM buffer, the 2^-11-sized cross terms A_lo*W_hi + A_hi*W_lo in another
+//    (their rounding is negligible); A_lo*W_lo (2^-22) is dropped.
+//  * the TMEM accumulator rounds TOWARD ZERO on every MMA: a biased 2^-24 relative loss per instruction, which over the
+//    2304 k-steps of the 18432-deep attention convolution would reach 1e-4. The main accumulator is therefore drained
+//    every CHUNK_KB k-blocks (8 MMAs) into fp32 registers of the epilogue warps with ordinary round-to-nearest adds
+//    while the MMA warp continues into the other TMEM buffer (ping-pong), bounding the bias at ~4e-7.
+// Roles per CTA (320 threads, persistent over tiles of 128 pixels x BN channels, k-block = 32 channels of one tap):
+//   warp 0    TMA producer: A box {32 ch, wbox*s, hbox*s, nbox} (im2col, padding and stride are TMA coordinates),
+//             W_hi and W_lo boxes {32 k, BN rows}; `stages`-deep mbarrier ring
+//   warp 1    TMEM allocation (4 x BN columns) + single-thread tcgen05.mma.kind::tf32 issue (12 MMAs per k-block)
+//   warps 2-5 splitter: A_lo tile of each stage
+//   warps 6-9 accumulate/epilogue: tcgen05.ld of each finished chunk -> += registers; at the end of the tile add the
+//             cross-term accumulator, apply scale/shift (+residual) (+ReLU) and store fp32 rows
+// nsplit = 1 runs the same pipeline as plain TF32 (one MMA per k-step, what PyTorch's cuDNN default does on this GPU).
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <tuple>
+
+#include "common.cuh"
+#include "engine.h"
+#include "tc_common.cuh"
+#include "tma_host.h"
+
+namespace dirb200 {
+
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int KB = 32;          // channels per k-block: one 128-byte fp32 row = one swizzle atom
+constexpr int NUM_THREADS = 320;
+constexpr int MAX_STAGES = 4;
+constexpr int CHUNK_KB = 2;     // k-blocks accumulated in TMEM before promotion (2 x 4 k-steps = 8 MMAs)
+constexpr int A_TILE = BM * 128;
+
+struct T32Args {
+  const float* scale;
+  const float* shift;
+  const float* res;  // optional residual [M][Cout]
+  float* y;          // [M][Cout]
+  int M, Cout, Ho, Wo;
+  int stride, pad, kw;
+  int taps, cblocks;  // K loop = taps * cblocks k-blocks
+  int relu;
+  int m_tiles, n_tiles, stages, raster_m;
+  int nsplit;  // 3: error-compensated 3xTF32, 1: plain TF32
+};
+
+template <int BN>
+struct Cfg32 {
+  static constexpr int B_TILE = BN * 128;
+  static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;  // A, A_lo, W_hi, W_lo
+  static constexpr uint32_t TMEM_COLS = 4 * BN;                // main[2] (ping-pong per chunk) + cross[2] (per tile)
+  static int stages() {
+    int s = (220 * 1024) / STAGE_BYTES;
+    return s > MAX_STAGES ? MAX_STAGES : s;
+  }
+  static int smem_bytes(int stages) { return 1024 + stages * STAGE_BYTES + 256; }
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                 const __grid_constant__ CUtensorMap tmBlo, const T32Args a) {
+  using Cfg = Cfg32<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stages = a.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                      // TMA bytes of a stage have landed
+  uint64_t* empty_bar = bars + MAX_STAGES;        // the MMAs reading a stage have completed
+  uint64_t* split_bar = bars + 2 * MAX_STAGES;    // A_lo of a stage is written (128 arrivals)
+  uint64_t* main_full = bars + 3 * MAX_STAGES;    // [2] a chunk's accumulator is complete
+  uint64_t* main_empty = main_full + 2;           // [2] ... and has been drained (128 arrivals)
+  uint64_t* cross_empty = main_empty + 2;         // [2] the tile's cross-term accumulator has been drained
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(cross_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = a.m_tiles * a.n_tiles;
+  const int nkb = a.taps * a.cblocks;
+  const bool comp = a.nsplit == 3;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmBhi);
+    tma_prefetch_desc(&tmBlo);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&split_bar[s], 128);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&main_full[i], 1);
+      mbar_init(&main_empty[i], 128);
+      mbar_init(&cross_empty[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_ptr_smem)),
+                 "r"(Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // everything above overlaps the previous kernel's tail
+
+  auto stage_A = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
+  auto stage_Alo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + A_TILE; };
+  auto stage_Bhi = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 2 * A_TILE; };
+  auto stage_Blo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 2 * A_TILE + Cfg::B_TILE; };
+  auto tile_m0 = [&](int tile) { return (a.raster_m ? tile % a.m_tiles : tile / a.n_tiles) * BM; };
+  auto tile_n0 = [&](int tile) { return (a.raster_m ? tile / a.m_tiles : tile % a.n_tiles) * BN; };
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===================== TMA producer
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx = A_TILE + Cfg::B_TILE * (comp ? 2 : 1);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = tile_m0(tile), n0 = tile_n0(tile);
+        const int wo0 = m0 % a.Wo;
+        const int ho0 = (m0 / a.Wo) % a.Ho;
+        const int b0 = m0 / (a.Wo * a.Ho);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], tx);
+          const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
+          const int ky = tap / a.kw, kx = tap - ky * a.kw;
+          tma_load_4d(&tmA, &full_bar[s], stage_A(s), cb * KB, wo0 * a.stride + kx - a.pad, ho0 * a.stride + ky - a.pad,
+                      b0);
+          tma_load_2d(&tmBhi, &full_bar[s], stage_Bhi(s), kb * KB, n0);
+          if (comp) tma_load_2d(&tmBlo, &full_bar[s], stage_Blo(s), kb * KB, n0);
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===================== MMA issuer
+      constexpr uint32_t ID = idesc(BN, 2u);
+      int s = 0;
+      uint32_t ph = 0, g = 0, t = 0;  // g: running chunk counter (main ping-pong), t: running tile counter (cross)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const uint32_t d_cross = tmem_base + (2 + (t & 1)) * BN;
+        if (comp) {
+          mbar_wait(&cross_empty[t & 1], ((t >> 1) & 1) ^ 1);
+          fence_after();
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int kc = kb % CHUNK_KB;
+          if (kc == 0) {  // a new chunk: its accumulator buffer must have been drained
+            mbar_wait(&main_empty[g & 1], ((g >> 1) & 1) ^ 1);
+            fence_after();
+          }
+          const uint32_t d_main = tmem_base + (g & 1) * BN;
+          mbar_wait(&full_bar[s], ph);
+          if (comp) mbar_wait(&split_bar[s], ph);
+          fence_after();
+          const uint64_t dA = desc128(s32(stage_A(s))), dAlo = desc128(s32(stage_Alo(s)));
+          const uint64_t dBhi = desc128(s32(stage_Bhi(s))), dBlo = desc128(s32(stage_Blo(s)));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // +32 B per K=8 step inside the swizzle atom
+            umma_tf32(d_main, dA + 2 * k, dBhi + 2 * k, ID, (kc | k) ? 1u : 0u);
+            if (comp) {
+              umma_tf32(d_cross, dAlo + 2 * k, dBhi + 2 * k, ID, (kb | k) ? 1u : 0u);
+              umma_tf32(d_cross, dA + 2 * k, dBlo + 2 * k, ID, 1u);
+            }
+          }
+          umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have consumed it
+          if (kc == CHUNK_KB - 1 || kb == nkb - 1) {
+            umma_commit(&main_full[g & 1]);  // chunk complete (the tile's last one also covers the cross terms)
+            ++g;
+          }
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== splitter: A_lo[i] = rn_tf32(A[i] - trunc_tf32(A[i])), same byte position in its own tile
+    if (comp) {
+      const int tid = threadIdx.x - 64;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          const uint4* src = reinterpret_cast<const uint4*>(stage_A(s));
+          uint4* dst = reinterpret_cast<uint4*>(stage_Alo(s));
+#pragma unroll
+          for (int i = 0; i < A_TILE / 16 / 128; ++i) {
+            uint4 v = src[tid + i * 128];
+            uint32_t* e = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float x = __uint_as_float(e[j]);
+              const float lo = x - __uint_as_float(e[j] & 0xFFFFE000u);  // exact; the MMA truncates x the same way
+              e[j] = (__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u;      // round to tf32 (the MMA would truncate)
+            }
+            dst[tid + i * 128] = v;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+          mbar_arrive(&split_bar[s]);
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== accumulate + epilogue (warp w may touch TMEM lanes 32*(w%4) .. +31)
+    const int lane_base = (warp & 3) * 32;
+    const uint32_t lane_addr = (uint32_t)lane_base << 16;
+    const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+    uint32_t g = 0, t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const int m0 = tile_m0(tile), n0 = tile_n0(tile);
+      float acc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      for (int c = 0; c < nchunks; ++c, ++g) {
+        mbar_wait(&main_full[g & 1], (g >> 1) & 1);
+        fence_after();
+        const uint32_t taddr = tmem_base + lane_addr + (g & 1) * BN;
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          float v[32];
+          tmem_ld32(taddr + j * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+        }
+        fence_before();
+        mbar_arrive(&main_empty[g & 1]);
+      }
+      if (comp) {  // the last chunk's commit covered every MMA of the tile, cross terms included
+        const uint32_t taddr = tmem_base + lane_addr + (2 + (t & 1)) * BN;
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          float v[32];
+          tmem_ld32(taddr + j * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+        }
+        fence_before();
+        mbar_arrive(&cross_empty[t & 1]);
+      }
+      const int m = m0 + lane_base + lane;
+      if (m < a.M) {
+        float* yrow = a.y + (size_t)m * a.Cout + n0;
+        const float* rrow = a.res ? a.res + (size_t)m * a.Cout + n0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < BN; j += 4) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + n0 + j));
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + n0 + j));
+          float4 o;
+          o.x = fmaf(acc[j + 0], sc.x, sh.x);
+          o.y = fmaf(acc[j + 1], sc.y, sh.y);
+          o.z = fmaf(acc[j + 2], sc.z, sh.z);
+          o.w = fmaf(acc[j + 3], sc.w, sh.w);
+          if (rrow) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + j));
+            o.x += r.x;
+            o.y += r.y;
+            o.z += r.z;
+            o.w += r.w;
+          }
+          if (a.relu) {
+            o.x = fmaxf(o.x, 0.f);
+            o.y = fmaxf(o.y, 0.f);
+            o.z = fmaxf(o.z, 0.f);
+            o.w = fmaxf(o.w, 0.f);
+          }
+          *reinterpret_cast<float4*>(yrow + j) = o;
+        }
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+}
+
+// w [n] -> hi = rn_tf32(w), lo = rn_tf32(w - hi)   (round-to-nearest-even on the 13 dropped mantissa bits)
+__device__ __forceinline__ float rn_tf32(float x) {
+  const uint32_t b = __float_as_uint(x);
+  return __uint_as_float((b + 0xFFFu + ((b >> 13) & 1u)) & 0xFFFFE000u);
+}
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = w[i];
+  const float h = rn_tf32(x);
+  hi[i] = h;
+  lo[i] = rn_tf32(x - h);
+}
+
+int pick_bn32(int Cout) { return Cout % 128 == 0 ? 128 : 64; }
+
+bool act_map32_cached(const float* x, int B, int H, int W, int C, int stride, const tma::Boxes& bx, const char* name,
+                      CUtensorMap* out) {
+  typedef std::tuple<const void*, int, int, int, int, int, int, int, int> Key;
+  static thread_local tma::MapCache<Key> cache;
+  Key key(x, B, H, W, C, stride, bx.wbox, bx.hbox, bx.nbox);
+  if (cache.find(key, out)) return true;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)(bx.wbox * stride), (cuuint32_t)(bx.hbox * stride), (cuuint32_t)bx.nbox};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = tma::get_encode()(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "dirb200: cuTensorMapEncodeTiled(fp32 A) failed: %d (layer %s)\n", (int)r, name);
+    return false;
+  }
+  cache.put(key, *out);
+  return true;
+}
+
+template <int BN>
+int launch_t32(const CUtensorMap& tmA, const ConvLayer& L, T32Args a, cudaStream_t st) {
+  using Cfg = Cfg32<BN>;
+  a.stages = Cfg::stages();
+  const int smem = Cfg::smem_bytes(a.stages);
+  if (ensure_dynamic_smem(reinterpret_cast<const void*>(conv_tf32_kernel<BN>), smem) != cudaSuccess) return DIRB200_E_CUDA;
+  const int tiles = a.m_tiles * a.n_tiles;
+  const int grid = tiles < tma::num_sms() ? tiles : tma::num_sms();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  if (cudaLaunchKernelEx(&cfg, conv_tf32_kernel<BN>, tmA, L.wmap32hi, L.wmap32lo, a) != cudaSuccess) return DIRB200_E_CUDA;
+  return DIRB200_OK;
+}
+
+}  // namespace
+
+bool conv_tf32_supported(const ConvLayer& L, int B, int H, int W) {
+  if (!L.w32hi || L.wmap32_bn == 0 || !tma::get_encode()) return false;
+  if (L.Cin % KB != 0 || L.Cout % 64 != 0 || L.K != L.Kpad) return false;
+  if (L.stride != 1 && L.stride != 2) return false;
+  const int Ho = (H + 2 * L.pad - L.kh) / L.stride + 1, Wo = (W + 2 * L.pad - L.kw) / L.stride + 1;
+  if (!tma::is_pow2(Ho) || !tma::is_pow2(Wo)) return false;
+  if (Wo > BM && Wo % BM != 0) return false;
+  return true;
+}
+
+// Splits L.w32 into the tf32 hi / lo copies (caller-allocated, Cout*Kpad floats each) and builds their tensor maps.
+int conv_tf32_prepare_weights(ConvLayer& L, float* hi, float* lo, cudaStream_t st) {
+  L.wmap32_bn = 0;
+  L.w32hi = L.w32lo = nullptr;
+  tma::EncodeTiledFn enc = tma::get_encode();
+  if (!enc || !L.w32 || !hi || !lo || L.Cin % KB != 0 || L.Cout % 64 != 0 || L.K != L.Kpad) return 0;
+  const int64_t n = (int64_t)L.Cout * L.Kpad;
+  split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L.w32, hi, lo, n);
+  const int bn = pick_bn32(L.Cout);
+  cuuint64_t dims[2] = {(cuuint64_t)L.Kpad, (cuuint64_t)L.Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)L.Kpad * 4};
+  cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)bn};
+  cuuint32_t es[2] = {1, 1};
+  for (int i = 0; i < 2; ++i) {
+    CUresult r = enc(i ? &L.wmap32lo : &L.wmap32hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, i ? lo : hi, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return DIRB200_E_CUDA;
+  }
+  L.w32hi = hi;
+  L.w32lo = lo;
+  L.wmap32_bn = bn;
+  return DIRB200_OK;
+}
+
+int launch_conv_tf32(const ConvLayer& L, const float* x, float* y, const float* res, int B, int H, int W, int nsplit,
+                     cudaStream_t st) {
+  const int Ho = (H + 2 * L.pad - L.kh) / L.stride + 1, Wo = (W + 2 * L.pad - L.kw) / L.stride + 1;
+  const tma::Boxes bx = tma::pick_boxes(Ho, Wo, BM);
+  CUtensorMap tmA;
+  if (!act_map32_cached(x, B, H, W, L.Cin, L.stride, bx, L.name.c_str(), &tmA)) return DIRB200_E_CUDA;
+  T32Args a{};
+  a.scale = L.scale;
+  a.shift = L.shift;
+  a.res = res;
+  a.y = y;
+  a.M = B * Ho * Wo;
+  a.Cout = L.Cout;
+  a.Ho = Ho;
+  a.Wo = Wo;
+  a.stride = L.stride;
+  a.pad = L.pad;
+  a.kw = L.kw;
+  a.taps = L.kh * L.kw;
+  a.cblocks = L.Cin / KB;
+  a.relu = L.relu;
+  a.m_tiles = (a.M + BM - 1) / BM;
+  a.n_tiles = L.Cout / L.wmap32_bn;
+  a.raster_m = (double)L.Cout * L.K > (double)B * H * W * L.Cin ? 1 : 0;
+  a.nsplit = nsplit == 1 ? 1 : 3;
+  return L.wmap32_bn == 128 ? launch_t32<128>(tmA, L, a, st) : launch_t32<64>(tmA, L, a, st);
+}
+
+}  // namespace dirb200

@@ -44,6 +44,7 @@ bool pdl_enabled() {
   } while (0)
 
 Engine::~Engine() {
+  if (nccl_comm && nccl_destroy) nccl_destroy(nccl_comm);
   if (side) cudaStreamDestroy(side);
   for (int i = 0; i < 2; ++i) {
     if (ev_fork[i]) cudaEventDestroy(ev_fork[i]);
@@ -181,7 +182,17 @@ ConvLayer Engine::make_conv(const std::string& wname, const std::string& bias, c
   if (L.w32) launch_pack_conv_weight(w, L.w32, L.w16, L.Cout, L.Cin, L.kh, L.kw, L.Kpad, fin_stream);
   fold(bias, bn, &L.scale, &L.shift, L.Cout);
   if (bf16() && L.w16 && err.empty()) conv_tc_prepare_weights(L);
+  if (!bf16() && err.empty()) prepare_tf32(L);
   return L;
+}
+
+// fp32 / tf32 configurations: tf32 hi/lo copies of the packed weights for conv_tf32.cu (tensor-core shaped layers only)
+void Engine::prepare_tf32(ConvLayer& L) {
+  if (dry || !L.w32 || L.Cin % 32 != 0 || L.Cout % 64 != 0 || L.K != L.Kpad) return;
+  if (L.Cin == 2560) return;  // fusion.0 runs in its exact factored form (fusion.cu), never as a dense conv
+  float* hi = dalloc((size_t)L.Cout * L.Kpad);
+  float* lo = dalloc((size_t)L.Cout * L.Kpad);
+  if (hi && lo) conv_tf32_prepare_weights(L, hi, lo, fin_stream);
 }
 
 void Engine::make_dual(ConvLayer& F, const ConvLayer& main, const ConvLayer& second) {
@@ -358,6 +369,7 @@ static ConvLayer concat_convs(Engine& e, const std::string& w0, const std::strin
   e.fold(b0, bn0, &L.scale, &L.shift, half, 0, L.Cout);
   e.fold(b1, bn1, &L.scale, &L.shift, half, half, L.Cout);
   if (e.bf16() && L.w16 && e.err.empty()) conv_tc_prepare_weights(L);
+  if (!e.bf16() && e.err.empty()) e.prepare_tf32(L);
   return L;
 }
 
@@ -498,7 +510,19 @@ void Engine::conv(const ConvLayer& L, const T* x, T* y, const T* resid, int B, i
                              (double)L.Cout * L.K);
     pr->layer = &L;
     pr->tc = (sizeof(T) == 2 && !in_nchw && !disable_tc && conv_tc_supported(L, B, H, W_)) ? 1 : 0;
+    if (sizeof(T) == 4 && !in_nchw && !fp32_simt && conv_tf32_supported(L, B, H, W_)) pr->tc = 1;
     cudaEventRecord(pr->a, st);
+  }
+  if (sizeof(T) == 4 && !in_nchw && !fp32_simt && conv_tf32_supported(L, B, H, W_)) {
+    int rc = launch_conv_tf32(L, reinterpret_cast<const float*>(x), reinterpret_cast<float*>(y),
+                              reinterpret_cast<const float*>(resid), B, H, W_, tf32_nsplit(), st);
+    if (rc && !sticky_rc) {
+      sticky_rc = rc;
+      err = "tcgen05 tf32 conv launch failed for " + L.name;
+    }
+    ++tc_launches;
+    if (pr) cudaEventRecord(pr->b, st);
+    return;
   }
   if (sizeof(T) == 2 && !in_nchw && !disable_tc && conv_tc_supported(L, B, H, W_)) {
     int rc = launch_conv_tc(L, reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
@@ -920,10 +944,18 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   }
   T* c2_skip = run_residual<T>(skip3, c2, act3, B, 32, 32, ar, st3);
   if (overlap) cudaEventRecord(ev_join[0], side);
+  // an early return must not leave work of this forward running on the side stream behind the caller's back
+  auto bail = [&](int code) {
+    if (side && !no_overlap && !plan) {
+      cudaEventRecord(ev_join[0], side);
+      cudaStreamWaitEvent(st, ev_join[0], 0);
+    }
+    return code;
+  };
   T* img_feat1 = nullptr;
   rc = run_stage<T>(0, fusion4, rec, RS, para, PS, B, plan ? nullptr : rec + DIRB200_STAGE_FLOATS, RS,
                     plan ? nullptr : para + 128, PS, &img_feat1, nullptr, nullptr, ar, st);
-  if (rc) return rc;
+  if (rc) return bail(rc);
   // enhance_layer{4,3}: the block input cat(fusion, img_feat) is only pre-activated (act); its raw copy is never
   // written: the skip half of the pair GEMM reads the two sources directly (third A operand of conv_tc_kernel)
   auto enhance = [&](const ResidualBlock& r, const T* a0, const T* a1, int S) -> T* {
@@ -951,7 +983,7 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   rc = run_stage<T>(1, fusion3, plan ? nullptr : rec + DIRB200_STAGE_FLOATS, RS, plan ? nullptr : para + 128, PS, B,
                     plan ? nullptr : rec + 2 * DIRB200_STAGE_FLOATS, RS, plan ? nullptr : para + 256, PS, &img_feat2,
                     nullptr, (aux && !plan) ? o->proj_feat : nullptr, ar, st);
-  if (rc) return rc;
+  if (rc) return bail(rc);
   if (aux) {  // models/dir.py:470-476: only the seg/dense heads consume enhance_layer3
     const ResidualBlock& enh3 = res["decoder.enhance_layer3."];
     T* enhance3 = enhance(enh3, fusion3, img_feat2, 32);
@@ -968,10 +1000,10 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
     }
   }
   if (plan) return DIRB200_OK;
-  if (ar.overflow) return DIRB200_E_WORKSPACE;
+  if (ar.overflow) return bail(DIRB200_E_WORKSPACE);
   if (aux && side && !no_overlap) cudaStreamWaitEvent(st, ev_join[1], 0);  // proj_feat rasteriser (run_stage)
   last_forward_launches = launches;
-  if (sticky_rc) return sticky_rc;
+  if (sticky_rc) return bail(sticky_rc);
   CK(cudaPeekAtLastError());
   return DIRB200_OK;
 }

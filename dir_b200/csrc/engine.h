@@ -35,6 +35,11 @@ struct ConvLayer {
   int wmap_bn = 0;   // rows per weight box (0: no tensor map)
   CUtensorMap wmap2;  // same weights with wmap_bn/2-row boxes: operand halves of the 2-CTA (cta_group::2) kernel
   bool wmap2_ok = false;
+  // fp32 / tf32 configurations (conv_tf32.cu): the weights split into tf32 hi + lo parts, fp32 [Cout][Kpad] each
+  float* w32hi = nullptr;
+  float* w32lo = nullptr;
+  CUtensorMap wmap32hi, wmap32lo;  // box 32(k) x wmap32_bn rows, 128B swizzle
+  int wmap32_bn = 0;               // rows per weight box (0: no tensor-core path for this layer)
   int tc_bn_cap = 256;   // largest n-tile the tensor-core path may pick (128 for layers that add a residual)
   bool tc_stem = false;  // 7x7/s2/Cin=3 stem packed for the tensor-core stem variant
 };
@@ -116,8 +121,10 @@ struct Engine {
   bool dense_fusion = false;  // DIRB200_DENSE_FUSION=1: materialise bone_proj and run the dense 2560-ch conv
   bool disable_pair_fusion = false;  // DIRB200_NO_PAIR_FUSION=1: keep conv3 and skip/downsample as separate launches
   bool disable_tc = false;  // DIRB200_DISABLE_TC=1: force the CUDA-core conv in bf16 mode (debug A/B)
+  bool fp32_simt = false;   // DIRB200_FP32_SIMT=1: fp32 configuration on the CUDA-core conv (the round-1 path; debug A/B)
   const ConvLayer* find_conv(const std::string& weight_key) const;
   void* nccl_comm = nullptr;
+  void (*nccl_destroy)(void*) = nullptr;  // set with nccl_comm (capi.cu binds NCCL at run time)
   const unsigned char* img_u8 = nullptr;  // set by forward_u8: raw uint8 HWC BGR frames instead of the fp32 image
   // timing hook (bench.py roofline): CUDA events around every conv launch whose name starts with prof_prefix
   struct ProfRec {
@@ -146,6 +153,7 @@ struct Engine {
 
   ~Engine();
   bool bf16() const { return cfg.precision == DIRB200_PRECISION_BF16; }
+  int tf32_nsplit() const { return cfg.precision == DIRB200_PRECISION_TF32 ? 1 : 3; }  // MMAs per k-step, conv_tf32.cu
   size_t esize() const { return bf16() ? 2 : 4; }
 
   // finalize helpers
@@ -160,6 +168,7 @@ struct Engine {
   ConvLayer make_conv(const std::string& wname, const std::string& bias, const std::string& bn, int stride, int pad,
                       int relu);
   void fuse_post_bn(ConvLayer& c, const std::string& conv_bias, const std::string& bn);
+  void prepare_tf32(ConvLayer& L);
   PointMlp make_mlp(const std::string& prefix, int cin, int cmid, int cout);
   ResidualBlock make_residual(const std::string& prefix);
   ManoWeights make_mano(const std::string& prefix, bool left);
@@ -193,6 +202,11 @@ struct Engine {
   int forward(const float* img, int B, Arena& ar, const dirb200_outputs* out, cudaStream_t st);
 };
 
+// fp32-grade tensor-core conv (conv_tf32.cu): 3xTF32 with chunked round-to-nearest accumulation (nsplit 3) or plain TF32
+bool conv_tf32_supported(const ConvLayer& L, int B, int H, int W);
+int conv_tf32_prepare_weights(ConvLayer& L, float* hi, float* lo, cudaStream_t st);  // splits L.w32, builds the maps
+int launch_conv_tf32(const ConvLayer& L, const float* x, float* y, const float* res, int B, int H, int W, int nsplit,
+                     cudaStream_t st);
 // tensor-core conv (conv_tc.cu). Returns false if the shape is not supported (caller falls back to CUDA cores).
 bool conv_tc_supported(const ConvLayer& L, int B, int H, int W);
 int conv_tc_prepare_weights(ConvLayer& L);  // builds L.wmap

@@ -32,8 +32,11 @@ extern "C" {
 #define DIRB200_E_MISSING (-4)   /* finalize: a required state_dict key was never set */
 #define DIRB200_E_WORKSPACE (-5) /* workspace too small */
 
-#define DIRB200_PRECISION_FP32 0 /* fp32 activations + fp32 CUDA-core contractions (parity config) */
+#define DIRB200_PRECISION_FP32 0 /* parity config: fp32 activations; convs on tcgen05 as error-compensated 3xTF32 with
+                                    round-to-nearest fp32 accumulation (<= the error of an fp32 cuDNN/MKL conv) */
 #define DIRB200_PRECISION_BF16 1 /* bf16 feature maps, tcgen05 bf16 MMA with fp32 accumulate; joint space fp32 */
+#define DIRB200_PRECISION_TF32 2 /* fp32 activations, plain TF32 tcgen05 convs: the arithmetic PyTorch's cuDNN default
+                                    (torch.backends.cudnn.allow_tf32 = True) gives the reference on this GPU */
 
 #define DIRB200_DTYPE_F32 0
 #define DIRB200_DTYPE_I64 1
