@@ -372,6 +372,146 @@ extern "C" int dirb200_bone_proj(dirb200_handle* h, const float* uv, const float
   return DIRB200_OK;
 }
 
+// ---- seams of the joint space: ImgFeature2JointFeature, ResSimplePGCN, STE, RegressorOffset.
+// Inputs arrive in the reference's own tensor layouts and are packed into the record / token layouts the kernels read.
+static void scatter_rows(float* dst, int dst_stride, int dst_off, const float* src, int n, int B, cudaStream_t st) {
+  cudaMemcpy2DAsync(dst + dst_off, (size_t)dst_stride * 4, src, (size_t)n * 4, (size_t)n * 4, B, cudaMemcpyDeviceToDevice,
+                    st);
+}
+
+template <typename T>
+static int seam_img2joint(Engine& e, int s, const float* img_feat, const float* uv_l, const float* uv_r, int B, float* out_l,
+                          float* out_r, Arena& ar, cudaStream_t st) {
+  const StageWeights& sw = e.stage[s];
+  const int S = sw.S;
+  T* x = reinterpret_cast<T*>(ar.alloc((size_t)B * S * S * 256 * sizeof(T)));
+  float* rec = reinterpret_cast<float*>(ar.alloc((size_t)B * DIRB200_STAGE_FLOATS * 4));
+  float* out = reinterpret_cast<float*>(ar.alloc((size_t)B * 42 * 128 * 4));
+  if (ar.overflow) return DIRB200_E_WORKSPACE;
+  launch_nchw_to_nhwc<T>(img_feat, x, B, 256, S, S, st);
+  cudaMemsetAsync(rec, 0, (size_t)B * DIRB200_STAGE_FLOATS * 4, st);
+  scatter_rows(rec, DIRB200_STAGE_FLOATS, DIRB200_OFF_UV_L, uv_l, 42, B, st);
+  scatter_rows(rec, DIRB200_STAGE_FLOATS, DIRB200_OFF_UV_R, uv_r, 42, B, st);
+  EmbedArgs a{};
+  a.feat = x;
+  a.S = S;
+  a.prev_record = rec;
+  a.rec_stride = DIRB200_STAGE_FLOATS;
+  for (int h = 0; h < 2; ++h) {
+    a.filters[h] = sw.filters[h];
+    a.pos[h] = sw.pos[h];
+  }
+  a.out = out;
+  a.B = B;
+  a.skip_pos = 1;
+  launch_joint_embed<T>(a, st);
+  cudaMemcpy2DAsync(out_l, 21 * 128 * 4, out, 42 * 128 * 4, 21 * 128 * 4, B, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpy2DAsync(out_r, 21 * 128 * 4, out + 21 * 128, 42 * 128 * 4, 21 * 128 * 4, B, cudaMemcpyDeviceToDevice, st);
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_img2joint(dirb200_handle* h, int stage, const float* img_feat, const float* uv_left,
+                                 const float* uv_right, int batch, float* out_left, float* out_right, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  H_CHECK(h);
+  if (!e.finalized) return fail(e, DIRB200_E_STATE, "finalize_weights first");
+  if (stage < 1 || stage > 2 || !img_feat || !uv_left || !uv_right || !out_left || !out_right || batch <= 0)
+    return fail(e, DIRB200_E_INVALID, "bad img2joint argument");
+  Arena ar;
+  ar.base = reinterpret_cast<char*>(workspace);
+  ar.size = workspace_bytes;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = e.bf16() ? seam_img2joint<__nv_bfloat16>(e, stage - 1, img_feat, uv_left, uv_right, batch, out_left, out_right,
+                                                    ar, st)
+                    : seam_img2joint<float>(e, stage - 1, img_feat, uv_left, uv_right, batch, out_left, out_right, ar, st);
+  if (rc == DIRB200_E_WORKSPACE) e.err = "workspace too small";
+  return rc;
+}
+
+extern "C" int dirb200_gcn(dirb200_handle* h, int stage, const float* x_left, const float* x_right, int batch,
+                           float* y_left, float* y_right, void* workspace, size_t workspace_bytes, void* stream) {
+  H_CHECK(h);
+  if (!e.finalized) return fail(e, DIRB200_E_STATE, "finalize_weights first");
+  if (stage < 1 || stage > 2 || !x_left || !x_right || !y_left || !y_right || batch <= 0)
+    return fail(e, DIRB200_E_INVALID, "bad gcn argument");
+  Arena ar;
+  ar.base = reinterpret_cast<char*>(workspace);
+  ar.size = workspace_bytes;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t tok = (size_t)batch * 42 * 128;
+  float* x = reinterpret_cast<float*>(ar.alloc(tok * 4));
+  float* y = reinterpret_cast<float*>(ar.alloc(tok * 4));
+  float* gh0 = reinterpret_cast<float*>(ar.alloc(2 * tok * 4));
+  float* gh1 = reinterpret_cast<float*>(ar.alloc(2 * tok * 4));
+  if (ar.overflow) return fail(e, DIRB200_E_WORKSPACE, "workspace too small");
+  cudaMemcpy2DAsync(x, 42 * 128 * 4, x_left, 21 * 128 * 4, 21 * 128 * 4, batch, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpy2DAsync(x + 21 * 128, 42 * 128 * 4, x_right, 21 * 128 * 4, 21 * 128 * 4, batch, cudaMemcpyDeviceToDevice, st);
+  e.run_gcn(stage - 1, e.bf16(), x, gh0, gh1, nullptr, 0, y, batch, /*skip_gpos=*/1, st);
+  cudaMemcpy2DAsync(y_left, 21 * 128 * 4, y, 42 * 128 * 4, 21 * 128 * 4, batch, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpy2DAsync(y_right, 21 * 128 * 4, y + 21 * 128, 42 * 128 * 4, 21 * 128 * 4, batch, cudaMemcpyDeviceToDevice, st);
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_ste(dirb200_handle* h, int stage, const float* x, int batch, float* y, void* stream) {
+  H_CHECK(h);
+  if (!e.finalized) return fail(e, DIRB200_E_STATE, "finalize_weights first");
+  if (stage < 1 || stage > 2 || !x || !y || batch <= 0) return fail(e, DIRB200_E_INVALID, "bad ste argument");
+  const StageWeights& sw = e.stage[stage - 1];
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (e.bf16() && sw.ste_packed && !e.ste_simt)
+    launch_ste_tc(x, y, sw.ste, sw.ste_packed, batch, st);
+  else
+    launch_ste(x, y, sw.ste, batch, st);
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_regressor_offset(dirb200_handle* h, int stage, const float* feat_left, const float* feat_right,
+                                        const float* para_left, const float* para_right, const float* offset, int batch,
+                                        float* stage_record, float* mano_para, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
+  H_CHECK(h);
+  if (!e.finalized) return fail(e, DIRB200_E_STATE, "finalize_weights first");
+  if (stage < 1 || stage > 2 || !feat_left || !feat_right || !para_left || !para_right || !offset || !stage_record ||
+      !mano_para || batch <= 0)
+    return fail(e, DIRB200_E_INVALID, "bad regressor_offset argument");
+  Arena ar;
+  ar.base = reinterpret_cast<char*>(workspace);
+  ar.size = workspace_bytes;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int B = batch, s = stage - 1;
+  float* tok = reinterpret_cast<float*>(ar.alloc((size_t)B * 2688 * 4));
+  float* prev_para = reinterpret_cast<float*>(ar.alloc((size_t)B * 128 * 4));
+  float* prev_rec = reinterpret_cast<float*>(ar.alloc((size_t)B * DIRB200_STAGE_FLOATS * 4));
+  if (ar.overflow) return fail(e, DIRB200_E_WORKSPACE, "workspace too small");
+  scatter_rows(tok, 2688, 0, feat_left, 1344, B, st);
+  scatter_rows(tok, 2688, 1344, feat_right, 1344, B, st);
+  scatter_rows(prev_para, 128, 0, para_left, 64, B, st);
+  scatter_rows(prev_para, 128, 64, para_right, 64, B, st);
+  cudaMemsetAsync(prev_rec, 0, (size_t)B * DIRB200_STAGE_FLOATS * 4, st);
+  scatter_rows(prev_rec, DIRB200_STAGE_FLOATS, DIRB200_OFF_OFFSET, offset, 3, B, st);
+  const StageWeights& sw = e.stage[s];
+  RegressArgs a{};
+  for (int hd = 0; hd < 2; ++hd) {  // models/dir.py:344-347: [feat | prev_para] per hand, [feat_l | feat_r | offset]
+    a.in0[hd] = VecSeg{tok + hd * 1344, 1344, 2688};
+    a.in1[hd] = VecSeg{prev_para + hd * 64, 64, 128};
+    a.Wm[hd] = sw.Wm[hd];
+    a.bm[hd] = sw.bm[hd];
+    a.mano[hd] = e.mano[s + 1][hd];
+  }
+  a.off0 = VecSeg{tok, 2688, 2688};
+  a.off1 = VecSeg{prev_rec + DIRB200_OFF_OFFSET, 3, DIRB200_STAGE_FLOATS};
+  a.Wo = sw.Wo;
+  a.bo = sw.bo;
+  a.stage_record = stage_record;
+  a.rec_stride = DIRB200_STAGE_FLOATS;
+  a.mano_para = mano_para;
+  a.para_stride = 128;
+  a.do_proj_feat = 0;
+  a.B = B;
+  launch_regress_mano(a, st);
+  return DIRB200_OK;
+}
+
 template <typename T>
 static int seam_conv(Engine& e, const ConvLayer& L, const float* x, const float* res, int B, int H, int W, float* y,
                      Arena& ar, cudaStream_t st) {

@@ -14,13 +14,17 @@
 //    2304 k-steps of the 18432-deep attention convolution would reach 1e-4. The main accumulator is therefore drained
 //    every CHUNK_KB k-blocks (8 MMAs) into fp32 registers of the epilogue warps with ordinary round-to-nearest adds
 //    while the MMA warp continues into the other TMEM buffer (ping-pong), bounding the bias at ~4e-7.
-// Roles per CTA (320 threads, persistent over tiles of 128 pixels x BN channels, k-block = 32 channels of one tap):
+// Roles per CTA (448 threads, persistent over tiles of 128 pixels x BN channels, k-block = 32 channels of one tap):
 //   warp 0    TMA producer: A box {32 ch, wbox*s, hbox*s, nbox} (im2col, padding and stride are TMA coordinates),
 //             W_hi and W_lo boxes {32 k, BN rows}; `stages`-deep mbarrier ring
 //   warp 1    TMEM allocation (4 x BN columns) + single-thread tcgen05.mma.kind::tf32 issue (12 MMAs per k-block)
 //   warps 2-5 splitter: A_lo tile of each stage
-//   warps 6-9 accumulate/epilogue: tcgen05.ld of each finished chunk -> += registers; at the end of the tile add the
-//             cross-term accumulator, apply scale/shift (+residual) (+ReLU) and store fp32 rows
+//   warps 6-13 accumulate/epilogue, two groups of four warps owning one half of the BN columns each: tcgen05.ld of each
+//             finished chunk -> += registers; at the end of the tile add the cross-term accumulator, apply scale/shift
+//             (+residual, fetched in batches of eight 16-byte loads per thread) (+ReLU) and store fp32 rows
+// Stem variant (7x7 stride 2, Cin = 3; models/backbone/resnet.py:176): the image is repacked to a zero-padded NHWC4
+//   fp32 buffer; a k-block is one kernel row (8 px x 4 ch = 32 floats = 128 B) and the A box comes from an
+//   OVERLAPPING-stride TMA view of that buffer (consecutive output pixels are 2 px = 32 B apart).
 // nsplit = 1 runs the same pipeline as plain TF32 (one MMA per k-step, what PyTorch's cuDNN default does on this GPU).
 #include <cuda.h>
 
@@ -41,7 +45,8 @@ using namespace tc;
 
 constexpr int BM = 128;
 constexpr int KB = 32;          // channels per k-block: one 128-byte fp32 row = one swizzle atom
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 448;  // producer + MMA + 4 splitter + 8 accumulate/epilogue warps
+constexpr int EPI_THREADS = 256;
 constexpr int MAX_STAGES = 4;
 constexpr int CHUNK_KB = 2;     // k-blocks accumulated in TMEM before promotion (2 x 4 k-steps = 8 MMAs)
 constexpr int A_TILE = BM * 128;
@@ -57,6 +62,7 @@ struct T32Args {
   int relu;
   int m_tiles, n_tiles, stages, raster_m;
   int nsplit;  // 3: error-compensated 3xTF32, 1: plain TF32
+  int stem;    // 1: k-block = kernel row ky of the 7x7 stem, A from the overlapping view of the padded NHWC4 image
 };
 
 template <int BN>
@@ -68,7 +74,7 @@ struct Cfg32 {
     int s = (220 * 1024) / STAGE_BYTES;
     return s > MAX_STAGES ? MAX_STAGES : s;
   }
-  static int smem_bytes(int stages) { return 1024 + stages * STAGE_BYTES + 256; }
+  static int smem_bytes(int stages) { return 1024 + stages * STAGE_BYTES + 2 * BN * 4 + 256; }
 };
 
 template <int BN>
@@ -79,7 +85,9 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = a.stages;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * Cfg::STAGE_BYTES);
+  float* s_scale = reinterpret_cast<float*>(smem + stages * Cfg::STAGE_BYTES);  // affine of the current n-tile
+  float* s_shift = s_scale + BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN);
   uint64_t* full_bar = bars;                      // TMA bytes of a stage have landed
   uint64_t* empty_bar = bars + MAX_STAGES;        // the MMAs reading a stage have completed
   uint64_t* split_bar = bars + 2 * MAX_STAGES;    // A_lo of a stage is written (128 arrivals)
@@ -104,8 +112,8 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&main_full[i], 1);
-      mbar_init(&main_empty[i], 128);
-      mbar_init(&cross_empty[i], 128);
+      mbar_init(&main_empty[i], EPI_THREADS);
+      mbar_init(&cross_empty[i], EPI_THREADS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -141,10 +149,14 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], tx);
-          const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
-          const int ky = tap / a.kw, kx = tap - ky * a.kw;
-          tma_load_4d(&tmA, &full_bar[s], stage_A(s), cb * KB, wo0 * a.stride + kx - a.pad, ho0 * a.stride + ky - a.pad,
-                      b0);
+          if (a.stem) {  // kernel row ky = kb: window {8 px x 4 ch} per output pixel, rows 2*ho + ky - 3
+            tma_load_4d(&tmA, &full_bar[s], stage_A(s), 0, wo0, ho0 * 2 + kb - 3, b0);
+          } else {
+            const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
+            const int ky = tap / a.kw, kx = tap - ky * a.kw;
+            tma_load_4d(&tmA, &full_bar[s], stage_A(s), cb * KB, wo0 * a.stride + kx - a.pad,
+                        ho0 * a.stride + ky - a.pad, b0);
+          }
           tma_load_2d(&tmBhi, &full_bar[s], stage_Bhi(s), kb * KB, n0);
           if (comp) tma_load_2d(&tmBlo, &full_bar[s], stage_Blo(s), kb * KB, n0);
           if (++s == stages) {
@@ -230,22 +242,36 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ===================== accumulate + epilogue (warp w may touch TMEM lanes 32*(w%4) .. +31)
+    // ===================== accumulate + epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; warps 6-9 own the first
+    // half of the tile's columns, warps 10-13 the second
+    constexpr int HN = BN / 2;
+    const int et = threadIdx.x - 192;  // 0..255
+    const int half = et >> 7;
     const int lane_base = (warp & 3) * 32;
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
     const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
     uint32_t g = 0, t = 0;
+    int cur_n0 = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
       const int m0 = tile_m0(tile), n0 = tile_n0(tile);
-      float acc[BN];
+      if (n0 != cur_n0) {  // (re)stage the per-channel affine of this n-tile
+        if (cur_n0 >= 0) asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone is done with the previous one
+        if (et < BN) {
+          s_scale[et] = __ldg(a.scale + n0 + et);
+          s_shift[et] = __ldg(a.shift + n0 + et);
+        }
+        cur_n0 = n0;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      float acc[HN];
 #pragma unroll
-      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      for (int j = 0; j < HN; ++j) acc[j] = 0.f;
       for (int c = 0; c < nchunks; ++c, ++g) {
         mbar_wait(&main_full[g & 1], (g >> 1) & 1);
         fence_after();
-        const uint32_t taddr = tmem_base + lane_addr + (g & 1) * BN;
+        const uint32_t taddr = tmem_base + lane_addr + (g & 1) * BN + half * HN;
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j) {
+        for (int j = 0; j < HN / 32; ++j) {
           float v[32];
           tmem_ld32(taddr + j * 32, v);
           tmem_ld_wait();
@@ -256,9 +282,9 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_arrive(&main_empty[g & 1]);
       }
       if (comp) {  // the last chunk's commit covered every MMA of the tile, cross terms included
-        const uint32_t taddr = tmem_base + lane_addr + (2 + (t & 1)) * BN;
+        const uint32_t taddr = tmem_base + lane_addr + (2 + (t & 1)) * BN + half * HN;
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j) {
+        for (int j = 0; j < HN / 32; ++j) {
           float v[32];
           tmem_ld32(taddr + j * 32, v);
           tmem_ld_wait();
@@ -270,31 +296,41 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       const int m = m0 + lane_base + lane;
       if (m < a.M) {
-        float* yrow = a.y + (size_t)m * a.Cout + n0;
-        const float* rrow = a.res ? a.res + (size_t)m * a.Cout + n0 : nullptr;
+        float* yrow = a.y + (size_t)m * a.Cout + n0 + half * HN;
+        const float* rrow = a.res ? a.res + (size_t)m * a.Cout + n0 + half * HN : nullptr;
+        const float* sc = s_scale + half * HN;
+        const float* sh = s_shift + half * HN;
 #pragma unroll
-        for (int j = 0; j < BN; j += 4) {
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + n0 + j));
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + n0 + j));
-          float4 o;
-          o.x = fmaf(acc[j + 0], sc.x, sh.x);
-          o.y = fmaf(acc[j + 1], sc.y, sh.y);
-          o.z = fmaf(acc[j + 2], sc.z, sh.z);
-          o.w = fmaf(acc[j + 3], sc.w, sh.w);
+        for (int jb = 0; jb < HN; jb += 32) {  // 32 columns = eight 16-byte loads in flight per thread
+          float4 r[8];
           if (rrow) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + j));
-            o.x += r.x;
-            o.y += r.y;
-            o.z += r.z;
-            o.w += r.w;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) r[q] = __ldg(reinterpret_cast<const float4*>(rrow + jb + q * 4));
           }
-          if (a.relu) {
-            o.x = fmaxf(o.x, 0.f);
-            o.y = fmaxf(o.y, 0.f);
-            o.z = fmaxf(o.z, 0.f);
-            o.w = fmaxf(o.w, 0.f);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int j = jb + q * 4;
+            const float4 s4 = *reinterpret_cast<const float4*>(sc + j);
+            const float4 h4 = *reinterpret_cast<const float4*>(sh + j);
+            float4 o;
+            o.x = fmaf(acc[j + 0], s4.x, h4.x);
+            o.y = fmaf(acc[j + 1], s4.y, h4.y);
+            o.z = fmaf(acc[j + 2], s4.z, h4.z);
+            o.w = fmaf(acc[j + 3], s4.w, h4.w);
+            if (rrow) {
+              o.x += r[q].x;
+              o.y += r[q].y;
+              o.z += r[q].z;
+              o.w += r[q].w;
+            }
+            if (a.relu) {
+              o.x = fmaxf(o.x, 0.f);
+              o.y = fmaxf(o.y, 0.f);
+              o.z = fmaxf(o.z, 0.f);
+              o.w = fmaxf(o.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(yrow + j) = o;
           }
-          *reinterpret_cast<float4*>(yrow + j) = o;
         }
       }
     }
@@ -319,7 +355,50 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict
   lo[i] = rn_tf32(x - h);
 }
 
+// NCHW fp32 image -> zero-padded NHWC4 fp32: out[b][h][w + 3][c] (c = 3 is zero), row pitch (W + 8) pixels
+__global__ void stem_pack32_kernel(const float* __restrict__ img, float4* __restrict__ out, int B, int H, int W) {
+  pdl_wait();
+  const int Wp = W + 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * H * Wp) return;
+  const int wp = (int)(idx % Wp);
+  const int64_t t = idx / Wp;
+  const int h = (int)(t % H), b = (int)(t / H);
+  const int w = wp - 3;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (w >= 0 && w < W) {
+    const float* p = img + ((int64_t)b * 3 * H + h) * W + w;
+    v.x = __ldg(p);
+    v.y = __ldg(p + (int64_t)H * W);
+    v.z = __ldg(p + 2 * (int64_t)H * W);
+  }
+  out[idx] = v;
+}
+
+// stem weights [64][3][7][7] -> [64][7 * 32] with k = ky*32 + kx*4 + c (zero for kx = 7 and c = 3)
+__global__ void stem_pack_weight32_kernel(const float* __restrict__ w, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 224) return;
+  const int k = idx % 224, n = idx / 224;
+  const int ky = k / 32, r = k % 32, kx = r / 4, c = r % 4;
+  out[idx] = (kx < 7 && c < 3) ? w[((n * 3 + c) * 7 + ky) * 7 + kx] : 0.f;
+}
+
 int pick_bn32(int Cout) { return Cout % 128 == 0 ? 128 : 64; }
+
+bool weight_maps32(float* hi, float* lo, int Kpad, int Cout, int bn, CUtensorMap* mhi, CUtensorMap* mlo) {
+  cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)Kpad * 4};
+  cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)bn};
+  cuuint32_t es[2] = {1, 1};
+  for (int i = 0; i < 2; ++i) {
+    CUresult r = tma::get_encode()(i ? mlo : mhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, i ? lo : hi, dims, strides, box, es,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+  }
+  return true;
+}
 
 bool act_map32_cached(const float* x, int B, int H, int W, int C, int stride, const tma::Boxes& bx, const char* name,
                       CUtensorMap* out) {
@@ -343,7 +422,7 @@ bool act_map32_cached(const float* x, int B, int H, int W, int C, int stride, co
 }
 
 template <int BN>
-int launch_t32(const CUtensorMap& tmA, const ConvLayer& L, T32Args a, cudaStream_t st) {
+int launch_t32(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, T32Args a, cudaStream_t st) {
   using Cfg = Cfg32<BN>;
   a.stages = Cfg::stages();
   const int smem = Cfg::smem_bytes(a.stages);
@@ -360,7 +439,7 @@ int launch_t32(const CUtensorMap& tmA, const ConvLayer& L, T32Args a, cudaStream
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  if (cudaLaunchKernelEx(&cfg, conv_tf32_kernel<BN>, tmA, L.wmap32hi, L.wmap32lo, a) != cudaSuccess) return DIRB200_E_CUDA;
+  if (cudaLaunchKernelEx(&cfg, conv_tf32_kernel<BN>, tmA, tmBhi, tmBlo, a) != cudaSuccess) return DIRB200_E_CUDA;
   return DIRB200_OK;
 }
 
@@ -385,16 +464,9 @@ int conv_tf32_prepare_weights(ConvLayer& L, float* hi, float* lo, cudaStream_t s
   const int64_t n = (int64_t)L.Cout * L.Kpad;
   split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L.w32, hi, lo, n);
   const int bn = pick_bn32(L.Cout);
-  cuuint64_t dims[2] = {(cuuint64_t)L.Kpad, (cuuint64_t)L.Cout};
-  cuuint64_t strides[1] = {(cuuint64_t)L.Kpad * 4};
-  cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)bn};
-  cuuint32_t es[2] = {1, 1};
-  for (int i = 0; i < 2; ++i) {
-    CUresult r = enc(i ? &L.wmap32lo : &L.wmap32hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, i ? lo : hi, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return DIRB200_E_CUDA;
-  }
+  if (!weight_maps32(hi, lo, L.Kpad, L.Cout, bn, &L.wmap32hi, &L.wmap32lo)) return DIRB200_E_CUDA;
+  // 64-row boxes as well: small-M launches (deep layers at small batch) use the narrower tile to fill the SMs
+  L.wmap32_alt64 = bn == 128 && weight_maps32(hi, lo, L.Kpad, L.Cout, 64, &L.wmap32hi64, &L.wmap32lo64);
   L.w32hi = hi;
   L.w32lo = lo;
   L.wmap32_bn = bn;
@@ -426,7 +498,77 @@ int launch_conv_tf32(const ConvLayer& L, const float* x, float* y, const float* 
   a.n_tiles = L.Cout / L.wmap32_bn;
   a.raster_m = (double)L.Cout * L.K > (double)B * H * W * L.Cin ? 1 : 0;
   a.nsplit = nsplit == 1 ? 1 : 3;
-  return L.wmap32_bn == 128 ? launch_t32<128>(tmA, L, a, st) : launch_t32<64>(tmA, L, a, st);
+  if (L.wmap32_bn == 128 && !(L.wmap32_alt64 && a.m_tiles * a.n_tiles * 4 < tma::num_sms() * 3))
+    return launch_t32<128>(tmA, L.wmap32hi, L.wmap32lo, a, st);
+  a.n_tiles = L.Cout / 64;
+  if (L.wmap32_bn == 128) return launch_t32<64>(tmA, L.wmap32hi64, L.wmap32lo64, a, st);
+  return launch_t32<64>(tmA, L.wmap32hi, L.wmap32lo, a, st);
+}
+
+// ---- stem (7x7 s2, 3 -> 64) on the same kernel
+size_t conv_tf32_stem_scratch_bytes(int B, int H, int W) { return (size_t)B * H * (W + 8) * 16; }
+size_t conv_tf32_stem_weight_floats() { return 3 * 64 * 224; }  // packed + hi + lo
+
+// `buf` = conv_tf32_stem_weight_floats() floats (caller-allocated): packed weights, then their hi / lo split
+int conv_tf32_prepare_stem(ConvLayer& L, const float* w_raw, float* buf, cudaStream_t st) {
+  L.tf32_stem = false;
+  if (!tma::get_encode() || !buf || L.Cin != 3 || L.Cout != 64 || L.kh != 7 || L.kw != 7 || L.stride != 2 || L.pad != 3)
+    return 0;
+  float *packed = buf, *hi = buf + 64 * 224, *lo = buf + 2 * 64 * 224;
+  stem_pack_weight32_kernel<<<(64 * 224 + 255) / 256, 256, 0, st>>>(w_raw, packed);
+  split_tf32_kernel<<<(64 * 224 + 255) / 256, 256, 0, st>>>(packed, hi, lo, 64 * 224);
+  if (!weight_maps32(hi, lo, 224, 64, 64, &L.wmap32hi, &L.wmap32lo)) return DIRB200_E_CUDA;
+  L.tf32_stem = true;
+  return DIRB200_OK;
+}
+
+bool conv_tf32_stem_supported(const ConvLayer& L, int H, int W) { return L.tf32_stem && H % 2 == 0 && W == 256; }
+
+int launch_conv_tf32_stem(const ConvLayer& L, const float* img, float* scratch, float* y, int B, int H, int W, int nsplit,
+                          cudaStream_t st) {
+  const int Wp = W + 8, Ho = H / 2, Wo = W / 2;
+  const int64_t n = (int64_t)B * H * Wp;
+  launch_pdl(stem_pack32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, img,
+             reinterpret_cast<float4*>(scratch), B, H, W);
+  typedef std::tuple<const void*, int, int, int> Key;
+  static thread_local tma::MapCache<Key> cache;
+  Key key(scratch, B, H, W);
+  CUtensorMap tm;
+  if (!cache.find(key, &tm)) {
+    // overlapping view of the padded NHWC4 buffer: the 8-pixel window of output pixel wo starts at padded pixel 2*wo
+    cuuint64_t dims[4] = {32, (cuuint64_t)Wo, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {32, (cuuint64_t)Wp * 16, (cuuint64_t)H * Wp * 16};
+    cuuint32_t box[4] = {32, (cuuint32_t)BM, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = tma::get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, scratch, dims, strides, box, es,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      fprintf(stderr, "dirb200: cuTensorMapEncodeTiled(fp32 stem A, overlapping strides) failed: %d\n", (int)r);
+      return DIRB200_E_CUDA;
+    }
+    cache.put(key, tm);
+  }
+  T32Args a{};
+  a.scale = L.scale;
+  a.shift = L.shift;
+  a.res = nullptr;
+  a.y = y;
+  a.M = B * Ho * Wo;
+  a.Cout = 64;
+  a.Ho = Ho;
+  a.Wo = Wo;
+  a.stride = 2;
+  a.pad = 3;
+  a.kw = 7;
+  a.taps = 7;
+  a.cblocks = 1;
+  a.relu = L.relu;
+  a.m_tiles = (a.M + BM - 1) / BM;
+  a.n_tiles = 1;
+  a.nsplit = nsplit == 1 ? 1 : 3;
+  a.stem = 1;
+  return launch_t32<64>(tm, L.wmap32hi, L.wmap32lo, a, st);
 }
 
 }  // namespace dirb200

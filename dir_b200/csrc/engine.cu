@@ -392,6 +392,10 @@ int Engine::build(cudaStream_t st) {
     if (sp) launch_pack_stem_pool_weight(W("backbone.conv1.weight"), sp, st);
     stem_pool_w = sp;
   }
+  if (!dry && !bf16() && err.empty()) {
+    float* buf = dalloc(conv_tf32_stem_weight_floats());
+    if (buf) conv_tf32_prepare_stem(stem, W("backbone.conv1.weight"), buf, st);
+  }
   const int nblocks[4] = {3, 4, 6, 3};
   for (int l = 0; l < 4; ++l) {
     layers[l].clear();
@@ -603,6 +607,8 @@ int Engine::run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** 
   __nv_bfloat16* stem_scratch =
       tc_stem ? reinterpret_cast<__nv_bfloat16*>(ar.alloc(conv_tc_stem_scratch_bytes(B, H, W_))) : nullptr;
   float* u8_scratch = tc_stem ? nullptr : aalloc<float>(ar, (int64_t)B * 3 * H * W_);  // fp32 image from uint8 frames
+  const bool stem32 = sizeof(T) == 4 && !fp32_simt && conv_tf32_stem_supported(stem, H, W_);
+  float* stem32_scratch = stem32 ? reinterpret_cast<float*>(ar.alloc(conv_tf32_stem_scratch_bytes(B, H, W_))) : nullptr;
   T* stem_out = aalloc<T>(ar, (int64_t)B * H2 * W2 * 64);
   T* pool_out = aalloc<T>(ar, (int64_t)B * H4 * W4 * 64);
   const int64_t rsz = (int64_t)B * H4 * W4 * 256;
@@ -639,6 +645,15 @@ int Engine::run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** 
     if (rc && !sticky_rc) {
       sticky_rc = rc;
       err = "tcgen05 stem launch failed";
+    }
+    launches += 2;
+    tc_launches += 1;
+  } else if (stem32) {  // fp32 / tf32 configurations: the stem on conv_tf32.cu's overlapping-view variant
+    int rc = launch_conv_tf32_stem(stem, img, stem32_scratch, reinterpret_cast<float*>(stem_out), B, H, W_, tf32_nsplit(),
+                                   st);
+    if (rc && !sticky_rc) {
+      sticky_rc = rc;
+      err = "tcgen05 tf32 stem launch failed";
     }
     launches += 2;
     tc_launches += 1;
@@ -757,6 +772,48 @@ int Engine::run_init(const T* c4, int B, float* stage_rec, int rec_stride, float
   return DIRB200_OK;
 }
 
+// SemGCN stack of stage s for both hands (SemGCN/p_gcn.py:63-73) + global_pos_emb (models/dir.py:103-110):
+// x (B,2,21,128) -> y (B,2,21,128); gh0/gh1 = two (2,B,2,21,128) scratch planes. tc: tf32 tcgen05 GEMMs (bf16 config).
+void Engine::run_gcn(int s, bool tc, const float* x, float* gh0, float* gh1, const float* prev_rec, int prev_stride,
+                     float* y, int B, int skip_gpos, cudaStream_t st) {
+  const StageWeights& sw = stage[s];
+  auto agg_of = [&](int l) {
+    GcnAgg g{};
+    for (int h = 0; h < 2; ++h) {
+      g.A1[h] = sw.gcn[l].A1[h];
+      g.scale[h] = sw.gcn[l].scale[h];
+      g.shift[h] = sw.gcn[l].shift[h];
+    }
+    return g;
+  };
+  float *hin = nullptr, *hout = gh0;
+  for (int l = 0; l < 4; ++l) {
+    GcnGemmArgs g{};
+    g.x = l == 0 ? x : nullptr;
+    g.hin = hin;
+    if (l > 0) g.agg = agg_of(l - 1);
+    g.hout = hout;
+    for (int h = 0; h < 2; ++h) g.W[h] = sw.gcn[l].W[h];
+    g.B = B;
+    if (tc && sw.gcn[l].Wtc[0] && sw.gcn[l].Wtc[1] && !gcn_simt)
+      launch_gcn_gemm_tc(g, sw.gcn[l].Wtc[0], sw.gcn[l].Wtc[1], st);
+    else
+      launch_gcn_gemm(g, st);
+    hin = hout;
+    hout = (hout == gh0) ? gh1 : gh0;
+  }
+  GcnFinishArgs f{};
+  f.hin = hin;
+  f.agg = agg_of(3);
+  f.gpos = sw.gpos;
+  f.prev_record = prev_rec;
+  f.rec_stride = prev_stride;
+  f.y = y;
+  f.B = B;
+  f.skip_gpos = skip_gpos;
+  launch_gcn_finish(f, st);
+}
+
 template <typename T>
 int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_stride, const float* prev_para,
                       int prev_para_stride, int B, float* stage_rec, int rec_stride, float* para, int para_stride,
@@ -788,42 +845,7 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
   e.out = jf0;
   e.B = B;
   launch_joint_embed<T>(e, st);
-  auto agg_of = [&](int l) {
-    GcnAgg g{};
-    for (int h = 0; h < 2; ++h) {
-      g.A1[h] = sw.gcn[l].A1[h];
-      g.scale[h] = sw.gcn[l].scale[h];
-      g.shift[h] = sw.gcn[l].shift[h];
-    }
-    return g;
-  };
-  float *hin = nullptr, *hout = gh0;
-  for (int l = 0; l < 4; ++l) {
-    GcnGemmArgs g{};
-    g.x = l == 0 ? jf0 : nullptr;
-    g.hin = hin;
-    if (l > 0) g.agg = agg_of(l - 1);
-    g.hout = hout;
-    for (int h = 0; h < 2; ++h) g.W[h] = sw.gcn[l].W[h];
-    g.B = B;
-    if (std::is_same<T, __nv_bfloat16>::value && sw.gcn[l].Wtc[0] && sw.gcn[l].Wtc[1] && !gcn_simt)
-      launch_gcn_gemm_tc(g, sw.gcn[l].Wtc[0], sw.gcn[l].Wtc[1], st);
-    else
-      launch_gcn_gemm(g, st);
-    hin = hout;
-    hout = (hout == gh0) ? gh1 : gh0;
-  }
-  {
-    GcnFinishArgs f{};
-    f.hin = hin;
-    f.agg = agg_of(3);
-    f.gpos = sw.gpos;
-    f.prev_record = prev_rec;
-    f.rec_stride = prev_stride;
-    f.y = jf1;
-    f.B = B;
-    launch_gcn_finish(f, st);
-  }
+  run_gcn(s, std::is_same<T, __nv_bfloat16>::value, jf0, gh0, gh1, prev_rec, prev_stride, jf1, B, 0, st);
   float* gin = jf1;
   if (std::is_same<T, __nv_bfloat16>::value && sw.ste_packed && !ste_simt)
     launch_ste_tc(gin, tok, sw.ste, sw.ste_packed, B, st);

@@ -40,6 +40,9 @@ struct ConvLayer {
   float* w32lo = nullptr;
   CUtensorMap wmap32hi, wmap32lo;  // box 32(k) x wmap32_bn rows, 128B swizzle
   int wmap32_bn = 0;               // rows per weight box (0: no tensor-core path for this layer)
+  CUtensorMap wmap32hi64, wmap32lo64;  // the same weights as 64-row boxes (narrow tiles for small-M launches)
+  bool wmap32_alt64 = false;
+  bool tf32_stem = false;          // 7x7/s2/Cin=3 stem packed for conv_tf32.cu's stem variant
   int tc_bn_cap = 256;   // largest n-tile the tensor-core path may pick (128 for layers that add a residual)
   bool tc_stem = false;  // 7x7/s2/Cin=3 stem packed for the tensor-core stem variant
 };
@@ -194,6 +197,8 @@ struct Engine {
   template <typename T>
   int run_init(const T* c4, int B, float* stage_rec, int rec_stride, float* para, int para_stride, Arena& ar,
                cudaStream_t st);
+  void run_gcn(int s, bool tc, const float* x, float* gh0, float* gh1, const float* prev_rec, int prev_stride, float* y,
+               int B, int skip_gpos, cudaStream_t st);
   template <typename T>
   int run_stage(int s, const T* img_feat, const float* prev_rec, int prev_stride, const float* prev_para,
                 int prev_para_stride, int B, float* stage_rec, int rec_stride, float* para, int para_stride,
@@ -207,6 +212,12 @@ bool conv_tf32_supported(const ConvLayer& L, int B, int H, int W);
 int conv_tf32_prepare_weights(ConvLayer& L, float* hi, float* lo, cudaStream_t st);  // splits L.w32, builds the maps
 int launch_conv_tf32(const ConvLayer& L, const float* x, float* y, const float* res, int B, int H, int W, int nsplit,
                      cudaStream_t st);
+size_t conv_tf32_stem_scratch_bytes(int B, int H, int W);
+size_t conv_tf32_stem_weight_floats();
+int conv_tf32_prepare_stem(ConvLayer& L, const float* w_raw, float* buf, cudaStream_t st);
+bool conv_tf32_stem_supported(const ConvLayer& L, int H, int W);
+int launch_conv_tf32_stem(const ConvLayer& L, const float* img, float* scratch, float* y, int B, int H, int W, int nsplit,
+                          cudaStream_t st);
 // tensor-core conv (conv_tc.cu). Returns false if the shape is not supported (caller falls back to CUDA cores).
 bool conv_tc_supported(const ConvLayer& L, int B, int H, int W);
 int conv_tc_prepare_weights(ConvLayer& L);  // builds L.wmap

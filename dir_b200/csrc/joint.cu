@@ -75,6 +75,17 @@ __global__ void __launch_bounds__(128) joint_embed_kernel(EmbedArgs a) {
       outv[r][0] = v[0] + b2.x; outv[r][1] = v[1] + b2.y; outv[r][2] = v[2] + b2.z; outv[r][3] = v[3] + b2.w;
     });
   }
+  if (a.skip_pos) {  // seam: ImgFeature2JointFeature.forward alone (models/dir.py:197-200)
+    float* out = a.out + ((int64_t)(b * 2 + hand) * NJ) * 128;
+    const int cg = n % 32, rg = n / 32;
+    if (rg < 3) {
+#pragma unroll
+      for (int r = 0; r < 7; ++r)
+        *reinterpret_cast<float4*>(out + (rg * 7 + r) * 128 + cg * 4) =
+            make_float4(outv[r][0], outv[r][1], outv[r][2], outv[r][3]);
+    }
+    return;
+  }
   {  // ---- pos_emb: 3 -> 128 (BN, ReLU) -> 128
     const PointMlp& f = a.pos[hand];
     float w0 = f.w1t[n], w1 = f.w1t[128 + n], w2 = f.w1t[256 + n];
@@ -155,6 +166,14 @@ __global__ void __launch_bounds__(256) gcn_finish_kernel(GcnFinishArgs a) {
   __shared__ __align__(16) float xs[GBT][128];
   const int i = blockIdx.x, hand = blockIdx.y, b0 = blockIdx.z * GBT, tid = threadIdx.x;
   const int nb = min(GBT, a.B - b0);
+  if (a.skip_gpos) {  // seam: the SemGCN stack alone (SemGCN/p_gcn.py:63-73)
+    for (int e = tid; e < nb * 32; e += 256) {
+      const int row = e >> 5, c4 = e & 31;
+      *reinterpret_cast<float4*>(a.y + ((size_t)((b0 + row) * 2 + hand) * NJ + i) * 128 + c4 * 4) =
+          gcn_aggregate(a.hin, a.agg, a.B, b0 + row, hand, i, c4);
+    }
+    return;
+  }
   const PointMlp& g = a.gpos;
   const float sgn = hand == 0 ? -1.f : 1.f;
   for (int e = tid; e < GBT * 128; e += 256) {  // hidden layer of global_pos_emb: 3 -> 128, BN, ReLU

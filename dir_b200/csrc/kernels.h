@@ -81,6 +81,7 @@ struct EmbedArgs {
   PointMlp pos[2];      // pos_emb_{left,right} 3->128->128
   float* out;           // (B,2,21,128)
   int B;
+  int skip_pos;         // 1: image feature only (ImgFeature2JointFeature.forward seam), no pos_emb term
 };
 template <typename T>
 void launch_joint_embed(const EmbedArgs& a, cudaStream_t st);
@@ -115,6 +116,7 @@ struct GcnFinishArgs {  // tokens = relu(bn(agg(H))) + global_pos_emb(xyz/0.15 -
   int rec_stride;
   float* y;  // (B,2,21,128) = (B,42,128) tokens
   int B;
+  int skip_gpos;  // 1: y = relu(bn(agg(H))) only (ResSimplePGCN.forward seam)
 };
 void launch_gcn_finish(const GcnFinishArgs& a, cudaStream_t st);
 

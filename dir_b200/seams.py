@@ -126,6 +126,50 @@ def joint2bone(model, stage, img_feat, prev, want_vis=False):
     return stage_dict(rec, para), feats
 
 
+def img2joint(model, stage, img_feat, uv_left, uv_right):
+    """ImgFeature2JointFeature.forward of both hands (models/dir.py:197-200) -> two (B,21,128) tensors."""
+    img_feat, uv_left, uv_right = _f32(img_feat), _f32(uv_left), _f32(uv_right)
+    B = img_feat.shape[0]
+    h, ws = _prep(model, B)
+    out = [torch.empty(B, 21, 128, device=img_feat.device) for _ in range(2)]
+    h.check(h.lib.dirb200_img2joint(h.h, stage, _ptr(img_feat), _ptr(uv_left), _ptr(uv_right), B, _ptr(out[0]),
+                                    _ptr(out[1]), _ptr(ws), ws.numel(), _stream()), "img2joint")
+    return out
+
+
+def gcn(model, stage, x_left, x_right):
+    """ResSimplePGCN.forward of gcn_left / gcn_right (SemGCN/p_gcn.py:63-73): (B,21,128) -> (B,21,128) per hand."""
+    x_left, x_right = _f32(x_left), _f32(x_right)
+    B = x_left.shape[0]
+    h, ws = _prep(model, B)
+    out = [torch.empty(B, 21, 128, device=x_left.device) for _ in range(2)]
+    h.check(h.lib.dirb200_gcn(h.h, stage, _ptr(x_left), _ptr(x_right), B, _ptr(out[0]), _ptr(out[1]), _ptr(ws),
+                              ws.numel(), _stream()), "gcn")
+    return out
+
+
+def ste(model, stage, x):
+    """STE.forward (transformer/mixSTE.py:194-205): (B,42,128) -> (B,42,64)."""
+    x = _f32(x)
+    B = x.shape[0]
+    h, _ = _prep(model, B)
+    y = torch.empty(B, 42, 64, device=x.device)
+    h.check(h.lib.dirb200_ste(h.h, stage, _ptr(x), B, _ptr(y), _stream()), "ste")
+    return y
+
+
+def regressor_offset(model, stage, feat_left, feat_right, para_left, para_right, offset):
+    """RegressorOffset.forward (models/dir.py:339-381) -> stage dict incl. pd_mano_para_*."""
+    args = [_f32(t) for t in (feat_left, feat_right, para_left, para_right, offset.reshape(offset.shape[0], 3))]
+    B = args[0].shape[0]
+    h, ws = _prep(model, B)
+    rec = torch.zeros(B, capi.STAGE_FLOATS, device=args[0].device)
+    para = torch.zeros(B, 2, 64, device=args[0].device)
+    h.check(h.lib.dirb200_regressor_offset(h.h, stage, *[_ptr(a) for a in args], B, _ptr(rec), _ptr(para), _ptr(ws),
+                                           ws.numel(), _stream()), "regressor_offset")
+    return stage_dict(rec, para)
+
+
 def bone_proj(model, uv, feat, size, distance):
     uv, feat = _f32(uv), _f32(feat)
     B = uv.shape[0]

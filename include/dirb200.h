@@ -139,6 +139,24 @@ int dirb200_mano(dirb200_handle* h, int which, const float* para, int batch, flo
 int dirb200_joint2bone(dirb200_handle* h, int stage, const float* img_feat, const float* prev_record,
                        const float* prev_para, int batch, float* stage_record, float* mano_para, float* img_feat_out,
                        float* joint_feat, float* vis_img_feat, void* workspace, size_t workspace_bytes, void* stream);
+/* ImgFeature2JointFeature.forward (models/dir.py:197-200) of both hands of a stage: F.grid_sample (bilinear, zeros,
+ * align_corners=False) + the `filters` point-MLP. img_feat (B,256,S,S); uv (B,21,2) in [-1,1]; out (B,21,128) = the
+ * reference's (B,128*21) viewed (B,128,21) and permuted (models/dir.py:94-95). */
+int dirb200_img2joint(dirb200_handle* h, int stage, const float* img_feat, const float* uv_left, const float* uv_right,
+                      int batch, float* out_left, float* out_right, void* workspace, size_t workspace_bytes,
+                      void* stream);
+/* ResSimplePGCN.forward (SemGCN/p_gcn.py:63-73; gcn_left / gcn_right of a stage): four PGraphConv + BN + ReLU layers
+ * (SemGCN/p_graph_conv.py:39-60). x, y (B,21,128). bf16 handles run the tf32 tcgen05 GEMMs (gcn_tc.cu). */
+int dirb200_gcn(dirb200_handle* h, int stage, const float* x_left, const float* x_right, int batch, float* y_left,
+                float* y_right, void* workspace, size_t workspace_bytes, void* stream);
+/* STE.forward (transformer/mixSTE.py:194-205; `interaction` of a stage): x (B,42,128) -> y (B,42,64). The reference
+ * adds the position embedding into x in place; here x is read-only. bf16 handles run the tcgen05 kernel (ste_tc.cu). */
+int dirb200_ste(dirb200_handle* h, int stage, const float* x, int batch, float* y, void* stream);
+/* RegressorOffset.forward (models/dir.py:339-381): joint features (B,21,64) per hand, previous MANO parameters (B,64)
+ * per hand and previous offset (B,3) -> stage slice of the record (MANO layers + projection included) + mano_para. */
+int dirb200_regressor_offset(dirb200_handle* h, int stage, const float* feat_left, const float* feat_right,
+                             const float* para_left, const float* para_right, const float* offset, int batch,
+                             float* stage_record, float* mano_para, void* workspace, size_t workspace_bytes, void* stream);
 /* Joint2BoneFeature.bone_proj (models/dir.py:146-174): uv (B,21,2), feat (B,21,64) -> (B,1280,S,S) */
 int dirb200_bone_proj(dirb200_handle* h, const float* uv, const float* feat, int batch, int size, float distance,
                       float* out, void* stream);

@@ -22,6 +22,12 @@ p = os.path.join(ROOT, "MEASURED_PEAKS.json")
 if os.path.exists(p):
     d = json.load(open(p))
     pk = {"tflops": d["bf16_tflops_sustained"], "hbm": d["hbm_gbs"]}
+# tf32 MMA issue rate measured by scripts/mma_probe.cu (profiles/mma_probe_r2.txt): 3064 flop/clk/SM = 891 TFLOP/s at
+# 1965 MHz; precision fp32 spends three tf32 MMAs per algorithmic MAC (3xTF32), precision tf32 one
+if args.precision == "fp32":
+    pk["tflops"] = 891.0 / 3
+elif args.precision == "tf32":
+    pk["tflops"] = 891.0
 net = dir_b200.DIR(21, "./misc/mano", precision=args.precision, max_batch=args.batch).cuda()
 net.load_state_dict(make_state_dict(0), strict=False)
 img = torch.randn(args.batch, 3, 256, 256, generator=torch.Generator().manual_seed(0)).cuda()
@@ -37,7 +43,8 @@ h.profile_read()
 h.profile_layer(None)
 tot = sum(r["ms"] for r in rows)
 floor = 0.0
-print(f"# B={args.batch} {args.precision}; peaks: {pk['tflops']} TFLOP/s (sustained), {pk['hbm']} GB/s (measured)")
+print(f"# B={args.batch} {args.precision}; peaks: {pk['tflops']:.1f} algorithmic TFLOP/s "
+      f"({'cuBLAS bf16 sustained' if args.precision == 'bf16' else 'tf32 MMA issue rate / MMAs per MAC'}), {pk['hbm']} GB/s (measured)")
 print(f"{'layer':58s} tc {'k':>3s} {'cin':>5s} {'cout':>5s} {'ms':>7s} {'TF/s':>7s} {'GB/s':>7s} {'floor_ms':>8s} {'x floor':>7s} bound")
 for r in rows:
     t_c = r["flops"] / (pk["tflops"] * 1e12) * 1e3

@@ -4,9 +4,13 @@ seeded inputs, with the committed golden outputs of the unmodified reference (te
 — at the benchmark's full batch — through size-independent properties.
 
 Tolerances (relative = max|a-b| / max|b| per tensor):
-  fp32 configuration : 1e-4   (north_star's bar; measured ~1e-6..1e-5)
-  bf16 configuration : stated per test, measured values are printed (bf16 feature maps cannot meet 1e-4;
-                       SURVEY.md H1 measured 0.2 mm drift for the reference's own bf16 autocast).
+  fp32 configuration : 1e-4   (north_star's bar). Measured 3e-5..6e-5 on the worst tensor of the whole forward against a
+                       float64 evaluation of the oracle; the fp32 oracle itself (torch CPU) sits 2.5e-5 from that truth
+                       and PyTorch's fp32 cuDNN forward on the same B200 5.6e-5 (profiles/drift_table_r2.txt): this is
+                       the noise floor of fp32 arithmetic through this network, not a property of the kernels.
+  bf16 configuration : bf16 feature maps cannot meet 1e-4. The bar is the reference's OWN drift when run in bf16
+                       (torch.autocast) on the same weights and inputs, evaluated inside the tests: per stage, our mean
+                       per-vertex drift must not exceed it (measured: 2.4 mm vs 3.1-3.5 mm at stage 2).
 """
 import os
 
@@ -297,6 +301,55 @@ def test_forward_bf16_vs_golden(m16, golden_dir, X):
     d_mm = float((outs[2]["pd_mesh_xyz_left"].cpu() - ref_v).norm(dim=-1).mean() * 1000)
     print(f"bf16 whole-forward worst relative error {worst:.2e}; mean per-vertex drift {d_mm:.3f} mm")
     assert d_mm < 5.0
+
+
+def _mesh_drift_mm(outs, want, i):
+    d = torch.cat([(outs[i][k].float().cpu() - want[i][k].float()).norm(dim=-1).flatten()
+                   for k in ("pd_mesh_xyz_left", "pd_mesh_xyz_right")]) * 1000
+    return float(d.mean()), float(d.max())
+
+
+def test_forward_fp32_b32_vs_float64_oracle(m32, synth_sd):
+    """BASELINE.json configs[1] at its full size (B=32, ResNet-50, 3 stages, fp32): every output tensor against the oracle
+    evaluated in float64 on the host; the fp32 oracle's own distance to that truth is printed beside it."""
+    from oracle import dir_oracle as O
+
+    img = torch.randn(32, 3, 256, 256, generator=torch.Generator().manual_seed(3232))
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in synth_sd.items()}
+    truth = O.dir_forward(sd64, img.double())
+    host32 = O.dir_forward(synth_sd, img)
+    outs, _ = m32({"img": img}, None, None)
+    worst, floor = 0.0, 0.0
+    for i in range(3):
+        for k in O.OUT_KEYS:
+            worst = max(worst, rel(outs[i][k], truth[i][k].float()))
+            floor = max(floor, rel(host32[i][k], truth[i][k].float()))
+    mm = _mesh_drift_mm(outs, truth, 2)
+    print(f"B=32 fp32: worst relative error vs float64 oracle {worst:.2e} (torch CPU fp32 oracle: {floor:.2e}); "
+          f"stage-2 per-vertex drift mean {mm[0]:.5f} mm max {mm[1]:.5f} mm")
+    assert worst < TOL32
+    assert mm[1] < 0.01  # MPVPE budget of north_star, per vertex
+
+
+def test_forward_bf16_b128_vs_oracle_and_reference_autocast(m16, synth_sd):
+    """The benchmarked configuration at its full batch (B=128, bf16) against the fp32 oracle, with the reference's own
+    bf16 behaviour (the same op sequence under torch.autocast(bfloat16) on the host) as the yardstick: per stage our
+    mean per-vertex drift must not exceed the reference-autocast drift on the same 128 images."""
+    from oracle import dir_oracle as O
+
+    img = torch.randn(128, 3, 256, 256, generator=torch.Generator().manual_seed(128128))
+    want = O.dir_forward(synth_sd, img)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        auto = O.dir_forward(synth_sd, img)
+    auto = [{k: (v.float() if v is not None else None) for k, v in d.items()} for d in auto[:3]]
+    outs, _ = m16({"img": img}, None, None)
+    for i in range(3):
+        ours, ref = _mesh_drift_mm(outs, want, i), _mesh_drift_mm(auto, want, i)
+        worst = max(rel(outs[i][k], want[i][k]) for k in O.OUT_KEYS)
+        print(f"B=128 bf16 stage {i}: per-vertex drift mean {ours[0]:.3f} mm max {ours[1]:.2f} mm "
+              f"(reference under bf16 autocast: mean {ref[0]:.3f} mm max {ref[1]:.2f} mm); worst relative {worst:.3f}")
+        assert ours[0] <= ref[0], (i, ours, ref)
+    assert _mesh_drift_mm(outs, want, 2)[0] < 4.0
 
 
 @pytest.mark.parametrize("which", ["m32", "m16"])
