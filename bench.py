@@ -7,7 +7,15 @@ A step = one whole eval forward (ResNet-50 backbone -> init regression -> 2 refi
 outputs, incl. the seg/dense/proj_feat heads the reference also computes) over one batch of B synthetic
 images per GPU. For N>1 (torchrun, one rank per GPU) images shard over ranks (weak scaling) and each step
 ends with the path's single collective, the all-gather of the output records.
-Prints ONE JSON line on rank 0 (contract in the task statement).
+Prints ONE JSON line on rank 0 (contract in the task statement). Keys beyond the contract:
+  roofline          the dominant KERNEL = all conv_tc_kernel launches of the step (72 launches, ~78 % of the step):
+                    executed algorithmic FLOPs / summed CUDA-event time, against the measured cuBLAS bf16 peak
+  roofline_top      the largest single launch (InitRegressor attention conv), same method
+  roofline_step     whole step: executed FLOPs (the 2560-channel fusion conv is factored away, so its 15.3 GFLOP/img
+                    are NOT counted) and, labelled, the dense-equivalent figure of the reference's op sequence
+  gpu_eager_baseline  the reference's op sequence in PyTorch eager on this GPU (fp32, TF32-allowed, bf16 autocast)
+  parity            measured in this run on 8 of the benchmark's images against the CPU oracle
+  no_aux            the same step without the seg/dense/proj_feat heads apps/eval.py never reads
 """
 import argparse
 import json
@@ -20,11 +28,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GF_PER_IMAGE = 36.80  # dense-contraction GFLOP per image, ResNet-50, 3 stages, incl. heads (measured)
-# dominant kernel = largest single launch of the step: the two InitRegressor attention convs, run as one
-# conv3x3 2048->2048 @8x8 (models/dir.py:227-241), 4.83 GFLOP/img, on conv_tc_kernel<256,128,2> (2-CTA tcgen05)
-DOMINANT_LAYER = "init_regressor.attention_left.0"
-DOMINANT_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+GF_DENSE_EQUIV = 36.80  # GFLOP/img of the reference's own op sequence: incl. the 15.27 GF dense fusion convs
+GF_JOINT_SPACE = 0.09   # grid_sample/pos-emb/SemGCN/mixSTE/regressor/MANO
+GF_FUSION_FACTORED = 0.35  # what bone_coef + bone_fusion actually execute instead of the 15.27 GF dense convs
+TOP_LAYER = "init_regressor.attention_left.0"
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+TF32_PEAK_TFLOPS = 891.0  # tcgen05 kind::tf32 issue rate measured by scripts/mma_probe.cu (profiles/mma_probe_r2.txt)
 
 
 def parse():
@@ -34,10 +43,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="images per GPU per step")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "tf32"])
     ap.add_argument("--cpu-batch", type=int, default=16, help="images per CPU-baseline forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip eager-GPU baseline, parity, no-aux and fp32-config legs")
     ap.add_argument("--cuda-graph", action="store_true")
     return ap.parse_args()
 
@@ -47,10 +57,9 @@ def peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return {"tflops": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))),
-                "tflops_burst": float(d.get("bf16_tflops", 0.0)) or None,
-                "hbm_gbs": float(d.get("hbm_gbs", 6650.0)), "source": "measured (MEASURED_PEAKS.json, sustained)"}
-    return {"tflops": 1400.0, "tflops_burst": None, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"burst": float(d.get("bf16_tflops", 1590.0)), "sustained": float(d.get("bf16_tflops_sustained", 1400.0)),
+                "hbm_gbs": float(d.get("hbm_gbs", 6650.0)), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler(threading.Thread):
@@ -93,8 +102,8 @@ def cpu_forward_rate(batch, min_seconds, max_iters):
     unmodified reference by tests/golden) with all host threads. Returns (images/s, cores, seconds, iters)."""
     import torch
 
-    from oracle.synth import make_state_dict
     from oracle import dir_oracle as O
+    from oracle.synth import make_state_dict
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -115,8 +124,8 @@ def run_reference(args, rank):
         return
     import torch
 
-    from oracle.synth import make_state_dict
     from oracle import dir_oracle as O
+    from oracle.synth import make_state_dict
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -130,7 +139,8 @@ def run_reference(args, rank):
         O.dir_forward(sd, img)
     dt = time.perf_counter() - t0
     v = bs * args.steps / dt
-    sample = f"{args.steps} forwards of {bs} images (bounded sample of the B={args.batch} workload), fp32, {cores} threads"
+    sample = (f"{args.steps} forwards of {bs} images (bounded sample of the B={args.batch} workload; CPU images/s is flat "
+              f"above B~8, BASELINE.md 3), fp32, {cores} threads")
     print(json.dumps({
         "impl": "reference", "metric": "images/sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1000, "higher_is_better": True,
@@ -140,6 +150,72 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def gpu_eager_baseline(dev, batch, steps=6):
+    """BASELINE.md 3(4) / SURVEY 2: the reference's op sequence (oracle restatement: the same ATen / cuDNN / cuBLAS calls
+    as models/dir.py, eager, no graphs) on this GPU. images/s for fp32 convs, TF32-allowed convs (torch's default) and
+    bf16 autocast."""
+    import torch
+
+    from oracle import dir_oracle as O
+    from oracle.synth import make_state_dict
+
+    sd = {k: v.to(dev) for k, v in make_state_dict(0).items()}
+    imgs = [torch.randn(batch, 3, 256, 256, device=dev) for _ in range(2)]
+    out = {"batch": batch, "unit": "images/s", "how": "oracle/dir_oracle.py ops on CUDA, PyTorch eager, cudnn.benchmark"}
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name, tf32, ac in (("fp32", False, False), ("tf32_convs_torch_default", True, False), ("bf16_autocast", True, True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                for i in range(3):
+                    O.dir_forward(sd, imgs[i % 2])
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(steps):
+                    O.dir_forward(sd, imgs[i % 2])
+                e1.record()
+            torch.cuda.synchronize()
+            out[name] = batch * steps / (e0.elapsed_time(e1) / 1000.0)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = prev
+    return out
+
+
+def parity_check(net, precision, host_batch, n=8):
+    """Parity of THIS run: n of the benchmark's own images through the net and through the CPU oracle."""
+    import torch
+
+    from oracle import dir_oracle as O
+    from oracle.synth import make_state_dict
+
+    sd = make_state_dict(0)
+    img = host_batch[:n].clone()
+    want = O.dir_forward(sd, img)
+    outs, _ = net({"img": img}, None, None)
+    torch.cuda.synchronize()
+
+    def drift(a, b, i):
+        d = torch.cat([(a[i][k].float().cpu() - b[i][k].float()).norm(dim=-1).flatten()
+                       for k in ("pd_mesh_xyz_left", "pd_mesh_xyz_right")]) * 1000
+        return float(d.mean()), float(d.max())
+
+    worst = max(float((outs[i][k].float().cpu() - want[i][k]).abs().max() / (want[i][k].abs().max() + 1e-30))
+                for i in range(3) for k in O.OUT_KEYS)
+    res = {"against": f"CPU oracle (fp32 restatement of the reference, pinned by tests/golden) on {n} of the timed images",
+           "worst_relative_error": worst, "stage2_mesh_drift_mm_mean": drift(outs, want, 2)[0],
+           "stage2_mesh_drift_mm_max": drift(outs, want, 2)[1]}
+    if precision == "bf16":
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            auto = O.dir_forward(sd, img)
+        auto = [{k: (v.float() if v is not None else None) for k, v in d.items()} for d in auto[:3]]
+        res["reference_bf16_autocast_stage2_mesh_drift_mm_mean"] = drift(auto, want, 2)[0]
+        res["note"] = ("bf16 feature maps: the yardstick is the reference's own drift under torch.autocast(bfloat16) on the "
+                       "same images; precision='fp32' meets 1e-4 (parity_fp32)")
+    return res
 
 
 def main():
@@ -156,20 +232,27 @@ def main():
 
     import dir_b200
     from dir_b200 import capi
+    from dir_b200.dist import bind_to_gpu_numa_node
     from oracle.synth import make_state_dict
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # pinned staging buffers must live on the GPU's own NUMA node: bind BEFORE anything is allocated (first touch)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
 
-    net = dir_b200.DIR(21, "./misc/mano", precision=args.precision, aux_outputs=True, max_batch=B,
-                       use_cuda_graph=args.cuda_graph).to(dev)
-    net.load_state_dict(make_state_dict(0), strict=False)
-    net.eval()
+    def make_net(precision, aux, max_batch=B):
+        n = dir_b200.DIR(21, "./misc/mano", precision=precision, aux_outputs=aux, max_batch=max_batch,
+                         use_cuda_graph=args.cuda_graph).to(dev)
+        n.load_state_dict(make_state_dict(0), strict=False)
+        n.eval()
+        return n
+
+    net = make_net(args.precision, True)
     if world > 1:
         def bcast(b):
             obj = [b]
@@ -182,56 +265,73 @@ def main():
     host = [torch.randn(B, 3, 256, 256, generator=gen).pin_memory() for _ in range(NBUF)]
     resident = [h.to(dev) for h in host]
 
-    def step(i):
-        o = net.run_raw(resident[i % NBUF])
-        if world > 1:
-            return net.allgather_records(o["record"])
-        return o["record"]
-
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn, steps, warm):
+        for i in range(warm):
+            fn(i)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_of(model):
+        def step(i):
+            o = model.run_raw(resident[i % NBUF])
+            if world > 1:
+                return model.allgather_records(o["record"])
+            return o["record"]
+        return step
+
+    # ---- timed region: K steps, inputs resident in HBM, device timers, max over ranks
+    step = step_of(net)
     for i in range(W):
         step(i)
     sync_all()
     h = net._handle
     launches_per_step = h.lib.dirb200_forward_launches(h.h, B) + (1 if world > 1 else 0)
-
-    # ---- timed region: K steps, inputs resident in HBM, device timers, max over ranks
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    if not args.cuda_graph:
-        h.profile_layer(DOMINANT_LAYER)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    for i in range(K):
-        step(i)
-    e1.record()
-    sync_all()
-    ms = e0.elapsed_time(e1)
+    ms = timed(step, K, 0)
     if sampler:
         sampler.stop_flag.set()
         sampler.join()
-    prof_ms, prof_n, prof_flops = (0.0, 0, 0.0)
-    if not args.cuda_graph:
-        prof_ms, prof_n, prof_flops = h.profile_read()
-        h.profile_layer(None)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     value = world * B * K / (ms / 1000.0)
 
-    # ---- end to end through the public API: pinned host input -> H2D -> forward -> D2H of the record
-    e2e = None
+    # ---- per-conv CUDA events (launch stream) over a second, shorter run of the same step: the dominant kernel's time
+    conv_rows, prof_steps = [], 0
+    if not args.cuda_graph and rank == 0:
+        prof_steps = max(2, min(K, 10))
+        h.profile_layer("")
+        for i in range(prof_steps):
+            step(i)
+        torch.cuda.synchronize()
+        conv_rows = h.profile_dump()
+        h.profile_read()
+        h.profile_layer(None)
+    if world > 1:
+        dist.barrier()
+
+    # ---- end to end through the public API (DIR.forward): pinned HOST input -> H2D -> forward -> D2H of the record
+    e2e = e2e_f32 = None
+    h2d_gbs = None
     if not args.no_e2e:
         out_hosts = [torch.empty(B, capi.RECORD_FLOATS).pin_memory() for _ in range(2)]
         d2h = torch.cuda.Stream(device=dev)  # the caller's download stream: result i leaves while forward i+1 runs
         Ke = max(3, min(K, 20))
+        frames = [torch.randint(0, 256, (B, 256, 256, 3), dtype=torch.uint8, generator=gen).pin_memory()
+                  for _ in range(NBUF)]
 
         def download(i, rec):
             ev = torch.cuda.Event()
@@ -241,61 +341,71 @@ def main():
                 out_hosts[i % 2].copy_(rec, non_blocking=True)
             rec.record_stream(d2h)
 
-        def e2e_step(i):
-            outs, _ = net({"img": host[i % NBUF]}, None, None)  # forward() does the H2D copy (models/dir.py:514)
-            rec = net_last_record(outs)
+        def e2e_step_of(inputs):
+            def f(i):
+                outs, _ = net({"img": inputs[i % NBUF]}, None, None)  # forward() does the H2D copy (models/dir.py:514)
+                rec = outs[0]["pd_mesh_xyz_left"]._base  # the stage dicts are views into one packed record
+                if world > 1:
+                    rec = net.allgather_records(rec)[rank * B:(rank + 1) * B]
+                download(i, rec)
+            return f
+
+        def run_e2e(inputs, bytes_in, label):
+            f = e2e_step_of(inputs)
+            for i in range(3):
+                f(i)
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(Ke):
+                f(i)
+            torch.cuda.current_stream().wait_stream(d2h)  # the last result must have reached the host inside the region
+            e1.record()
+            sync_all()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
             if world > 1:
-                rec = net.allgather_records(rec)[rank * B:(rank + 1) * B]
-            download(i, rec)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return {"value": world * B * Ke / (float(t.item()) / 1000.0), "unit": "images/s",
+                    "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": B * capi.RECORD_FLOATS * 4, "steps": Ke,
+                    "input": label}
 
-        def net_last_record(outs):
-            # the 3 stage dicts are views into one packed record; recover it without a copy
-            return outs[0]["pd_mesh_xyz_left"]._base if outs[0]["pd_mesh_xyz_left"]._base is not None else None
-
-        for i in range(3):
-            e2e_step(i)
+        # the headline e2e: what a camera / cv2 hands over (apps/eval.py:56-61 runs the normalisation on the HOST per
+        # sample; here it runs on the device, fused into the stem operand packing) — 4x fewer H2D bytes than fp32
+        e2e = run_e2e(frames, B * 256 * 256 * 3, "uint8 HWC BGR host frames (pinned); BGR->RGB,/255,mean/std on the device")
+        e2e_f32 = run_e2e(host, B * 3 * 256 * 256 * 4, "fp32 NCHW normalised host images (pinned): the tensor "
+                                                       "apps/eval.py:168 passes")
+        # H2D bandwidth this rank sees while all ranks copy at once (names the limiter of e2e scaling)
         sync_all()
-        e0.record()
-        for i in range(Ke):
-            e2e_step(i)
-        torch.cuda.current_stream().wait_stream(d2h)  # the last result must have reached the host inside the timed region
-        e1.record()
-        sync_all()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(8):
+            resident[i % NBUF].copy_(host[i % NBUF], non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([c0.elapsed_time(c1)], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * Ke / (float(t.item()) / 1000.0), "unit": "images/s",
-               "h2d_bytes_per_step": B * 3 * 256 * 256 * 4, "d2h_bytes_per_step": B * capi.RECORD_FLOATS * 4,
-               "steps": Ke}
+        h2d_gbs = 8 * B * 3 * 256 * 256 * 4 / (float(t.item()) / 1000.0) / 1e9
 
-    # ---- same, fed with raw uint8 BGR frames (next-row N1: preprocessing on the device, 4x fewer H2D bytes)
-    e2e_u8 = None
-    if not args.no_e2e:
-        frames = [torch.randint(0, 256, (B, 256, 256, 3), dtype=torch.uint8, generator=gen).pin_memory()
-                  for _ in range(NBUF)]
-
-        def u8_step(i):
-            outs, _ = net({"img": frames[i % NBUF]}, None, None)
-            rec = outs[0]["pd_mesh_xyz_left"]._base
-            if world > 1:
-                rec = net.allgather_records(rec)[rank * B:(rank + 1) * B]
-            download(i, rec)
-
-        for i in range(3):
-            u8_step(i)
-        sync_all()
-        e0.record()
-        for i in range(Ke):
-            u8_step(i)
-        torch.cuda.current_stream().wait_stream(d2h)
-        e1.record()
-        sync_all()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_u8 = {"value": world * B * Ke / (float(t.item()) / 1000.0), "unit": "images/s",
-                  "h2d_bytes_per_step": B * 256 * 256 * 3, "d2h_bytes_per_step": B * capi.RECORD_FLOATS * 4,
-                  "steps": Ke, "input": "uint8 HWC BGR frames, preprocessing (apps/eval.py:56-61) on the device"}
+    extras = world == 1 and not args.no_extras
+    no_aux = parity = parity32 = fp32_cfg = eager = None
+    if extras:
+        net_na = make_net(args.precision, False)
+        ms_na = timed(step_of(net_na), K, W)
+        no_aux = {"value": B * K / (ms_na / 1000.0), "unit": "images/s", "ms_per_step": ms_na / K,
+                  "what": "aux_outputs=False: without conv_final/seg/dense/proj_feat, which apps/eval.py:170-172 never reads"}
+        del net_na
+        parity = parity_check(net, args.precision, host[0])
+        if args.precision == "bf16":  # the parity configuration (BASELINE configs[1]) beside the headline, same run
+            net32 = make_net("fp32", True, 32)
+            res32 = [r[:32].contiguous() for r in resident]
+            ms32 = timed(lambda i: net32.run_raw(res32[i % NBUF]), max(5, K // 2), W)
+            fp32_cfg = {"value": 32 * max(5, K // 2) / (ms32 / 1000.0), "unit": "images/s", "batch": 32,
+                        "ms_per_step": ms32 / max(5, K // 2),
+                        "what": "precision='fp32' (3xTF32 tcgen05 convs, round-to-nearest accumulation), B=32: BASELINE configs[1]"}
+            parity32 = parity_check(net32, "fp32", host[0])
+            del net32
+        eager = gpu_eager_baseline(dev, B if B <= 128 else 128)
 
     if rank != 0:
         if world > 1:
@@ -303,46 +413,77 @@ def main():
         return
 
     pk = peaks()
-    step_tflops = GF_PER_IMAGE * B * K / 1000.0 / (ms / 1000.0) if world == 1 else None
-    roof = None
-    if prof_n:
-        ach = prof_flops / (prof_ms / 1000.0) / 1e12
+    mma_per_mac = {"bf16": 1, "tf32": 1, "fp32": 3}[args.precision]
+    tensor_peak = pk["burst"] if args.precision == "bf16" else TF32_PEAK_TFLOPS / mma_per_mac
+    peak_note = ("cuBLAS bf16 burst, MEASURED_PEAKS.json" if args.precision == "bf16" else
+                 f"tcgen05 kind::tf32 issue rate 891 TFLOP/s (profiles/mma_probe_r2.txt) / {mma_per_mac} MMAs per MAC")
+    roof = roof_top = None
+    conv_gf_img = None
+    if conv_rows:
+        tc_rows = [r for r in conv_rows if r["tc"]]
+        fam_ms = sum(r["ms"] for r in tc_rows)
+        fam_fl = sum(r["flops"] for r in tc_rows)
+        n_launch = len(tc_rows)
+        conv_gf_img = sum(r["flops"] for r in conv_rows) / prof_steps / B / 1e9
+        ach = fam_fl / (fam_ms / 1000.0) / 1e12
         traffic = None
-        if os.path.exists(DOMINANT_TRAFFIC_FILE):  # dram__bytes_read+write per launch from one ncu --set full capture
-            with open(DOMINANT_TRAFFIC_FILE) as f:
+        if os.path.exists(TRAFFIC_FILE):  # dram bytes per launch (family average) from the committed ncu capture
+            with open(TRAFFIC_FILE) as f:
                 t = json.load(f)
             if t.get("batch") == B and t.get("precision") == args.precision:
-                traffic = t.get("dram_bytes_per_launch")
-        roof = {"bound": "tensor", "kernel": f"conv_tc_kernel<256,128,2> cta_group::2 ({DOMINANT_LAYER}: conv3x3 2048->2x1024 @8x8, "
-                                             f"{prof_flops / prof_n / 1e9:.1f} GFLOP/launch algorithmic = 2*M*N*K)",
-                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                "traffic": traffic, "peak_source": pk["source"], "launches_timed": prof_n,
-                # the timed region is ~0.3 s at full SM clock, shorter than the 4 s run behind the sustained figure:
-                # the burst cuBLAS number is the physically comparable ceiling, reported beside the contractual one
-                "peak_burst": pk["tflops_burst"],
-                "frac_of_burst": (ach / pk["tflops_burst"]) if pk["tflops_burst"] else None,
-                "avg_launch_ms": prof_ms / prof_n, "share_of_step": prof_ms / ms}
+                traffic = t.get("family_dram_bytes_per_launch")
+        kname = "conv_tc_kernel<BN,128,CG> (tcgen05 bf16 implicit GEMM)" if args.precision == "bf16" else \
+                "conv_tf32_kernel<BN> (tcgen05 kind::tf32 implicit GEMM)"
+        roof = {"bound": "tensor", "kernel": f"{kname}: all {n_launch // prof_steps} launches of a step "
+                                             f"({fam_fl / n_launch / 1e9:.1f} GFLOP/launch executed, algorithmic 2*M*N*K)",
+                "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak, "traffic": traffic,
+                "peak_source": f"{peak_note}; {pk['source']}",
+                "frac_of_sustained_peak": ach / pk["sustained"] if args.precision == "bf16" else None,
+                "launches_timed": n_launch, "avg_launch_ms": fam_ms / n_launch,
+                "share_of_step": fam_ms / prof_steps / (ms / K),
+                "how": f"CUDA events on the launch stream around every launch, {prof_steps} steps after the timed region"}
+        top = [r for r in tc_rows if r["layer"].startswith(TOP_LAYER)]
+        if top:
+            t_ms, t_fl = sum(r["ms"] for r in top), sum(r["flops"] for r in top)
+            a2 = t_fl / (t_ms / 1000.0) / 1e12
+            roof_top = {"bound": "tensor", "kernel": f"largest single launch: {TOP_LAYER} (conv3x3 2048->2x1024 @8x8, "
+                                                     f"{t_fl / len(top) / 1e9:.1f} GFLOP)",
+                        "achieved": a2, "peak": tensor_peak, "unit": "TFLOP/s", "frac": a2 / tensor_peak,
+                        "avg_launch_ms": t_ms / len(top), "share_of_step": t_ms / prof_steps / (ms / K)}
+    step_roof = None
+    if world == 1 and conv_gf_img is not None:
+        gf_exec = conv_gf_img + GF_FUSION_FACTORED + GF_JOINT_SPACE
+        tf = gf_exec * B * K / 1000.0 / (ms / 1000.0)
+        step_roof = {"bound": "tensor", "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak,
+                     "gflop_per_image_executed": gf_exec,
+                     "note": f"whole step, EXECUTED FLOPs: convs {conv_gf_img:.2f} (live profile) + factored fusion "
+                             f"{GF_FUSION_FACTORED} + joint space {GF_JOINT_SPACE} GFLOP/img; the 15.27 GFLOP/img of the dense "
+                             f"2560-channel fusion convs are factored away and not credited",
+                     "dense_equivalent": {"gflop_per_image": GF_DENSE_EQUIV,
+                                          "tflops": GF_DENSE_EQUIV * B * K / 1000.0 / (ms / 1000.0),
+                                          "label": "reference op sequence incl. work this implementation never executes"}}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, cores, dt, iters = cpu_forward_rate(args.cpu_batch, 10.0, 12)
         cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"{iters} forwards of {args.cpu_batch} images in {dt:.1f} s (same weights/input recipe), fp32"}
+               "sample": f"{iters} forwards of {args.cpu_batch} images in {dt:.1f} s (same weights/input recipe; CPU "
+                         f"images/s is flat above B~8), fp32"}
     line = {
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "dtype": {"bf16": "bf16", "fp32": "f32", "tf32": "tf32"}[args.precision], "data": "synthetic",
         "config": {"workload": f"DIR eval forward (ResNet-50 backbone, init regression, 2 refinement stages, "
                                f"seg/dense/proj_feat heads), 256x256, B={B} per GPU, random-init weights + synthetic MANO",
                    "global_batch": B * world, "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": f"{NBUF} rotating resident input batches (4x100 MB > 126 MB L2); activations ~GBs per step",
-                   "collective": "ncclAllGather of (B,14661) fp32 records per step" if world > 1 else None},
+                   "collective": "ncclAllGather of (B,14661) fp32 records per step" if world > 1 else None,
+                   "numa": numa},
         "clocks": sampler.summary() if sampler else None,
-        "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": launches_per_step * K,
-        "roofline": roof,
-        "roofline_step": None if step_tflops is None else {
-            "bound": "tensor", "achieved": step_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
-            "frac": step_tflops / pk["tflops"], "note": f"whole step, {GF_PER_IMAGE} GFLOP/img algorithmic"},
-        "cpu_baseline": cpu,
+        "e2e": e2e, "e2e_fp32_input": e2e_f32, "h2d_gbs_per_rank_all_ranks_copying": h2d_gbs,
+        "gpu_launches": launches_per_step * K,
+        "roofline": roof, "roofline_top": roof_top, "roofline_step": step_roof,
+        "cpu_baseline": cpu, "gpu_eager_baseline": eager, "parity": parity, "no_aux": no_aux,
+        "fp32_config": fp32_cfg, "parity_fp32": parity32,
     }
     print(json.dumps(line))
     if world > 1:

@@ -56,3 +56,37 @@ def forward_sharded(model, img_global: torch.Tensor):
         local = torch.cat([local, local.new_zeros(pad - local.shape[0], local.shape[1])], 0)
     full = assemble(model.allgather_records(local.contiguous()), n, world)
     return model.unpack_record(full)
+
+
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this process (and, by first touch, every pinned host buffer it allocates afterwards) to the CPU cores of the
+    NUMA node its GPU hangs off. With one process per GPU and all ranks left on node 0, eight concurrent H2D streams
+    share one socket's memory controllers and cross the socket interconnect (measured round 1: 0.74 end-to-end scaling
+    at 8 GPUs with the kernels themselves at 0.97). Returns a small report dict, or None when sysfs has no answer."""
+    import os
+
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(f"{base}/local_cpulist") as f:
+            cpulist = f.read().strip()
+        node = None
+        if os.path.exists(f"{base}/numa_node"):
+            with open(f"{base}/numa_node") as f:
+                node = int(f.read().strip())
+        cpus = set()
+        for part in cpulist.split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return {"gpu": bdf, "numa_node": node, "bound": False, "why": "no local cpu is in this process' cpuset"}
+        os.sched_setaffinity(0, cpus)
+        torch.set_num_threads(max(1, min(len(cpus), 8)))
+        return {"gpu": bdf, "numa_node": node, "bound": True, "cpus": len(cpus), "of_allowed": len(allowed)}
+    except (OSError, ValueError, AttributeError, RuntimeError) as e:
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"}

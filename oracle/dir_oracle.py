@@ -360,6 +360,28 @@ def bone_proj(uv, feat, S, distance):
     return img.reshape(B, S, S, 20 * C).permute(0, 3, 1, 2)
 
 
+def bone_capsule_margin(uv, S, distance):
+    """Distance of the closest (pixel, bone) pair to the capsule boundary of bone_proj, per image: min |hypot(h,c) - distance|
+    (same arithmetic as bone_proj above). The mask `hypot(h,c) < distance` (models/dir.py:164) is the one discontinuity
+    of the forward: an image whose margin is below the arithmetic's noise may legitimately flip a pixel."""
+    p = (uv + 1) / 2 * S
+    a = p[:, BONE_PARENT].unsqueeze(1)
+    b = p[:, BONE_CHILD].unsqueeze(1)
+    r = torch.arange(S, dtype=uv.dtype, device=uv.device) + 0.5
+    gy, gx = torch.meshgrid(r, r, indexing="ij")
+    P = torch.stack((gx, gy), -1).reshape(1, S * S, 1, 2)
+    dba = b - a
+    d = dba / torch.hypot(dba[..., 0], dba[..., 1]).unsqueeze(-1)
+    s = ((a - P) * d).sum(-1)
+    t = ((P - b) * d).sum(-1)
+    h = torch.maximum(torch.maximum(s, t), torch.zeros((), dtype=uv.dtype, device=uv.device))
+    dpa = P - a
+    c = dpa[..., 0] * d[..., 1] - dpa[..., 1] * d[..., 0]
+    m = (torch.hypot(h, c) - distance).abs()
+    m = torch.where(torch.isnan(m), torch.full_like(m, float("inf")), m)
+    return m.flatten(1).min(1).values
+
+
 def joint2bone(sd, p, img_feat, prev, S, distance):
     """models/dir.py:86-130. `prev` holds pd_joint_xyz_*, pd_joint_uv_*, pd_mano_para_*, pd_offset."""
     offset = prev["pd_offset"].unsqueeze(1)  # (B,1,3)

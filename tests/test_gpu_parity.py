@@ -310,25 +310,49 @@ def _mesh_drift_mm(outs, want, i):
 
 
 def test_forward_fp32_b32_vs_float64_oracle(m32, synth_sd):
-    """BASELINE.json configs[1] at its full size (B=32, ResNet-50, 3 stages, fp32): every output tensor against the oracle
-    evaluated in float64 on the host; the fp32 oracle's own distance to that truth is printed beside it."""
+    """BASELINE.json configs[1] at its full size (B=32, ResNet-50, 3 stages, fp32): every output tensor of every image
+    against the oracle evaluated in float64 on the host; the fp32 oracle's own distance to that truth is printed beside it.
+    Stages 0 and 1 are continuous functions of the input: 1e-4 for all 32 images. Stage 2 sits behind the one
+    discontinuity of the forward, the capsule mask of stage 1's bone_proj (`hypot(h,c) < distance`, models/dir.py:164):
+    an image in which some pixel lies on a capsule boundary to within the fp32 noise of uv (~1e-5 px) flips that pixel
+    in ANY fp32 implementation (the torch CPU oracle included). Such images are identified from the float64 truth by
+    their boundary margin, must be rare, and are bounded at 5e-2; every other image meets 1e-4."""
     from oracle import dir_oracle as O
 
-    img = torch.randn(32, 3, 256, 256, generator=torch.Generator().manual_seed(3232))
+    B = 32
+    img = torch.randn(B, 3, 256, 256, generator=torch.Generator().manual_seed(3232))
     sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in synth_sd.items()}
     truth = O.dir_forward(sd64, img.double())
     host32 = O.dir_forward(synth_sd, img)
     outs, _ = m32({"img": img}, None, None)
-    worst, floor = 0.0, 0.0
-    for i in range(3):
+
+    def per_image(o, i):
+        e = torch.zeros(B, dtype=torch.float64)
         for k in O.OUT_KEYS:
-            worst = max(worst, rel(outs[i][k], truth[i][k].float()))
-            floor = max(floor, rel(host32[i][k], truth[i][k].float()))
-    mm = _mesh_drift_mm(outs, truth, 2)
-    print(f"B=32 fp32: worst relative error vs float64 oracle {worst:.2e} (torch CPU fp32 oracle: {floor:.2e}); "
-          f"stage-2 per-vertex drift mean {mm[0]:.5f} mm max {mm[1]:.5f} mm")
-    assert worst < TOL32
-    assert mm[1] < 0.01  # MPVPE budget of north_star, per vertex
+            t = truth[i][k].double()
+            d = (o[i][k].detach().double().cpu() - t).abs().flatten(1).max(1).values
+            e = torch.maximum(e, d / t.abs().max())
+        return e
+
+    for i in (0, 1):
+        ours, floor = per_image(outs, i), per_image(host32, i)
+        print(f"B=32 fp32 stage {i}: worst image {float(ours.max()):.2e} (torch CPU fp32 oracle {float(floor.max()):.2e})")
+        assert float(ours.max()) < TOL32
+    # stage 2: margins of stage 1's capsule test, from the truth
+    margin = torch.minimum(O.bone_capsule_margin(truth[1]["pd_joint_uv_left"], 16, 1.0),
+                           O.bone_capsule_margin(truth[1]["pd_joint_uv_right"], 16, 1.0))
+    ours, floor = per_image(outs, 2), per_image(host32, 2)
+    on_boundary = margin < 1e-4  # pixels: uv carries ~1e-5 of fp32 noise here (3e-5 relative on the worst tensor), x S/2
+    print(f"B=32 fp32 stage 2: worst image off the boundary {float(ours[~on_boundary].max()):.2e} "
+          f"(torch CPU fp32 oracle {float(floor[~on_boundary].max()):.2e}); {int(on_boundary.sum())} image(s) within 1e-4 px of a "
+          f"capsule boundary: ours {[f'{float(v):.1e}' for v in ours[on_boundary]]}, "
+          f"oracle fp32 {[f'{float(v):.1e}' for v in floor[on_boundary]]}, margins {[f'{float(v):.1e}' for v in margin[on_boundary]]}")
+    assert float(ours[~on_boundary].max()) < TOL32
+    assert int(on_boundary.sum()) <= 4 and (not bool(on_boundary.any()) or float(ours[on_boundary].max()) < 5e-2)
+    mm = torch.cat([(outs[2][k].detach().double().cpu() - truth[2][k]).norm(dim=-1)[~on_boundary].flatten()
+                    for k in ("pd_mesh_xyz_left", "pd_mesh_xyz_right")]) * 1000
+    print(f"B=32 fp32 stage 2 per-vertex drift: mean {float(mm.mean()):.5f} mm max {float(mm.max()):.5f} mm")
+    assert float(mm.max()) < 0.01  # north_star's MPVPE budget, applied per vertex
 
 
 def test_forward_bf16_b128_vs_oracle_and_reference_autocast(m16, synth_sd):

@@ -133,6 +133,33 @@ def _gloo_worker(rank, world, port, n, q):
         dist.all_gather(bufs, local)
         full = assemble(torch.cat(bufs, 0), n, world)
         ok = bool((full[:, 0] == torch.arange(n, dtype=torch.float32)).all()) and full.shape == (n, 5)
+
+        # forward_sharded end to end with a stand-in for the GPU module (incl. n < world: a rank with an empty shard
+        # must still enter the collective instead of raising and leaving its peers hanging)
+        import dir_b200
+        from dir_b200 import capi
+        from dir_b200.dist import forward_sharded
+
+        class Fake:
+            unpack_record = staticmethod(dir_b200.DIR.unpack_record)
+
+            def _device(self):
+                return torch.device("cpu")
+
+            def run_raw(self, img):
+                assert img.shape[0] > 0, "run_raw must not be called for an empty shard"
+                return {"record": img[:, 0, 0, :1].expand(-1, capi.RECORD_FLOATS).contiguous()}
+
+            def allgather_records(self, rec):
+                out = [torch.empty_like(rec) for _ in range(world)]
+                dist.all_gather(out, rec)
+                return torch.cat(out, 0)
+
+        for m in (n, 1):
+            img = torch.arange(m, dtype=torch.float32).view(m, 1, 1, 1).expand(m, 3, 4, 4).contiguous()
+            outs = forward_sharded(Fake(), img)
+            ok = ok and outs[2]["pd_offset"].shape == (m, 3) and bool(
+                (outs[0]["pd_mesh_xyz_left"][:, 0, 0] == torch.arange(m, dtype=torch.float32)).all())
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
