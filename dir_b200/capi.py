@@ -24,6 +24,7 @@ EXPORTS = [
     "dirb200_joint2bone", "dirb200_bone_proj", "dirb200_nccl_unique_id", "dirb200_nccl_init",
     "dirb200_allgather_records", "dirb200_profile_layer", "dirb200_profile_read", "dirb200_conv_layer", "dirb200_profile_dump", "dirb200_forward_u8", "dirb200_preprocess_u8", "dirb200_eval_metrics",
     "dirb200_img2joint", "dirb200_gcn", "dirb200_ste", "dirb200_regressor_offset",
+    "dirb200_bone_fusion",
 ]
 
 
@@ -78,6 +79,7 @@ def load_library():
     lib.dirb200_gcn.argtypes = [vp, ip, vp, vp, ip, vp, vp, vp, C.c_size_t, vp]
     lib.dirb200_ste.argtypes = [vp, ip, vp, ip, vp, vp]
     lib.dirb200_regressor_offset.argtypes = [vp, ip, vp, vp, vp, vp, vp, ip, vp, vp, vp, C.c_size_t, vp]
+    lib.dirb200_bone_fusion.argtypes = [vp, ip, vp, vp, vp, vp, ip, vp, vp, C.c_size_t, vp]
     lib.dirb200_bone_proj.argtypes = [vp, vp, vp, ip, ip, fp, vp, vp]
     lib.dirb200_nccl_unique_id.argtypes = [vp, C.c_char_p]
     lib.dirb200_nccl_init.argtypes = [vp, C.c_char_p, ip, ip]

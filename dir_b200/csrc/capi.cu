@@ -513,6 +513,48 @@ extern "C" int dirb200_regressor_offset(dirb200_handle* h, int stage, const floa
 }
 
 template <typename T>
+static int seam_bone_fusion(Engine& e, int s, const float* uv_l, const float* uv_r, const float* feat_l, const float* feat_r,
+                            int B, float* out_nchw, Arena& ar, cudaStream_t st) {
+  const int S = e.stage[s].S;
+  float* rec = reinterpret_cast<float*>(ar.alloc((size_t)B * DIRB200_STAGE_FLOATS * 4));
+  float* jf = reinterpret_cast<float*>(ar.alloc((size_t)B * 42 * 64 * 4));
+  T* bone = e.dense_fusion ? reinterpret_cast<T*>(ar.alloc((size_t)B * S * S * 2560 * sizeof(T))) : nullptr;
+  float* coef = e.dense_fusion ? nullptr : reinterpret_cast<float*>(ar.alloc((size_t)B * 40 * 2 * 9 * 256 * 4));
+  T* mid = reinterpret_cast<T*>(ar.alloc((size_t)B * S * S * 256 * sizeof(T)));
+  T* out = reinterpret_cast<T*>(ar.alloc((size_t)B * S * S * 256 * sizeof(T)));
+  if (ar.overflow) return DIRB200_E_WORKSPACE;
+  cudaMemsetAsync(rec, 0, (size_t)B * DIRB200_STAGE_FLOATS * 4, st);
+  scatter_rows(rec, DIRB200_STAGE_FLOATS, DIRB200_OFF_UV_L, uv_l, 42, B, st);
+  scatter_rows(rec, DIRB200_STAGE_FLOATS, DIRB200_OFF_UV_R, uv_r, 42, B, st);
+  scatter_rows(jf, 42 * 64, 0, feat_l, 21 * 64, B, st);
+  scatter_rows(jf, 42 * 64, 21 * 64, feat_r, 21 * 64, B, st);
+  e.sticky_rc = 0;
+  e.run_bone_fusion<T>(s, rec, DIRB200_STAGE_FLOATS, jf, B, bone, coef, mid, out, st);
+  if (e.sticky_rc) return e.sticky_rc;
+  launch_nhwc_to_nchw<T>(out, out_nchw, B, 256, S, S, st);
+  return DIRB200_OK;
+}
+
+extern "C" int dirb200_bone_fusion(dirb200_handle* h, int stage, const float* uv_left, const float* uv_right,
+                                   const float* feat_left, const float* feat_right, int batch, float* img_feat_out,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  H_CHECK(h);
+  if (!e.finalized) return fail(e, DIRB200_E_STATE, "finalize_weights first");
+  if (stage < 1 || stage > 2 || !uv_left || !uv_right || !feat_left || !feat_right || !img_feat_out || batch <= 0)
+    return fail(e, DIRB200_E_INVALID, "bad bone_fusion argument");
+  Arena ar;
+  ar.base = reinterpret_cast<char*>(workspace);
+  ar.size = workspace_bytes;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = e.bf16() ? seam_bone_fusion<__nv_bfloat16>(e, stage - 1, uv_left, uv_right, feat_left, feat_right, batch,
+                                                      img_feat_out, ar, st)
+                    : seam_bone_fusion<float>(e, stage - 1, uv_left, uv_right, feat_left, feat_right, batch, img_feat_out,
+                                              ar, st);
+  if (rc == DIRB200_E_WORKSPACE) e.err = "workspace too small";
+  return rc;
+}
+
+template <typename T>
 static int seam_conv(Engine& e, const ConvLayer& L, const float* x, const float* res, int B, int H, int W, float* y,
                      Arena& ar, cudaStream_t st) {
   const int Ho = (H + 2 * L.pad - L.kh) / L.stride + 1, Wo = (W + 2 * L.pad - L.kw) / L.stride + 1;

@@ -814,6 +814,36 @@ void Engine::run_gcn(int s, bool tc, const float* x, float* gh0, float* gh1, con
   launch_gcn_finish(f, st);
 }
 
+// bone_proj x2 -> cat -> fusion conv3x3(2560->256)+BN+ReLU -> conv1x1 (models/dir.py:118-122,146-174,57-62) of stage s:
+// uv from stage_rec, joint features jfeat (B,2,21,64) -> out NHWC (B,S,S,256). Scratch: bone (dense path only), coef, fus_mid.
+template <typename T>
+void Engine::run_bone_fusion(int s, const float* stage_rec, int rec_stride, const float* jfeat, int B, T* bone, float* coef,
+                             T* fus_mid, T* out, cudaStream_t st) {
+  const StageWeights& sw = stage[s];
+  const int S = sw.S;
+  if (dense_fusion) {
+    launch_bone_raster<T>(stage_rec, rec_stride, jfeat, bone, B, S, sw.distance, st);
+    ++launches;
+    conv<T>(sw.fusion0, bone, fus_mid, nullptr, B, S, S, st);
+  } else {
+    const bool coef_tc = std::is_same<T, __nv_bfloat16>::value && sw.fus_wp_tc && !coef_simt;
+    const bool fus_tc = std::is_same<T, __nv_bfloat16>::value && !fusion_simt && (S == 16 || S == 32);
+    const int p_bf16 = coef_tc && fus_tc;  // both ends on the tensor cores: the coefficient tensor travels as bf16
+    if (coef_tc)
+      launch_bone_coef_tc(jfeat, sw.fus_wp_tc, coef, p_bf16, B, st);
+    else
+      launch_bone_coef(jfeat, sw.fus_wp, coef, B, st);
+    if (fus_tc)
+      launch_bone_fusion_tc(stage_rec, rec_stride, coef, p_bf16, sw.fusion0.scale, sw.fusion0.shift,
+                            reinterpret_cast<__nv_bfloat16*>(fus_mid), B, S, sw.distance, st);
+    else
+      launch_bone_fusion<T>(stage_rec, rec_stride, coef, sw.fusion0.scale, sw.fusion0.shift, fus_mid, B, S, sw.distance,
+                            st);
+    launches += 2;
+  }
+  conv<T>(sw.fusion3, fus_mid, out, nullptr, B, S, S, st);
+}
+
 template <typename T>
 int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_stride, const float* prev_para,
                       int prev_para_stride, int B, float* stage_rec, int rec_stride, float* para, int para_stride,
@@ -883,27 +913,7 @@ int Engine::run_stage(int s, const T* img_feat, const float* prev_rec, int prev_
     cudaEventRecord(ev_join[1], side);
     ++launches;
   }
-  if (dense_fusion) {
-    launch_bone_raster<T>(stage_rec, rec_stride, jfeat, bone, B, S, sw.distance, st);
-    ++launches;
-    conv<T>(sw.fusion0, bone, fus_mid, nullptr, B, S, S, st);
-  } else {
-    const bool coef_tc = std::is_same<T, __nv_bfloat16>::value && sw.fus_wp_tc && !coef_simt;
-    const bool fus_tc = std::is_same<T, __nv_bfloat16>::value && !fusion_simt && (S == 16 || S == 32);
-    const int p_bf16 = coef_tc && fus_tc;  // both ends on the tensor cores: the coefficient tensor travels as bf16
-    if (coef_tc)
-      launch_bone_coef_tc(jfeat, sw.fus_wp_tc, coef, p_bf16, B, st);
-    else
-      launch_bone_coef(jfeat, sw.fus_wp, coef, B, st);
-    if (fus_tc)
-      launch_bone_fusion_tc(stage_rec, rec_stride, coef, p_bf16, sw.fusion0.scale, sw.fusion0.shift,
-                            reinterpret_cast<__nv_bfloat16*>(fus_mid), B, S, sw.distance, st);
-    else
-      launch_bone_fusion<T>(stage_rec, rec_stride, coef, sw.fusion0.scale, sw.fusion0.shift, fus_mid, B, S, sw.distance,
-                            st);
-    launches += 2;
-  }
-  conv<T>(sw.fusion3, fus_mid, out, nullptr, B, S, S, st);
+  run_bone_fusion<T>(s, stage_rec, rec_stride, jfeat, B, bone, coef, fus_mid, out, st);
   if (vis_nchw && !vis_on_side) {
     launch_bone_vis_nchw(stage_rec + DIRB200_OFF_UV_L, stage_rec + DIRB200_OFF_UV_R, rec_stride, jfeat, jfeat + 21 * 64,
                          42 * 64, vis_nchw, B, S, sw.distance, 1, st);
@@ -1045,6 +1055,10 @@ template float* Engine::run_residual<float>(const ResidualBlock&, const float*, 
 template __nv_bfloat16* Engine::run_residual<__nv_bfloat16>(const ResidualBlock&, const __nv_bfloat16*,
                                                             const __nv_bfloat16*, int, int, int, Arena&, cudaStream_t,
                                                             const __nv_bfloat16*, int);
+template void Engine::run_bone_fusion<float>(int, const float*, int, const float*, int, float*, float*, float*, float*,
+                                             cudaStream_t);
+template void Engine::run_bone_fusion<__nv_bfloat16>(int, const float*, int, const float*, int, __nv_bfloat16*, float*,
+                                                     __nv_bfloat16*, __nv_bfloat16*, cudaStream_t);
 template int Engine::run_init<float>(const float*, int, float*, int, float*, int, Arena&, cudaStream_t);
 template int Engine::run_init<__nv_bfloat16>(const __nv_bfloat16*, int, float*, int, float*, int, Arena&,
                                              cudaStream_t);

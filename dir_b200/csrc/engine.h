@@ -200,6 +200,9 @@ struct Engine {
   void run_gcn(int s, bool tc, const float* x, float* gh0, float* gh1, const float* prev_rec, int prev_stride, float* y,
                int B, int skip_gpos, cudaStream_t st);
   template <typename T>
+  void run_bone_fusion(int s, const float* stage_rec, int rec_stride, const float* jfeat, int B, T* bone, float* coef,
+                       T* fus_mid, T* out, cudaStream_t st);
+  template <typename T>
   int run_stage(int s, const T* img_feat, const float* prev_rec, int prev_stride, const float* prev_para,
                 int prev_para_stride, int B, float* stage_rec, int rec_stride, float* para, int para_stride,
                 T** img_feat_out, float** joint_feat_out, float* vis_nchw, Arena& ar, cudaStream_t st);

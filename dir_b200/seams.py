@@ -170,6 +170,18 @@ def regressor_offset(model, stage, feat_left, feat_right, para_left, para_right,
     return stage_dict(rec, para)
 
 
+def bone_fusion(model, stage, uv_left, uv_right, feat_left, feat_right):
+    """bone_proj x2 -> cat -> fusion (models/dir.py:118-122): uv (B,21,2), joint features (B,21,64) -> (B,256,S,S)."""
+    args = [_f32(t) for t in (uv_left, uv_right, feat_left, feat_right)]
+    B = args[0].shape[0]
+    h, ws = _prep(model, B)
+    S = 16 if stage == 1 else 32
+    out = torch.empty(B, 256, S, S, device=args[0].device)
+    h.check(h.lib.dirb200_bone_fusion(h.h, stage, *[_ptr(a) for a in args], B, _ptr(out), _ptr(ws), ws.numel(),
+                                      _stream()), "bone_fusion")
+    return out
+
+
 def bone_proj(model, uv, feat, size, distance):
     uv, feat = _f32(uv), _f32(feat)
     B = uv.shape[0]

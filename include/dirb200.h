@@ -161,6 +161,14 @@ int dirb200_regressor_offset(dirb200_handle* h, int stage, const float* feat_lef
 int dirb200_bone_proj(dirb200_handle* h, const float* uv, const float* feat, int batch, int size, float distance,
                       float* out, void* stream);
 
+/* The image-space half of Joint2BoneFeature.forward (models/dir.py:118-122): bone_proj of both hands (:146-174), channel
+ * concat, `fusion` = conv3x3(2560->256) + BN + ReLU + conv1x1 (:57-62). uv (B,21,2) and joint features (B,21,64) per
+ * hand (the output of proj_feat_emb) -> img_feat (B,256,S,S) NCHW. Runs the exact factored form (fusion.cu): fp32
+ * CUDA-core kernels on fp32 handles, the tcgen05 coefficient + accumulate kernels on bf16 handles. */
+int dirb200_bone_fusion(dirb200_handle* h, int stage, const float* uv_left, const float* uv_right,
+                        const float* feat_left, const float* feat_right, int batch, float* img_feat_out, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* One nn.Conv2d (+ its folded eval BatchNorm / bias, optional residual add, ReLU exactly as fused in the
  * forward) by the state_dict key of its weight, e.g. "backbone.layer2.0.conv2.weight"
  * (models/backbone/resnet.py:120-140). x (B,Cin,H,W), res/y (B,Cout,Ho,Wo) NCHW fp32. *used_tensor_cores is

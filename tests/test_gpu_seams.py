@@ -265,3 +265,57 @@ def test_joint2bone_bf16_vs_golden(m16, golden_dir, X):
     d_mm = float((res["pd_mesh_xyz_left"].cpu() - torch.as_tensor(g["pd_mesh_xyz_left"])).norm(dim=-1).mean() * 1000)
     print(f"joint2bone bf16: mean per-vertex drift {d_mm:.3f} mm")
     assert d_mm < 1.0
+
+
+# ------------------------------------------------------------------------------------------ bone_proj -> fusion conv
+def fusion_reference(sd, p, uv_l, uv_r, f_l, f_r, S, distance):
+    """models/dir.py:118-122 with the oracle's pieces: bone_proj x2 -> cat -> conv3x3(2560->256)+BN+ReLU -> conv1x1."""
+    from oracle import dir_oracle as O
+
+    x = torch.cat((O.bone_proj(uv_l, f_l, S, distance), O.bone_proj(uv_r, f_r, S, distance)), 1)
+    x = F.relu(O.bn2d(sd, p + "fusion.1.", O.conv(sd, p + "fusion.0.", x, pad=1)))
+    return O.conv(sd, p + "fusion.3.", x)
+
+
+def _fusion_inputs(B, uv_range, seed):
+    gen = torch.Generator().manual_seed(seed)
+    uv_l = (torch.rand(B, 21, 2, generator=gen) * 2 - 1) * uv_range
+    uv_r = (torch.rand(B, 21, 2, generator=gen) * 2 - 1) * uv_range
+    f_l, f_r = torch.randn(B, 21, 64, generator=gen), torch.randn(B, 21, 64, generator=gen)
+    if uv_range > 0:
+        uv_l[0, 5] = uv_l[0, 0]  # one collapsed bone (a == b: NaN direction in the reference -> empty mask)
+    return uv_l, uv_r, f_l, f_r
+
+
+@pytest.mark.parametrize("stage,S,dist,uv_range", [(1, 16, 1.0, 0.8), (2, 32, 2.0, 0.8), (2, 32, 2.0, 1.4), (1, 16, 1.0, 0.0)])
+def test_bone_fusion_fp32_vs_oracle(m32, synth_sd, stage, S, dist, uv_range):
+    """Exact factored form of the largest op of the network (15.3 GFLOP/img dense) on fp32 handles against the dense
+    reference computation. uv is an INPUT here, so the capsule masks are bit-identical and the comparison is clean."""
+    from dir_b200 import seams
+
+    uv_l, uv_r, f_l, f_r = _fusion_inputs(3, uv_range, 60 + stage)
+    p = "decoder.projecter_4." if stage == 1 else "decoder.projecter_3."
+    want = fusion_reference(synth_sd, p, uv_l, uv_r, f_l, f_r, S, dist)
+    got = seams.bone_fusion(m32, stage, uv_l.cuda(), uv_r.cuda(), f_l.cuda(), f_r.cuda())
+    assert rel(got, want) < TOL32
+
+
+@pytest.mark.parametrize("stage,S,dist,uv_range", [(1, 16, 1.0, 0.8), (2, 32, 2.0, 0.8), (2, 32, 2.0, 1.4)])
+def test_bone_fusion_tcgen05_vs_oracle(m16, synth_sd, stage, S, dist, uv_range):
+    """The kernels the bf16 configuration ships for this op (bone_coef_tc_kernel: kind::tf32; bone_fusion_tc_kernel:
+    kind::f16 with bf16 coefficients and bf16 capsule weights; fusion.3 on conv_tc_kernel) against the REFERENCE
+    computation. Rounding chain on the way to the output: coefficients P -> bf16, capsule weights -> bf16, the 256-channel
+    intermediate -> bf16, fusion.3 weights -> bf16, output -> bf16: five independent 2^-9 relative roundings (the tf32
+    truncations of features and fusion.0 weights are 4x smaller) => first-order bound 5 * 2^-9 = 9.8e-3 of max on the
+    worst element; typical elements average ~50 contributions: mean error below 2^-10 of max. Measured printed."""
+    from dir_b200 import seams
+
+    uv_l, uv_r, f_l, f_r = _fusion_inputs(4, uv_range, 70 + stage)
+    p = "decoder.projecter_4." if stage == 1 else "decoder.projecter_3."
+    want = fusion_reference(synth_sd, p, uv_l, uv_r, f_l, f_r, S, dist)
+    got = seams.bone_fusion(m16, stage, uv_l.cuda(), uv_r.cuda(), f_l.cuda(), f_r.cuda()).cpu()
+    worst = float((got - want).abs().max() / want.abs().max())
+    mean = float((got - want).abs().mean() / want.abs().max())
+    print(f"bone fusion tcgen05 stage {stage} uv_range {uv_range}: worst {worst:.2e} of max, mean {mean:.2e} of max")
+    assert worst < 5 * 2 ** -9
+    assert mean < 2 ** -10
