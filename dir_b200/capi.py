@@ -29,7 +29,8 @@ EXPORTS = [
 
 
 class Config(C.Structure):
-    _fields_ = [("precision", C.c_int), ("max_batch", C.c_int), ("aux_outputs", C.c_int), ("device", C.c_int)]
+    _fields_ = [("precision", C.c_int), ("max_batch", C.c_int), ("aux_outputs", C.c_int), ("device", C.c_int),
+                ("refine_stages", C.c_int)]
 
 
 class Outputs(C.Structure):
@@ -98,9 +99,9 @@ def load_library():
 class Handle:
     """Owns one dirb200_handle*. All methods raise DirB200Error on a non-zero return code."""
 
-    def __init__(self, precision="fp32", max_batch=128, aux_outputs=True, device=0):
+    def __init__(self, precision="fp32", max_batch=128, aux_outputs=True, device=0, refine_stages=2):
         self.lib = load_library()
-        cfg = Config(PRECISION[precision], int(max_batch), int(bool(aux_outputs)), int(device))
+        cfg = Config(PRECISION[precision], int(max_batch), int(bool(aux_outputs)), int(device), int(refine_stages))
         h = C.c_void_p()
         rc = self.lib.dirb200_create(C.byref(cfg), C.byref(h))
         if rc != 0:

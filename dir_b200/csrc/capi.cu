@@ -36,6 +36,14 @@ extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
     g_create_err = "unknown precision";
     return DIRB200_E_INVALID;
   }
+  if (cfg->refine_stages < 0 || cfg->refine_stages > 2) {
+    g_create_err = "refine_stages must be 0 (= 2), 1 or 2: the reference defines two refinement stages (models/dir.py:437-471)";
+    return DIRB200_E_INVALID;
+  }
+  if (cfg->refine_stages == 1 && cfg->aux_outputs) {
+    g_create_err = "refine_stages = 1 needs aux_outputs = 0 (seg/dense/proj_feat hang off the second stage)";
+    return DIRB200_E_INVALID;
+  }
   if (cfg->max_batch <= 0) {
     g_create_err = "max_batch must be positive";
     return DIRB200_E_INVALID;

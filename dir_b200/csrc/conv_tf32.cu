@@ -185,17 +185,20 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           const uint32_t d_main = tmem_base + (g & 1) * BN;
           mbar_wait(&full_bar[s], ph);
-          if (comp) mbar_wait(&split_bar[s], ph);
           fence_after();
           const uint64_t dA = desc128(s32(stage_A(s))), dAlo = desc128(s32(stage_Alo(s)));
           const uint64_t dBhi = desc128(s32(stage_Bhi(s))), dBlo = desc128(s32(stage_Blo(s)));
+          // the eight MMAs that only need the TMA data go first: they cover the splitter's latency
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // +32 B per K=8 step inside the swizzle atom
+          for (int k = 0; k < 4; ++k)  // +32 B per K=8 step inside the swizzle atom
             umma_tf32(d_main, dA + 2 * k, dBhi + 2 * k, ID, (kc | k) ? 1u : 0u);
-            if (comp) {
-              umma_tf32(d_cross, dAlo + 2 * k, dBhi + 2 * k, ID, (kb | k) ? 1u : 0u);
-              umma_tf32(d_cross, dA + 2 * k, dBlo + 2 * k, ID, 1u);
-            }
+          if (comp) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(d_cross, dA + 2 * k, dBlo + 2 * k, ID, (kb | k) ? 1u : 0u);
+            mbar_wait(&split_bar[s], ph);
+            fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(d_cross, dAlo + 2 * k, dBhi + 2 * k, ID, 1u);
           }
           umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have consumed it
           if (kc == CHUNK_KB - 1 || kb == nkb - 1) {

@@ -956,6 +956,20 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   const ResidualBlock& fus4 = res["decoder.fusion_layer4."];
   concat(c4, 2048, 1, c3_skip, 256, fus4, 16, &raw, &act);
   T* fusion4 = run_residual<T>(fus4, raw, act, B, 16, 16, ar, st);
+  if (cfg.refine_stages == 1) {  // "1 refine iter": init regression + projecter_4 only (truncation after models/dir.py:456)
+    T* img_feat1 = nullptr;
+    rc = run_stage<T>(0, fusion4, rec, RS, para, PS, B, plan ? nullptr : rec + DIRB200_STAGE_FLOATS, RS,
+                      plan ? nullptr : para + 128, PS, &img_feat1, nullptr, nullptr, ar, st);
+    if (rc) return rc;
+    if (plan) return DIRB200_OK;
+    if (ar.overflow) return DIRB200_E_WORKSPACE;
+    cudaMemset2DAsync(rec + 2 * DIRB200_STAGE_FLOATS, (size_t)RS * 4, 0, (size_t)DIRB200_STAGE_FLOATS * 4, B, st);
+    cudaMemset2DAsync(para + 256, (size_t)PS * 4, 0, 128 * 4, B, st);
+    last_forward_launches = launches;
+    if (sticky_rc) return sticky_rc;
+    CK(cudaPeekAtLastError());
+    return DIRB200_OK;
+  }
   // skip_layer3 (models/dir.py:459) needs only c2: fork it onto the side stream here, so its convs fill the SMs that
   // stage 1's small joint-space grids (SemGCN, mixSTE, MANO: 64-336 CTAs, latency-bound) leave idle
   const ResidualBlock& skip3 = res["decoder.skip_layer3."];

@@ -74,10 +74,12 @@ class DIR(nn.Module):
     precision 'fp32' (default: the reference's numerics, <=1e-4 relative; error-compensated 3xTF32 tcgen05 convs) |
     'bf16' (explicit opt-in: bf16 feature maps, fastest; drifts like the reference under bf16 autocast, DESIGN.md 2);
     aux_outputs: also return seg/dense/proj_feat (outs_list[3]);
-    max_batch: larger batches are processed in chunks; use_cuda_graph: capture one graph per batch size."""
+    max_batch: larger batches are processed in chunks; use_cuda_graph: capture one graph per batch size;
+    refine_stages: 2 = the reference forward (stage_num 3); 1 = init regression + projecter_4 only ("1 refine iter" of
+    BASELINE.json configs[0]; outs_list then holds two stage dicts; needs aux_outputs=False)."""
 
     def __init__(self, joint_num, mano_path, root_joint=0, precision="fp32", aux_outputs=True, max_batch=128,
-                 use_cuda_graph=False):
+                 use_cuda_graph=False, refine_stages=2):
         super().__init__()
         if joint_num != 21:
             raise ValueError("DIR is defined for the 21-joint hand skeleton (models/dir.py:25-26)")
@@ -89,6 +91,11 @@ class DIR(nn.Module):
         self.aux_outputs = bool(aux_outputs)
         self.max_batch = int(max_batch)
         self.use_cuda_graph = bool(use_cuda_graph)
+        self.refine_stages = int(refine_stages)
+        if self.refine_stages not in (1, 2):
+            raise ValueError("the reference defines two refinement stages (models/dir.py:437-471): refine_stages is 1 or 2")
+        if self.refine_stages == 1 and self.aux_outputs:
+            raise ValueError("refine_stages=1 needs aux_outputs=False (seg/dense/proj_feat hang off the second stage)")
         for name, shape in reference_key_shapes().items():
             parts = name.split(".")
             m = self
@@ -154,7 +161,7 @@ class DIR(nn.Module):
             self._packed = False
             self._workspace = {}
         if self._handle is None:
-            self._handle = capi.Handle(self.precision, self.max_batch, self.aux_outputs, index)
+            self._handle = capi.Handle(self.precision, self.max_batch, self.aux_outputs, index, self.refine_stages)
         return self._handle
 
     def required_keys(self):
@@ -321,7 +328,10 @@ class DIR(nn.Module):
         o = self.run_raw(input["img"])
         aux = {"dense": o["dense"], "seg": o["seg"], "proj_feat": o["proj_feat"]} if self.aux_outputs else \
               {"dense": None, "seg": None, "proj_feat": None}
-        return self.unpack_record(o["record"], aux), {}
+        outs = self.unpack_record(o["record"], aux)
+        if self.refine_stages == 1:
+            outs = outs[:2] + outs[3:]
+        return outs, {}
 
     # ------------------------------------------------------------------ multi-GPU (batch sharding + one all-gather)
     def init_nccl(self, rank, world, broadcast_bytes):

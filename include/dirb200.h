@@ -62,6 +62,10 @@ typedef struct dirb200_config {
   int max_batch;   /* largest per-call batch the handle will be asked for */
   int aux_outputs; /* 1: also compute seg/dense/proj_feat (models/dir.py:474-482,536-540) */
   int device;      /* CUDA device ordinal */
+  int refine_stages; /* 0 or 2: both refinement stages, i.e. the reference forward (stage_num = 3, models/dir.py:437-471);
+                        1: stop after projecter_4 (init regression + one refinement, BASELINE.json configs[0] "1 refine
+                        iter"; needs aux_outputs = 0, the stage-2 slice of the record is zero-filled). The reference has
+                        no further stages, so larger values are rejected. */
 } dirb200_config;
 
 /* Caller-owned output buffers of one forward (device pointers). */

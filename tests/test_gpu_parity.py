@@ -675,3 +675,55 @@ def test_bone_fusion_tensor_core_vs_cuda_core(synth_sd, monkeypatch, stage, S, B
     assert err < 3e-2 and mean < 5e-3
     one, fone = seams.joint2bone(tc, stage, feat[1:2], {k: v[1:2] for k, v in prev.items()})
     assert torch.equal(fone["img_feat"], a[1:2])  # per-image independence, bit-exact
+
+
+def test_one_refine_iteration_config(synth_sd):
+    """BASELINE.json configs[0]: B=1, ResNet-50, "1 refine iter" = init regression + projecter_4 (truncation of the
+    reference forward after models/dir.py:456). refine_stages=1 must reproduce stages 0 and 1 of the full
+    forward and skip everything behind them."""
+    from oracle import dir_oracle as O
+
+    one = _make(synth_sd, "fp32", max_batch=4, aux_outputs=False, refine_stages=1)
+    full = _make(synth_sd, "fp32", max_batch=4, aux_outputs=False)
+    img = torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(11))
+    want = O.dir_forward(synth_sd, img)
+    outs, _ = one({"img": img}, None, None)
+    assert len(outs) == 3 and outs[2]["seg"] is None  # two stage dicts + the (empty) aux dict
+    for i in range(2):
+        for k in O.OUT_KEYS:
+            assert rel(outs[i][k], want[i][k]) < TOL32, (i, k)
+    a, b = one.run_raw(img.cuda()), full.run_raw(img.cuda())
+    n = 2 * 4887
+    assert torch.equal(a["record"][:, :n], b["record"][:, :n])  # same kernels, same bits
+    assert float(a["record"][:, n:].abs().max()) == 0.0
+    h1, h2 = one._handle, full._handle
+    assert h1.lib.dirb200_forward_launches(h1.h, 1) < h2.lib.dirb200_forward_launches(h2.h, 1) - 20
+    import dir_b200
+
+    with pytest.raises(ValueError):
+        dir_b200.DIR(21, "./misc/mano", refine_stages=5)  # the reference has no third refinement stage (SURVEY D2)
+
+
+def test_forward_tf32_matches_what_torch_does_by_default_on_this_gpu(synth_sd):
+    """precision='tf32': fp32 activations, plain TF32 tensor-core convs — the arithmetic PyTorch gives the REFERENCE on
+    this GPU out of the box (torch.backends.cudnn.allow_tf32 defaults to True). Yardstick evaluated here: the oracle's
+    op sequence in PyTorch eager on the same GPU with that default; our drift from the fp32 truth must not exceed 1.5x
+    its drift (both are ~0.5 mm: the tf32 truncation noise of ~60 conv layers)."""
+    from oracle import dir_oracle as O
+
+    m = _make(synth_sd, "tf32", max_batch=16)
+    img = torch.randn(16, 3, 256, 256, generator=torch.Generator().manual_seed(1616))
+    want = O.dir_forward(synth_sd, img)
+    sd_gpu = {k: v.cuda() for k, v in synth_sd.items()}
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        eager = O.dir_forward(sd_gpu, img.cuda())
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    outs, _ = m({"img": img}, None, None)
+    for i in range(3):
+        ours, ref = _mesh_drift_mm(outs, want, i), _mesh_drift_mm(eager, want, i)
+        print(f"tf32 stage {i}: per-vertex drift mean {ours[0]:.3f} mm max {ours[1]:.2f} mm "
+              f"(PyTorch eager with TF32 convs on this GPU: mean {ref[0]:.3f} mm max {ref[1]:.2f} mm)")
+        assert ours[0] <= 1.5 * ref[0] + 0.02, (i, ours, ref)

@@ -48,7 +48,7 @@ def test_create_fails_loudly_without_b200(lib):
 
     if torch.cuda.is_available():
         pytest.skip("GPU present")
-    cfg = capi.Config(0, 8, 1, 0)
+    cfg = capi.Config(0, 8, 1, 0, 2)
     h = ctypes.c_void_p()
     rc = lib.dirb200_create(ctypes.byref(cfg), ctypes.byref(h))
     assert rc == -3 and not h.value
@@ -56,7 +56,7 @@ def test_create_fails_loudly_without_b200(lib):
     m = dir_b200.DIR(21, "./misc/mano")
     with pytest.raises(dir_b200.DirB200Error):
         m({"img": torch.zeros(1, 3, 256, 256)}, None, None)
-    bad = capi.Config(7, 8, 1, 0)
+    bad = capi.Config(7, 8, 1, 0, 2)
     assert lib.dirb200_create(ctypes.byref(bad), ctypes.byref(h)) == -1  # unknown precision
 
 
