@@ -439,6 +439,7 @@ def main():
                 "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak, "traffic": traffic,
                 "peak_source": f"{peak_note}; {pk['source']}",
                 "frac_of_sustained_peak": ach / pk["sustained"] if args.precision == "bf16" else None,
+                "algorithmic_bytes_per_launch": sum(r["bytes"] for r in tc_rows) / n_launch,
                 "launches_timed": n_launch, "avg_launch_ms": fam_ms / n_launch,
                 "share_of_step": fam_ms / prof_steps / (ms / K),
                 "how": f"CUDA events on the launch stream around every launch, {prof_steps} steps after the timed region"}
