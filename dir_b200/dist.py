@@ -85,8 +85,19 @@ def bind_to_gpu_numa_node(local_rank: int):
         cpus &= allowed
         if not cpus:
             return {"gpu": bdf, "numa_node": node, "bound": False, "why": "no local cpu is in this process' cpuset"}
-        os.sched_setaffinity(0, cpus)
-        torch.set_num_threads(max(1, min(len(cpus), 8)))
-        return {"gpu": bdf, "numa_node": node, "bound": True, "cpus": len(cpus), "of_allowed": len(allowed)}
+        # several ranks share these cores (always the case on a single-node VM): give each rank its own slice, so that
+        # eight Python main threads, their NCCL proxy threads and the copy-engine interrupt handlers do not migrate
+        # over each other
+        nlocal = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        ordered = sorted(cpus)
+        share = len(ordered) // max(nlocal, 1)
+        if nlocal > 1 and share >= 2:
+            mine = set(ordered[local_rank * share:(local_rank + 1) * share])
+        else:
+            mine = cpus
+        os.sched_setaffinity(0, mine)
+        torch.set_num_threads(max(1, min(len(mine), 8)))
+        return {"gpu": bdf, "numa_node": node, "bound": True, "cpus": len(mine), "local_cpus": len(cpus),
+                "of_allowed": len(allowed)}
     except (OSError, ValueError, AttributeError, RuntimeError) as e:
         return {"bound": False, "why": f"{type(e).__name__}: {e}"}
