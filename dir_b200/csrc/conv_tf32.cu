@@ -25,7 +25,8 @@
 // Stem variant (7x7 stride 2, Cin = 3; models/backbone/resnet.py:176): the image is repacked to a zero-padded NHWC4
 //   fp32 buffer; a k-block is one kernel row (8 px x 4 ch = 32 floats = 128 B) and the A box comes from an
 //   OVERLAPPING-stride TMA view of that buffer (consecutive output pixels are 2 px = 32 B apart).
-// nsplit = 1 runs the same pipeline as plain TF32 (one MMA per k-step, what PyTorch's cuDNN default does on this GPU).
+// nsplit = 1 runs the same pipeline as plain TF32 (one MMA per k-step, what PyTorch's cuDNN default does on this GPU); the
+// splitter warps then round the A tile to tf32 in place (nearest-even), because the MMA's own truncation is one-sided.
 #include <cuda.h>
 
 #include <cstdio>
@@ -50,6 +51,7 @@ constexpr int EPI_THREADS = 256;
 constexpr int MAX_STAGES = 4;
 constexpr int CHUNK_KB = 2;     // k-blocks accumulated in TMEM before promotion (2 x 4 k-steps = 8 MMAs)
 constexpr int A_TILE = BM * 128;
+constexpr int OUT_STAGE = BM * 128;  // epilogue staging of one 32-column fp32 box (128B-swizzled), one per epilogue group
 
 struct T32Args {
   const float* scale;
@@ -71,21 +73,22 @@ struct Cfg32 {
   static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;  // A, A_lo, W_hi, W_lo
   static constexpr uint32_t TMEM_COLS = 4 * BN;                // main[2] (ping-pong per chunk) + cross[2] (per tile)
   static int stages() {
-    int s = (220 * 1024) / STAGE_BYTES;
+    int s = (192 * 1024) / STAGE_BYTES;
     return s > MAX_STAGES ? MAX_STAGES : s;
   }
-  static int smem_bytes(int stages) { return 1024 + stages * STAGE_BYTES + 2 * BN * 4 + 256; }
+  static int smem_bytes(int stages) { return 1024 + stages * STAGE_BYTES + 2 * OUT_STAGE + 2 * BN * 4 + 256; }
 };
 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-                 const __grid_constant__ CUtensorMap tmBlo, const T32Args a) {
+                 const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmY, const T32Args a) {
   using Cfg = Cfg32<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = a.stages;
-  float* s_scale = reinterpret_cast<float*>(smem + stages * Cfg::STAGE_BYTES);  // affine of the current n-tile
+  uint8_t* s_out = smem + stages * Cfg::STAGE_BYTES;  // 2 x 16 KB output staging (one per epilogue group)
+  float* s_scale = reinterpret_cast<float*>(s_out + 2 * OUT_STAGE);  // affine of the current n-tile
   float* s_shift = s_scale + BN;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN);
   uint64_t* full_bar = bars;                      // TMA bytes of a stage have landed
@@ -105,6 +108,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmBhi);
     tma_prefetch_desc(&tmBlo);
+    tma_prefetch_desc(&tmY);
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -185,6 +189,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           const uint32_t d_main = tmem_base + (g & 1) * BN;
           mbar_wait(&full_bar[s], ph);
+          if (!comp) mbar_wait(&split_bar[s], ph);  // plain TF32: the splitter rounds the A tile in place first
           fence_after();
           const uint64_t dA = desc128(s32(stage_A(s))), dAlo = desc128(s32(stage_Alo(s)));
           const uint64_t dBhi = desc128(s32(stage_Bhi(s))), dBlo = desc128(s32(stage_Blo(s)));
@@ -213,8 +218,10 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp < 6) {
-    // ===================== splitter: A_lo[i] = rn_tf32(A[i] - trunc_tf32(A[i])), same byte position in its own tile
-    if (comp) {
+    // ===================== splitter. 3xTF32: A_lo[i] = rn_tf32(A[i] - trunc_tf32(A[i])), same byte position in its own
+    // tile. Plain TF32: A[i] = rn_tf32(A[i]) in place — the MMA would TRUNCATE, a one-sided 2^-11 relative error per
+    // operand that compounds through ~60 layers into a 5x larger drift than round-to-nearest (what cuDNN's TF32 does).
+    {
       const int tid = threadIdx.x - 64;
       int s = 0;
       uint32_t ph = 0;
@@ -222,16 +229,20 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           const uint4* src = reinterpret_cast<const uint4*>(stage_A(s));
-          uint4* dst = reinterpret_cast<uint4*>(stage_Alo(s));
+          uint4* dst = reinterpret_cast<uint4*>(comp ? stage_Alo(s) : stage_A(s));
 #pragma unroll
           for (int i = 0; i < A_TILE / 16 / 128; ++i) {
             uint4 v = src[tid + i * 128];
             uint32_t* e = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float x = __uint_as_float(e[j]);
-              const float lo = x - __uint_as_float(e[j] & 0xFFFFE000u);  // exact; the MMA truncates x the same way
-              e[j] = (__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u;      // round to tf32 (the MMA would truncate)
+              if (comp) {
+                const float x = __uint_as_float(e[j]);
+                const float lo = x - __uint_as_float(e[j] & 0xFFFFE000u);  // exact; the MMA truncates x the same way
+                e[j] = (__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u;      // round to tf32 (the MMA would truncate)
+              } else {
+                e[j] = (e[j] + 0xFFFu + ((e[j] >> 13) & 1u)) & 0xFFFFE000u;  // round-to-nearest-even to tf32
+              }
             }
             dst[tid + i * 128] = v;
           }
@@ -297,46 +308,62 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_before();
         mbar_arrive(&cross_empty[t & 1]);
       }
-      const int m = m0 + lane_base + lane;
-      if (m < a.M) {
-        float* yrow = a.y + (size_t)m * a.Cout + n0 + half * HN;
-        const float* rrow = a.res ? a.res + (size_t)m * a.Cout + n0 + half * HN : nullptr;
-        const float* sc = s_scale + half * HN;
-        const float* sh = s_shift + half * HN;
+      // epilogue: 32 columns at a time through the group's 128B-swizzled staging buffer, written out by one TMA store
+      // (whole 128-byte lines; rows beyond M are clipped by the tensor map)
+      const int row = lane_base + lane;
+      const int m = m0 + row;
+      const bool live = m < a.M;
+      const float* rrow = (a.res && live) ? a.res + (size_t)m * a.Cout + n0 + half * HN : nullptr;
+      const float* sc = s_scale + half * HN;
+      const float* sh = s_shift + half * HN;
+      uint8_t* stg = s_out + half * OUT_STAGE + row * 128;
+      const uint32_t swz = (uint32_t)(row & 7);
+      const int gt = et & 127;  // thread index inside the group
 #pragma unroll
-        for (int jb = 0; jb < HN; jb += 32) {  // 32 columns = eight 16-byte loads in flight per thread
-          float4 r[8];
+      for (int jb = 0; jb < HN; jb += 32) {
+        float4 r[8];
+        if (rrow) {  // eight 16-byte loads in flight per thread
+#pragma unroll
+          for (int q = 0; q < 8; ++q) r[q] = __ldg(reinterpret_cast<const float4*>(rrow + jb + q * 4));
+        }
+        if (gt == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has read the buffer
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int j = jb + q * 4;
+          const float4 s4 = *reinterpret_cast<const float4*>(sc + j);
+          const float4 h4 = *reinterpret_cast<const float4*>(sh + j);
+          float4 o;
+          o.x = fmaf(acc[j + 0], s4.x, h4.x);
+          o.y = fmaf(acc[j + 1], s4.y, h4.y);
+          o.z = fmaf(acc[j + 2], s4.z, h4.z);
+          o.w = fmaf(acc[j + 3], s4.w, h4.w);
           if (rrow) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) r[q] = __ldg(reinterpret_cast<const float4*>(rrow + jb + q * 4));
+            o.x += r[q].x;
+            o.y += r[q].y;
+            o.z += r[q].z;
+            o.w += r[q].w;
           }
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int j = jb + q * 4;
-            const float4 s4 = *reinterpret_cast<const float4*>(sc + j);
-            const float4 h4 = *reinterpret_cast<const float4*>(sh + j);
-            float4 o;
-            o.x = fmaf(acc[j + 0], s4.x, h4.x);
-            o.y = fmaf(acc[j + 1], s4.y, h4.y);
-            o.z = fmaf(acc[j + 2], s4.z, h4.z);
-            o.w = fmaf(acc[j + 3], s4.w, h4.w);
-            if (rrow) {
-              o.x += r[q].x;
-              o.y += r[q].y;
-              o.z += r[q].z;
-              o.w += r[q].w;
-            }
-            if (a.relu) {
-              o.x = fmaxf(o.x, 0.f);
-              o.y = fmaxf(o.y, 0.f);
-              o.z = fmaxf(o.z, 0.f);
-              o.w = fmaxf(o.w, 0.f);
-            }
-            *reinterpret_cast<float4*>(yrow + j) = o;
+          if (a.relu) {
+            o.x = fmaxf(o.x, 0.f);
+            o.y = fmaxf(o.y, 0.f);
+            o.z = fmaxf(o.z, 0.f);
+            o.w = fmaxf(o.w, 0.f);
           }
+          *reinterpret_cast<float4*>(stg + (((uint32_t)q ^ swz) << 4)) = o;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> TMA (async proxy) reads
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+        if (gt == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmY)),
+                       "r"(s32(s_out + half * OUT_STAGE)), "r"(n0 + half * HN + jb), "r"(m0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
     }
+    if ((et & 127) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output bytes written
   }
   fence_before();
   __syncthreads();
@@ -424,9 +451,29 @@ bool act_map32_cached(const float* x, int B, int H, int W, int C, int stride, co
   return true;
 }
 
+// fp32 [rows][cols] row-major as 32-column x 128-row boxes with 128B swizzle (epilogue store)
+bool out_map32_cached(const float* y, int rows, int cols, CUtensorMap* out) {
+  typedef std::tuple<const void*, int, int> Key;
+  static thread_local tma::MapCache<Key> cache;
+  Key key(y, rows, cols);
+  if (cache.find(key, out)) return true;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)BM};
+  cuuint32_t es[2] = {1, 1};
+  if (tma::get_encode()(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(y), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  cache.put(key, *out);
+  return true;
+}
+
 template <int BN>
 int launch_t32(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, T32Args a, cudaStream_t st) {
   using Cfg = Cfg32<BN>;
+  CUtensorMap tmY;
+  if (!out_map32_cached(a.y, a.M, a.Cout, &tmY)) return DIRB200_E_CUDA;
   a.stages = Cfg::stages();
   const int smem = Cfg::smem_bytes(a.stages);
   if (ensure_dynamic_smem(reinterpret_cast<const void*>(conv_tf32_kernel<BN>), smem) != cudaSuccess) return DIRB200_E_CUDA;
@@ -442,7 +489,7 @@ int launch_t32(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorM
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  if (cudaLaunchKernelEx(&cfg, conv_tf32_kernel<BN>, tmA, tmBhi, tmBlo, a) != cudaSuccess) return DIRB200_E_CUDA;
+  if (cudaLaunchKernelEx(&cfg, conv_tf32_kernel<BN>, tmA, tmBhi, tmBlo, tmY, a) != cudaSuccess) return DIRB200_E_CUDA;
   return DIRB200_OK;
 }
 
