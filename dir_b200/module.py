@@ -74,7 +74,8 @@ class DIR(nn.Module):
     precision 'fp32' (default: the reference's numerics, <=1e-4 relative; error-compensated 3xTF32 tcgen05 convs) |
     'bf16' (explicit opt-in: bf16 feature maps, fastest; drifts like the reference under bf16 autocast, DESIGN.md 2);
     aux_outputs: also return seg/dense/proj_feat (outs_list[3]);
-    max_batch: larger batches are processed in chunks; use_cuda_graph: capture one graph per batch size;
+    max_batch: larger batches are processed in chunks; use_cuda_graph: capture the forward once per batch size and replay
+    it (the returned tensors are then the graph's own output buffers, double-buffered: valid until the call after next);
     refine_stages: 2 = the reference forward (stage_num 3); 1 = init regression + projecter_4 only ("1 refine iter" of
     BASELINE.json configs[0]; outs_list then holds two stage dicts; needs aux_outputs=False)."""
 
@@ -230,19 +231,26 @@ class DIR(nn.Module):
             return o
         key = (B, x.dtype)
         if key not in self._graphs:
-            sx = torch.empty_like(x)
-            so = self._alloc_outputs(B)
-            sx.copy_(x)
-            self._enqueue(sx, so)  # warm-up outside capture (sets function attributes)
-            torch.cuda.current_stream().synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._enqueue(sx, so)
-            self._graphs[key] = (g, sx, so)
-        g, sx, so = self._graphs[key]
+            # two complete (graph, static input, static outputs) sets used alternately: the outputs of call i stay valid
+            # until call i+2, so nothing has to be cloned out of the graph's buffers (proj_feat alone is 671 MB at B=128)
+            sets = []
+            for _ in range(2):
+                sx = torch.empty_like(x)
+                so = self._alloc_outputs(B)
+                sx.copy_(x)
+                self._enqueue(sx, so)  # warm-up outside capture (sets function attributes)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue(sx, so)
+                sets.append((g, sx, so))
+            self._graphs[key] = {"sets": sets, "next": 0}
+        entry = self._graphs[key]
+        g, sx, so = entry["sets"][entry["next"]]
+        entry["next"] ^= 1
         sx.copy_(x)
         g.replay()
-        return {k: v.clone() for k, v in so.items()}
+        return so
 
     def _to_device(self, img):
         """models/dir.py:514 does `input['img'].cuda()` on the compute stream. Host tensors are uploaded on a

@@ -114,7 +114,7 @@ def main():
     whole("oracle host bf16 autocast", lambda i: {k: v.float() for k, v in o[i].items() if v is not None})
 
     # ---- our seams, each fed with ground-truth inputs
-    for precision in ("fp32", "bf16"):
+    for precision in ("fp32", "tf32", "bf16"):
         net = dir_b200.DIR(21, "./misc/mano", precision=precision).to(dev)
         net.load_state_dict(sd, strict=False)
         net.eval()

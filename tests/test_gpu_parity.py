@@ -415,9 +415,15 @@ def test_cuda_graph_replay_matches_eager(synth_sd, X):
     e = _make(synth_sd, "fp32", max_batch=8)
     img = X["img"].cuda()
     want = e.run_raw(img)
-    for _ in range(2):
+    for _ in range(3):  # both graph sets, then the first one again
         got = m.run_raw(img)
         assert torch.equal(got["record"], want["record"]) and torch.equal(got["proj_feat"], want["proj_feat"])
+    # outputs are the graph's own double-buffered tensors: call i stays intact across call i+1
+    first = m.run_raw(img)
+    keep = first["record"].clone()
+    other = m.run_raw(torch.flip(img, dims=[0]))
+    assert torch.equal(first["record"], keep) and not torch.equal(other["record"], keep)
+    assert torch.equal(other["record"], want["record"].flip(0))
 
 
 def test_factored_fusion_equals_dense_path(synth_sd, X, monkeypatch):
