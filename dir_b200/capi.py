@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DIRB200_LIB") or os.path.join(_HERE, "libdirb200.so")  # override: A/B of builds
 
 PRECISION = {"fp32": 0, "bf16": 1, "tf32": 2}
+BACKBONE = {"resnet50": 0, "hrnet_w32": 32}
 DTYPE_F32, DTYPE_I64 = 0, 1
 STAGE_FLOATS = 4887
 RECORD_FLOATS = 3 * STAGE_FLOATS
@@ -30,7 +31,7 @@ EXPORTS = [
 
 class Config(C.Structure):
     _fields_ = [("precision", C.c_int), ("max_batch", C.c_int), ("aux_outputs", C.c_int), ("device", C.c_int),
-                ("refine_stages", C.c_int)]
+                ("refine_stages", C.c_int), ("backbone", C.c_int)]
 
 
 class Outputs(C.Structure):
@@ -99,9 +100,10 @@ def load_library():
 class Handle:
     """Owns one dirb200_handle*. All methods raise DirB200Error on a non-zero return code."""
 
-    def __init__(self, precision="fp32", max_batch=128, aux_outputs=True, device=0, refine_stages=2):
+    def __init__(self, precision="fp32", max_batch=128, aux_outputs=True, device=0, refine_stages=2, backbone="resnet50"):
         self.lib = load_library()
-        cfg = Config(PRECISION[precision], int(max_batch), int(bool(aux_outputs)), int(device), int(refine_stages))
+        cfg = Config(PRECISION[precision], int(max_batch), int(bool(aux_outputs)), int(device), int(refine_stages),
+                     BACKBONE[backbone])
         h = C.c_void_p()
         rc = self.lib.dirb200_create(C.byref(cfg), C.byref(h))
         if rc != 0:

@@ -40,6 +40,10 @@ extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
     g_create_err = "refine_stages must be 0 (= 2), 1 or 2: the reference defines two refinement stages (models/dir.py:437-471)";
     return DIRB200_E_INVALID;
   }
+  if (cfg->backbone != 0 && cfg->backbone != 32) {
+    g_create_err = "backbone must be 0 (ResNet-50, the reference) or 32 (HRNet-W32 extension)";
+    return DIRB200_E_INVALID;
+  }
   if (cfg->refine_stages == 1 && cfg->aux_outputs) {
     g_create_err = "refine_stages = 1 needs aux_outputs = 0 (seg/dense/proj_feat hang off the second stage)";
     return DIRB200_E_INVALID;
@@ -243,12 +247,15 @@ template <typename T>
 static int seam_backbone(Engine& e, const float* img, int B, int H, int W, float* c1, float* c2, float* c3, float* c4,
                          Arena& ar, cudaStream_t st) {
   T *t1 = nullptr, *t2 = nullptr, *t3 = nullptr, *t4 = nullptr;
-  int rc = e.run_backbone<T>(img, B, H, W, ar, &t1, &t2, &t3, &t4, st);
+  if (e.hrnet() && (H != 256 || W != 256)) return DIRB200_E_INVALID;
+  int rc = e.hrnet() ? e.run_backbone_hrnet<T>(img, B, ar, &t1, &t2, &t3, &t4, st)
+                     : e.run_backbone<T>(img, B, H, W, ar, &t1, &t2, &t3, &t4, st);
   if (rc) return rc;
-  launch_nhwc_to_nchw<T>(t1, c1, B, 256, H / 4, W / 4, st);
-  launch_nhwc_to_nchw<T>(t2, c2, B, 512, H / 8, W / 8, st);
-  launch_nhwc_to_nchw<T>(t3, c3, B, 1024, H / 16, W / 16, st);
-  launch_nhwc_to_nchw<T>(t4, c4, B, 2048, H / 32, W / 32, st);
+  // packed channel counts (HRNet: the 32-channel branch is stored in 64 channels, the upper half exactly zero)
+  launch_nhwc_to_nchw<T>(t1, c1, B, e.c1ch, H / 4, W / 4, st);
+  launch_nhwc_to_nchw<T>(t2, c2, B, e.c2ch, H / 8, W / 8, st);
+  launch_nhwc_to_nchw<T>(t3, c3, B, e.c3ch, H / 16, W / 16, st);
+  launch_nhwc_to_nchw<T>(t4, c4, B, e.c4ch, H / 32, W / 32, st);
   return DIRB200_OK;
 }
 
@@ -302,9 +309,9 @@ extern "C" int dirb200_residual(dirb200_handle* h, const char* name, const float
 
 template <typename T>
 static int seam_init(Engine& e, const float* c4, int B, float* rec, float* para, Arena& ar, cudaStream_t st) {
-  T* x = reinterpret_cast<T*>(ar.alloc((size_t)B * 64 * 2048 * sizeof(T)));
+  T* x = reinterpret_cast<T*>(ar.alloc((size_t)B * 64 * e.c4ch * sizeof(T)));
   if (ar.overflow) return DIRB200_E_WORKSPACE;
-  launch_nchw_to_nhwc<T>(c4, x, B, 2048, 8, 8, st);
+  launch_nchw_to_nhwc<T>(c4, x, B, e.c4ch, 8, 8, st);
   return e.run_init<T>(x, B, rec, DIRB200_STAGE_FLOATS, para, 128, ar, st);
 }
 

@@ -273,17 +273,19 @@ __global__ void fold_affine_kernel(const float* cb, const float* g, const float*
   shift[i] = h;
 }
 
+// Cout/Cin = packed (possibly zero-padded) channel counts, Cout_src/Cin_src = the tensor's own
 __global__ void pack_conv_weight_kernel(const float* __restrict__ src, float* __restrict__ d32,
-                                        __nv_bfloat16* __restrict__ d16, int Cout, int Cin, int kh, int kw, int Kpad) {
+                                        __nv_bfloat16* __restrict__ d16, int Cout, int Cin, int kh, int kw, int Kpad,
+                                        int Cout_src, int Cin_src) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)Cout * Kpad) return;
   int k = (int)(idx % Kpad);
   int n = (int)(idx / Kpad);
   float v = 0.f;
-  if (k < kh * kw * Cin) {
+  if (k < kh * kw * Cin && n < Cout_src) {
     int tap = k / Cin, ci = k - tap * Cin;
     int ky = tap / kw, kx = tap - ky * kw;
-    v = src[(((int64_t)n * Cin + ci) * kh + ky) * kw + kx];
+    if (ci < Cin_src) v = src[(((int64_t)n * Cin_src + ci) * kh + ky) * kw + kx];
   }
   if (d32) d32[idx] = v;
   if (d16) d16[idx] = __float2bfloat16_rn(v);
@@ -369,11 +371,11 @@ __global__ void attn_logits_kernel(const T* __restrict__ a, const float* __restr
 // a sequential sum only in association (fp32).
 template <typename T>
 __global__ void __launch_bounds__(256) attn_pool_kernel(const T* __restrict__ f, const float* __restrict__ attn,
-                                                        float* __restrict__ pooled, int P, int C) {
+                                                        float* __restrict__ pooled, int P, int C, int chunk) {
   pdl_wait();
   extern __shared__ float sa[];  // [P][2] attention, then [4][3][512] partial sums
   float* part = sa + P * 2;
-  const int b = blockIdx.x, c0 = blockIdx.y * 512;
+  const int b = blockIdx.x, c0 = blockIdx.y * chunk;  // chunk = channels per block: 512, or 256 for narrow maps
   for (int i = threadIdx.x; i < P * 2; i += blockDim.x) sa[i] = attn[(int64_t)b * P * 2 + i];
   __syncthreads();
   const int g = threadIdx.x & 63, q = threadIdx.x >> 6;
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(256) attn_pool_kernel(const T* __restrict__ f,
   for (int i = 0; i < 8; ++i) al[i] = ar[i] = am[i] = 0.f;
   const T* base = f + ((int64_t)b * P + q * pq) * C + c0 + g * 8;
 #pragma unroll 4
-  for (int p = 0; p < pq; ++p) {
+  for (int p = 0; p < (g * 8 < chunk ? pq : 0); ++p) {
     float v[8];
     Vec8<T>::ld(base + (int64_t)p * C, v);
     const float wl = sa[(q * pq + p) * 2], wr = sa[(q * pq + p) * 2 + 1];
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(256) attn_pool_kernel(const T* __restrict__ f,
     sl += sa[p * 2];
     sr += sa[p * 2 + 1];
   }
-  for (int c = threadIdx.x; c < 512; c += blockDim.x) {
+  for (int c = threadIdx.x; c < chunk; c += blockDim.x) {
     float tl = 0.f, tr = 0.f, tm = 0.f;
 #pragma unroll
     for (int qq = 0; qq < 4; ++qq) {
@@ -473,10 +475,68 @@ void launch_fold_affine(const float* cb, const float* g, const float* be, const 
 }
 
 void launch_pack_conv_weight(const float* src, float* d32, __nv_bfloat16* d16, int Cout, int Cin, int kh, int kw,
-                             int Kpad, cudaStream_t st) {
+                             int Kpad, cudaStream_t st, int Cout_src, int Cin_src) {
   int64_t total = (int64_t)Cout * Kpad;
-  pack_conv_weight_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(src, d32, d16, Cout, Cin, kh, kw, Kpad);
+  pack_conv_weight_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(src, d32, d16, Cout, Cin, kh, kw, Kpad,
+                                                                            Cout_src > 0 ? Cout_src : Cout,
+                                                                            Cin_src > 0 ? Cin_src : Cin);
 }
+
+// HRNet fuse layer: out = relu(sum_k up_nearest(term_k, 2^shift_k)), NHWC, all terms with C channels
+struct FuseArgs {
+  const void* term[4];
+  int shift[4];
+  int nterm;
+  void* out;
+  int B, H, W, C;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) fuse_sum_relu_kernel(FuseArgs a) {
+  pdl_wait();
+  const int c4n = a.C >> 2;
+  const int64_t total = (int64_t)a.B * a.H * a.W * c4n;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % c4n) * 4;
+  int64_t t = idx / c4n;
+  const int w = (int)(t % a.W);
+  t /= a.W;
+  const int h = (int)(t % a.H), b = (int)(t / a.H);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < a.nterm; ++k) {
+    const int sh = a.shift[k];
+    const int Hk = a.H >> sh, Wk = a.W >> sh;
+    const T* p = reinterpret_cast<const T*>(a.term[k]) + (((int64_t)b * Hk + (h >> sh)) * Wk + (w >> sh)) * a.C + c;
+    const float4 v = ActIO<T>::ld4(p);
+    s.x += v.x;
+    s.y += v.y;
+    s.z += v.z;
+    s.w += v.w;
+  }
+  s.x = fmaxf(s.x, 0.f);
+  s.y = fmaxf(s.y, 0.f);
+  s.z = fmaxf(s.z, 0.f);
+  s.w = fmaxf(s.w, 0.f);
+  ActIO<T>::st4(reinterpret_cast<T*>(a.out) + idx * 4, s);
+}
+
+template <typename T>
+void launch_fuse_sum_relu(const T* const* terms, const int* shifts, int nterm, T* out, int B, int H, int W, int C,
+                          cudaStream_t st) {
+  FuseArgs a{};
+  for (int k = 0; k < nterm; ++k) {
+    a.term[k] = terms[k];
+    a.shift[k] = shifts[k];
+  }
+  a.nterm = nterm;
+  a.out = out;
+  a.B = B; a.H = H; a.W = W; a.C = C;
+  const int64_t total = (int64_t)B * H * W * (C / 4);
+  launch_pdl(fuse_sum_relu_kernel<T>, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, st, a);
+}
+template void launch_fuse_sum_relu<float>(const float* const*, const int*, int, float*, int, int, int, int, cudaStream_t);
+template void launch_fuse_sum_relu<__nv_bfloat16>(const __nv_bfloat16* const*, const int*, int, __nv_bfloat16*, int, int,
+                                                  int, int, cudaStream_t);
 
 void launch_transpose2d(const float* src, float* dst, int rows, int cols, cudaStream_t st) {
   dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
@@ -498,9 +558,10 @@ void launch_attn_logits(const T* a, const float* w, const float* bias, float* at
 
 template <typename T>
 void launch_attn_pool(const T* f, const float* attn, float* pooled, int B, int P, int C, cudaStream_t st) {
-  // C is a multiple of 512 and P of 4 for every caller (2048 channels, 8x8 map; models/dir.py:263-268)
-  launch_pdl(attn_pool_kernel<T>, dim3(B, C / 512), dim3(256), (P * 2 + 4 * 3 * 512) * sizeof(float), st, f, attn, pooled,
-             P, C);
+  // C is a multiple of 256 and P of 4 for every caller (2048 channels, 8x8 map; models/dir.py:263-268; 256 for HRNet-W32)
+  const int chunk = C % 512 == 0 ? 512 : 256;
+  launch_pdl(attn_pool_kernel<T>, dim3(B, C / chunk), dim3(256), (P * 2 + 4 * 3 * 512) * sizeof(float), st, f, attn, pooled,
+             P, C, chunk);
 }
 
 #define INST(T)                                                                                                      \

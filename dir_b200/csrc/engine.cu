@@ -146,6 +146,10 @@ void Engine::fold(const std::string& conv_bias, const std::string& bn, float** s
   if (!*scale) {
     *scale = dalloc(total);
     *shift = dalloc(total);
+    if (*scale && *shift) {  // channels nobody folds into (zero padding) must produce exact zeros
+      cudaMemsetAsync(*scale, 0, (size_t)total * sizeof(float), fin_stream);
+      cudaMemsetAsync(*shift, 0, (size_t)total * sizeof(float), fin_stream);
+    }
   }
   if (!*scale || !*shift || !err.empty()) return;
   launch_fold_affine(cb, g, be, mu, var, *scale + off, *shift + off, n, fin_stream);
@@ -154,7 +158,7 @@ void Engine::fold(const std::string& conv_bias, const std::string& bn, float** s
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 ConvLayer Engine::make_conv(const std::string& wname, const std::string& bias, const std::string& bn, int stride,
-                            int pad, int relu) {
+                            int pad, int relu, int cin_pad, int cout_pad) {
   ConvLayer L;
   L.name = wname;
   const float* w = W(wname);
@@ -171,16 +175,22 @@ ConvLayer Engine::make_conv(const std::string& wname, const std::string& bias, c
     if (err.empty()) err = "conv weight must be 4-D: " + wname;
     return L;
   }
-  L.Cout = (int)sh[0];
-  L.Cin = (int)sh[1];
+  const int cout_src = (int)sh[0], cin_src = (int)sh[1];
+  L.Cout = cout_pad > 0 ? cout_pad : cout_src;
+  L.Cin = cin_pad > 0 ? cin_pad : cin_src;
+  if (L.Cout < cout_src || L.Cin < cin_src) {
+    if (err.empty()) err = "channel padding smaller than the tensor: " + wname;
+    return L;
+  }
   L.kh = (int)sh[2];
   L.kw = (int)sh[3];
   L.K = L.kh * L.kw * L.Cin;
   L.Kpad = round_up(L.K, 16);
   L.w32 = dalloc((size_t)L.Cout * L.Kpad);
   if (bf16()) L.w16 = reinterpret_cast<__nv_bfloat16*>(dalloc(((size_t)L.Cout * L.Kpad + 1) / 2));
-  if (L.w32) launch_pack_conv_weight(w, L.w32, L.w16, L.Cout, L.Cin, L.kh, L.kw, L.Kpad, fin_stream);
-  fold(bias, bn, &L.scale, &L.shift, L.Cout);
+  if (L.w32)
+    launch_pack_conv_weight(w, L.w32, L.w16, L.Cout, L.Cin, L.kh, L.kw, L.Kpad, fin_stream, cout_src, cin_src);
+  fold(bias, bn, &L.scale, &L.shift, cout_src, 0, L.Cout);
   if (bf16() && L.w16 && err.empty()) conv_tc_prepare_weights(L);
   if (!bf16() && err.empty()) prepare_tf32(L);
   return L;
@@ -383,39 +393,43 @@ int Engine::build(cudaStream_t st) {
       cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming);
     }
   }
-  // ---- backbone (models/backbone/resnet.py)
-  stem = make_conv("backbone.conv1.weight", "", "backbone.bn1.", 2, 3, 1);
-  if (!dry && bf16() && err.empty()) {
-    __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(dalloc(64 * 224 / 2));
-    if (wp) conv_tc_prepare_stem(stem, W("backbone.conv1.weight"), wp, st);
-    float* sp = dalloc(stem_pool_weight_bytes() / 4);
-    if (sp) launch_pack_stem_pool_weight(W("backbone.conv1.weight"), sp, st);
-    stem_pool_w = sp;
-  }
-  if (!dry && !bf16() && err.empty()) {
-    float* buf = dalloc(conv_tf32_stem_weight_floats());
-    if (buf) conv_tf32_prepare_stem(stem, W("backbone.conv1.weight"), buf, st);
-  }
-  const int nblocks[4] = {3, 4, 6, 3};
-  for (int l = 0; l < 4; ++l) {
-    layers[l].clear();
-    for (int b = 0; b < nblocks[l]; ++b) {
-      std::string p = "backbone.layer" + std::to_string(l + 1) + "." + std::to_string(b) + ".";
-      Bottleneck bk;
-      int stride = (b == 0 && l > 0) ? 2 : 1;
-      bk.c1 = make_conv(p + "conv1.weight", "", p + "bn1.", 1, 0, 1);
-      bk.c2 = make_conv(p + "conv2.weight", "", p + "bn2.", stride, 1, 1);
-      bk.c3 = make_conv(p + "conv3.weight", "", p + "bn3.", 1, 0, 1);
-      if (!dry && bf16() && bk.c3.w16) {  // residual-adding layer: smaller n-tile leaves room for the residual ring
-        bk.c3.tc_bn_cap = 128;  // (256 measured: -4 % images/s)
-        conv_tc_prepare_weights(bk.c3);
+  if (hrnet()) {
+    build_hrnet(cfg.backbone);
+  } else {
+    // ---- backbone (models/backbone/resnet.py)
+    stem = make_conv("backbone.conv1.weight", "", "backbone.bn1.", 2, 3, 1);
+    if (!dry && bf16() && err.empty()) {
+      __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(dalloc(64 * 224 / 2));
+      if (wp) conv_tc_prepare_stem(stem, W("backbone.conv1.weight"), wp, st);
+      float* sp = dalloc(stem_pool_weight_bytes() / 4);
+      if (sp) launch_pack_stem_pool_weight(W("backbone.conv1.weight"), sp, st);
+      stem_pool_w = sp;
+    }
+    if (!dry && !bf16() && err.empty()) {
+      float* buf = dalloc(conv_tf32_stem_weight_floats());
+      if (buf) conv_tf32_prepare_stem(stem, W("backbone.conv1.weight"), buf, st);
+    }
+    const int nblocks[4] = {3, 4, 6, 3};
+    for (int l = 0; l < 4; ++l) {
+      layers[l].clear();
+      for (int b = 0; b < nblocks[l]; ++b) {
+        std::string p = "backbone.layer" + std::to_string(l + 1) + "." + std::to_string(b) + ".";
+        Bottleneck bk;
+        int stride = (b == 0 && l > 0) ? 2 : 1;
+        bk.c1 = make_conv(p + "conv1.weight", "", p + "bn1.", 1, 0, 1);
+        bk.c2 = make_conv(p + "conv2.weight", "", p + "bn2.", stride, 1, 1);
+        bk.c3 = make_conv(p + "conv3.weight", "", p + "bn3.", 1, 0, 1);
+        if (!dry && bf16() && bk.c3.w16) {  // residual-adding layer: smaller n-tile leaves room for the residual ring
+          bk.c3.tc_bn_cap = 128;  // (256 measured: -4 % images/s)
+          conv_tc_prepare_weights(bk.c3);
+        }
+        bk.has_ds = (b == 0);
+        if (bk.has_ds) {
+          bk.ds = make_conv(p + "downsample.0.weight", "", p + "downsample.1.", stride, 0, 0);
+          make_dual(bk.c3ds, bk.c3, bk.ds);
+        }
+        layers[l].push_back(bk);
       }
-      bk.has_ds = (b == 0);
-      if (bk.has_ds) {
-        bk.ds = make_conv(p + "downsample.0.weight", "", p + "downsample.1.", stride, 0, 0);
-        make_dual(bk.c3ds, bk.c3, bk.ds);
-      }
-      layers[l].push_back(bk);
     }
   }
   // ---- init regressor (models/dir.py:218-305)
@@ -429,11 +443,12 @@ int Engine::build(cudaStream_t st) {
     const float* bl = W(ir + "attention_left.3.bias");
     const float* br = W(ir + "attention_right.3.bias");
     if (!dry && wl && wr && bl && br) {
-      attn_w = dalloc(2048);
+      const int half = c4ch / 2;  // feat_dim // 2 (models/dir.py:227-241)
+      attn_w = dalloc(2 * half);
       attn_b = dalloc(2);
       if (attn_w && attn_b) {
-        cudaMemcpyAsync(attn_w, wl, 1024 * 4, cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(attn_w + 1024, wr, 1024 * 4, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(attn_w, wl, (size_t)half * 4, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(attn_w + half, wr, (size_t)half * 4, cudaMemcpyDeviceToDevice, st);
         cudaMemcpyAsync(attn_b, bl, 4, cudaMemcpyDeviceToDevice, st);
         cudaMemcpyAsync(attn_b + 1, br, 4, cudaMemcpyDeviceToDevice, st);
       }
@@ -469,8 +484,146 @@ int Engine::build(cudaStream_t st) {
   return DIRB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ HRNet extension
+// HRNet-W32 (Sun et al., CVPR 2019; module / state_dict names of the authors' pose_hrnet.py) as a flat program over
+// numbered buffers. Not in the reference: the oracle is the self-authored oracle/hrnet_oracle.py.
+// Channel counts that are not multiples of 64 (the 32-channel branch) are zero-padded to 64 so that every conv runs on
+// the tensor-core kernels; padded output channels get scale = shift = 0 and stay exactly zero through ReLU/residual/fuse.
+void Engine::build_hrnet(int width) {
+  hr_convs.clear();
+  hr_ops.clear();
+  hr_bufs.clear();
+  hr_convs.reserve(512);  // the profiling hook keeps pointers into this vector: it must never reallocate
+  const int C[4] = {width, 2 * width, 4 * width, 8 * width};
+  auto pad64 = [](int c) { return (c + 63) / 64 * 64; };
+  const std::string p = "backbone.";
+  auto newbuf = [&](int H, int W_, int Cc) {
+    hr_bufs.push_back(HrBuf{H, W_, Cc});
+    return (int)hr_bufs.size() - 1;
+  };
+  // one conv + its BN: returns the id of the output buffer
+  auto add_conv = [&](const std::string& w, const std::string& bn, int cout, int k, int stride, int relu, int in, int res) {
+    const int padn = (k - 1) / 2;
+    const int H = in < 0 ? 256 : hr_bufs[in].H, W_ = in < 0 ? 256 : hr_bufs[in].W;
+    ConvLayer L = make_conv(p + w + ".weight", "", p + bn + ".", stride, padn, relu, in < 0 ? 0 : hr_bufs[in].C, pad64(cout));
+    if (!dry && bf16() && L.w16 && res >= 0) {
+      L.tc_bn_cap = 128;  // residual-adding layer (see the ResNet bottlenecks)
+      conv_tc_prepare_weights(L);
+    }
+    hr_convs.push_back(L);
+    HrOp op{};
+    op.kind = 0;
+    op.layer = (int)hr_convs.size() - 1;
+    op.in = in;
+    op.res = res;
+    op.out = newbuf((H + 2 * padn - k) / stride + 1, (W_ + 2 * padn - k) / stride + 1, pad64(cout));
+    hr_ops.push_back(op);
+    return op.out;
+  };
+  int x = add_conv("conv1", "bn1", 64, 3, 2, 1, -1, -1);
+  x = add_conv("conv2", "bn2", 64, 3, 2, 1, x, -1);
+  for (int b = 0; b < 4; ++b) {  // layer1: Bottleneck(64 -> 256) x4
+    const std::string q = "layer1." + std::to_string(b) + ".";
+    int t = add_conv(q + "conv1", q + "bn1", 64, 1, 1, 1, x, -1);
+    t = add_conv(q + "conv2", q + "bn2", 64, 3, 1, 1, t, -1);
+    const int idn = b == 0 ? add_conv(q + "downsample.0", q + "downsample.1", 256, 1, 1, 0, x, -1) : x;
+    x = add_conv(q + "conv3", q + "bn3", 256, 1, 1, 1, t, idn);
+  }
+  std::vector<int> xs;
+  xs.push_back(add_conv("transition1.0.0", "transition1.0.1", C[0], 3, 1, 1, x, -1));
+  xs.push_back(add_conv("transition1.1.0.0", "transition1.1.0.1", C[1], 3, 2, 1, x, -1));
+  const int stages[3][3] = {{2, 1, 2}, {3, 4, 3}, {4, 3, 4}};  // stage, modules, branches
+  for (const auto& sg : stages) {
+    const int stage = sg[0], nmod = sg[1], nbr = sg[2];
+    if (stage > 2) {  // the new branch is made from the last branch of the previous stage
+      const std::string t = "transition" + std::to_string(stage - 1) + "." + std::to_string(nbr - 1) + ".0.";
+      xs.push_back(add_conv(t + "0", t + "1", C[nbr - 1], 3, 2, 1, xs.back(), -1));
+    }
+    for (int m = 0; m < nmod; ++m) {
+      const std::string q = "stage" + std::to_string(stage) + "." + std::to_string(m) + ".";
+      for (int br = 0; br < nbr; ++br)
+        for (int k = 0; k < 4; ++k) {  // BasicBlock: conv-bn-relu, conv-bn, + identity, relu
+          const std::string bq = q + "branches." + std::to_string(br) + "." + std::to_string(k) + ".";
+          const int t = add_conv(bq + "conv1", bq + "bn1", C[br], 3, 1, 1, xs[br], -1);
+          xs[br] = add_conv(bq + "conv2", bq + "bn2", C[br], 3, 1, 1, t, xs[br]);
+        }
+      std::vector<int> fused;
+      for (int i = 0; i < nbr; ++i) {
+        HrOp f{};
+        f.kind = 1;
+        for (int j = 0; j < nbr; ++j) {
+          const std::string fq = q + "fuse_layers." + std::to_string(i) + "." + std::to_string(j) + ".";
+          int t = xs[j], sh = 0;
+          if (j > i) {  // 1x1 conv + BN at the low resolution; the nearest upsampling happens inside the fuse kernel
+            t = add_conv(fq + "0", fq + "1", C[i], 1, 1, 0, xs[j], -1);
+            sh = j - i;
+          } else if (j < i) {
+            for (int k = 0; k < i - j; ++k) {
+              const bool last = k == i - j - 1;
+              t = add_conv(fq + std::to_string(k) + ".0", fq + std::to_string(k) + ".1", last ? C[i] : C[j], 3, 2,
+                           last ? 0 : 1, t, -1);
+            }
+          }
+          f.term[f.nterm] = t;
+          f.shift[f.nterm] = sh;
+          ++f.nterm;
+        }
+        f.out = newbuf(hr_bufs[xs[i]].H, hr_bufs[xs[i]].W, hr_bufs[xs[i]].C);
+        hr_ops.push_back(f);
+        fused.push_back(f.out);
+      }
+      xs = fused;
+    }
+  }
+  for (int i = 0; i < 4; ++i) hr_out[i] = xs[i];
+  c1ch = pad64(C[0]);
+  c2ch = pad64(C[1]);
+  c3ch = pad64(C[2]);
+  c4ch = pad64(C[3]);
+  if (!dry && err.empty() && (c2ch != C[1] || c3ch != C[2] || c4ch != C[3])) err = "HRNet width must make c2..c4 multiples of 64";
+}
+
+template <typename T>
+int Engine::run_backbone_hrnet(const float* img, int B, Arena& ar, T** c1, T** c2, T** c3, T** c4, cudaStream_t st) {
+  std::vector<T*> ptr(hr_bufs.size());
+  for (size_t i = 0; i < hr_bufs.size(); ++i)
+    ptr[i] = reinterpret_cast<T*>(ar.alloc((size_t)B * hr_bufs[i].H * hr_bufs[i].W * hr_bufs[i].C * sizeof(T)));
+  float* u8_scratch = reinterpret_cast<float*>(ar.alloc((size_t)B * 3 * 256 * 256 * sizeof(float)));
+  if (!ar.base) return DIRB200_OK;
+  if (ar.overflow) return DIRB200_E_WORKSPACE;
+  if (img_u8) {  // input pipeline (apps/eval.py:56-61) as its own pass
+    launch_preprocess_u8(img_u8, u8_scratch, B, 256, 256, st);
+    ++launches;
+    img = u8_scratch;
+  }
+  for (const HrOp& op : hr_ops) {
+    if (op.kind == 0) {
+      const ConvLayer& L = hr_convs[op.layer];
+      if (op.in < 0)
+        conv<T>(L, reinterpret_cast<const T*>(img), ptr[op.out], nullptr, B, 256, 256, st, /*in_nchw=*/true);
+      else
+        conv<T>(L, ptr[op.in], ptr[op.out], op.res >= 0 ? ptr[op.res] : nullptr, B, hr_bufs[op.in].H, hr_bufs[op.in].W, st);
+    } else {
+      const T* terms[4];
+      for (int k = 0; k < op.nterm; ++k) terms[k] = ptr[op.term[k]];
+      const HrBuf& o = hr_bufs[op.out];
+      launch_fuse_sum_relu<T>(terms, op.shift, op.nterm, ptr[op.out], B, o.H, o.W, o.C, st);
+      ++launches;
+    }
+  }
+  if (c1) *c1 = ptr[hr_out[0]];
+  *c2 = ptr[hr_out[1]];
+  *c3 = ptr[hr_out[2]];
+  *c4 = ptr[hr_out[3]];
+  return DIRB200_OK;
+}
+template int Engine::run_backbone_hrnet<float>(const float*, int, Arena&, float**, float**, float**, float**, cudaStream_t);
+template int Engine::run_backbone_hrnet<__nv_bfloat16>(const float*, int, Arena&, __nv_bfloat16**, __nv_bfloat16**,
+                                                       __nv_bfloat16**, __nv_bfloat16**, cudaStream_t);
+
 const ConvLayer* Engine::find_conv(const std::string& k) const {
   std::vector<const ConvLayer*> all = {&stem, &attn_conv, &conv_final0, &conv_final3, &segdense0};
+  for (const auto& c : hr_convs) all.push_back(&c);
   for (int l = 0; l < 4; ++l)
     for (const auto& b : layers[l]) {
       all.push_back(&b.c1);
@@ -741,23 +894,24 @@ T* Engine::run_residual(const ResidualBlock& r, const T* rawx, const T* act, int
 template <typename T>
 int Engine::run_init(const T* c4, int B, float* stage_rec, int rec_stride, float* para, int para_stride, Arena& ar,
                      cudaStream_t st) {
-  T* attn_act = aalloc<T>(ar, (int64_t)B * 64 * 2048);
+  const int F = c4ch;  // feat_dim: 2048 (ResNet-50) or 256 (HRNet-W32)
+  T* attn_act = aalloc<T>(ar, (int64_t)B * 64 * F);
   float* attn = aalloc<float>(ar, (int64_t)B * 64 * 2);
-  float* pooled = aalloc<float>(ar, (int64_t)B * 3 * 2048);
+  float* pooled = aalloc<float>(ar, (int64_t)B * 3 * F);
   if (!ar.base) return DIRB200_OK;
   if (ar.overflow) return DIRB200_E_WORKSPACE;
   conv<T>(attn_conv, c4, attn_act, nullptr, B, 8, 8, st);
-  launch_attn_logits<T>(attn_act, attn_w, attn_b, attn, B, 64, 1024, st);
-  launch_attn_pool<T>(c4, attn, pooled, B, 64, 2048, st);
+  launch_attn_logits<T>(attn_act, attn_w, attn_b, attn, B, 64, F / 2, st);
+  launch_attn_pool<T>(c4, attn, pooled, B, 64, F, st);
   RegressArgs a{};
   for (int h = 0; h < 2; ++h) {
-    a.in0[h] = VecSeg{pooled + h * 2048, 2048, 3 * 2048};
+    a.in0[h] = VecSeg{pooled + h * F, F, 3 * F};
     a.in1[h] = VecSeg{nullptr, 0, 0};
     a.Wm[h] = init_Wm[h];
     a.bm[h] = init_bm[h];
     a.mano[h] = mano[0][h];
   }
-  a.off0 = VecSeg{pooled + 2 * 2048, 2048, 3 * 2048};
+  a.off0 = VecSeg{pooled + 2 * F, F, 3 * F};
   a.off1 = VecSeg{nullptr, 0, 0};
   a.Wo = init_Wo;
   a.bo = init_bo;
@@ -931,7 +1085,8 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   sticky_rc = 0;
   const bool plan = ar.base == nullptr;
   T *c2 = nullptr, *c3 = nullptr, *c4 = nullptr;
-  int rc = run_backbone<T>(img, B, 256, 256, ar, nullptr, &c2, &c3, &c4, st);
+  int rc = hrnet() ? run_backbone_hrnet<T>(img, B, ar, nullptr, &c2, &c3, &c4, st)
+                   : run_backbone<T>(img, B, 256, 256, ar, nullptr, &c2, &c3, &c4, st);
   if (rc) return rc;
   float* rec = plan ? nullptr : o->record;
   float* para = plan ? nullptr : o->mano_para;
@@ -951,10 +1106,10 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   // ---- stage 1 @16x16 (models/dir.py:442-456)
   T *raw = nullptr, *act = nullptr;
   const ResidualBlock& skip4 = res["decoder.skip_layer4."];
-  concat(c3, 1024, 0, nullptr, 0, skip4, 16, &raw, &act);
+  concat(c3, c3ch, 0, nullptr, 0, skip4, 16, &raw, &act);
   T* c3_skip = run_residual<T>(skip4, c3, act, B, 16, 16, ar, st);
   const ResidualBlock& fus4 = res["decoder.fusion_layer4."];
-  concat(c4, 2048, 1, c3_skip, 256, fus4, 16, &raw, &act);
+  concat(c4, c4ch, 1, c3_skip, 256, fus4, 16, &raw, &act);
   T* fusion4 = run_residual<T>(fus4, raw, act, B, 16, 16, ar, st);
   if (cfg.refine_stages == 1) {  // "1 refine iter": init regression + projecter_4 only (truncation after models/dir.py:456)
     T* img_feat1 = nullptr;
@@ -981,10 +1136,10 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   }
   T *raw3 = nullptr, *act3 = nullptr;
   {
-    const int64_t n = (int64_t)B * 32 * 32 * 512;
+    const int64_t n = (int64_t)B * 32 * 32 * c2ch;
     act3 = aalloc<T>(ar, n);
     if (!plan && !ar.overflow) {
-      launch_concat_preact<T>(c2, 512, 0, (const T*)nullptr, 0, skip3.bn1s, skip3.bn1b, raw3, act3, B, 32, 32, st3);
+      launch_concat_preact<T>(c2, c2ch, 0, (const T*)nullptr, 0, skip3.bn1s, skip3.bn1b, raw3, act3, B, 32, 32, st3);
       ++launches;
     }
   }

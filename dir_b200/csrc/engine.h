@@ -142,6 +142,27 @@ struct Engine {
   std::vector<ProfRec> prof;
   size_t prof_used = 0;
 
+  // ---- HRNet extension (cfg.backbone = 32; parity unpinned, oracle/hrnet_oracle.py): the backbone as a flat program
+  // over numbered NHWC buffers (no reuse: ~55 MB of bf16 activations per image)
+  struct HrOp {
+    int kind;                // 0: conv (+BN)(+residual)(+ReLU), 1: fuse = relu(sum of up to 4 nearest-upsampled terms)
+    int layer;               // index into hr_convs
+    int in, out, res;        // buffer ids; in = -1: the NCHW fp32 image; res = -1: none
+    int nterm, term[4], shift[4];
+  };
+  struct HrBuf {
+    int H, W, C;             // per image at a 256x256 input; C = packed channel count (multiple of 64, zero padded)
+  };
+  std::vector<ConvLayer> hr_convs;
+  std::vector<HrOp> hr_ops;
+  std::vector<HrBuf> hr_bufs;
+  int hr_out[4] = {-1, -1, -1, -1};
+  int c1ch = 256, c2ch = 512, c3ch = 1024, c4ch = 2048;  // packed channels of the pyramid the decoder sees
+  bool hrnet() const { return cfg.backbone != 0; }
+  void build_hrnet(int width);
+  template <typename T>
+  int run_backbone_hrnet(const float* img, int B, Arena& ar, T** c1, T** c2, T** c3, T** c4, cudaStream_t st);
+
   // ---- network
   ConvLayer stem;
   std::vector<Bottleneck> layers[4];
@@ -168,8 +189,9 @@ struct Engine {
   float* transposed_pairs(const std::string& name, int N, int K);
   void fold(const std::string& conv_bias, const std::string& bn, float** scale, float** shift, int n, int off = 0,
             int total = 0);
+  // cin_pad / cout_pad > 0: pack with zero-padded input / output channels (HRNet's 32-channel branch lives in 64)
   ConvLayer make_conv(const std::string& wname, const std::string& bias, const std::string& bn, int stride, int pad,
-                      int relu);
+                      int relu, int cin_pad = 0, int cout_pad = 0);
   void fuse_post_bn(ConvLayer& c, const std::string& conv_bias, const std::string& bn);
   void prepare_tf32(ConvLayer& L);
   PointMlp make_mlp(const std::string& prefix, int cin, int cmid, int cout);

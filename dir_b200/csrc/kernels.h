@@ -49,8 +49,13 @@ void launch_preprocess_u8(const unsigned char* img, float* out, int B, int H, in
 void launch_fold_affine(const float* conv_bias, const float* gamma, const float* beta, const float* mean,
                         const float* var, float* scale, float* shift, int n, cudaStream_t st);
 // src [Cout][Cin][kh][kw] fp32 -> dst32 [Cout][Kpad] (ky,kx,ci) fp32 and/or dst16 bf16 (same layout)
+// Cout / Cin are the PACKED channel counts; Cout_src / Cin_src (0 = same) the tensor's own: the rest is zero padding
 void launch_pack_conv_weight(const float* src, float* dst32, __nv_bfloat16* dst16, int Cout, int Cin, int kh, int kw,
-                             int Kpad, cudaStream_t st);
+                             int Kpad, cudaStream_t st, int Cout_src = 0, int Cin_src = 0);
+// HRNet fuse layer: out = relu(sum_k nearest-upsample(terms[k], 2^shifts[k])); NHWC, C channels everywhere, up to 4 terms
+template <typename T>
+void launch_fuse_sum_relu(const T* const* terms, const int* shifts, int nterm, T* out, int B, int H, int W, int C,
+                          cudaStream_t st);
 void launch_transpose2d(const float* src, float* dst, int rows, int cols, cudaStream_t st);  // dst[c][r]=src[r][c]
 void launch_transpose_pairs(const float* src /*[N][K]*/, float* dst /*[K/2][N][2]*/, int N, int K, cudaStream_t st);
 void launch_gcn_adjacency(const float* e1, float* A /*21x21*/, cudaStream_t st);

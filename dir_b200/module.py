@@ -22,6 +22,7 @@ from . import assets, capi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _KEYS_JSON = os.path.join(_HERE, "state_dict_keys.json")
+_KEYS_JSON_HRNET = os.path.join(_HERE, "state_dict_keys_hrnet_w32.json")
 
 STAGE_KEYS = [  # (key in outs_list[i], offset name, trailing shape) — models/dir.py:521-535
     ("pd_joint_uv_left", "uv_l", (21, 2)), ("pd_joint_uv_right", "uv_r", (21, 2)),
@@ -64,8 +65,9 @@ def _default_init(name, shape):
     return torch.zeros(shape)
 
 
-def reference_key_shapes():
-    with open(_KEYS_JSON) as f:
+def reference_key_shapes(backbone="resnet50"):
+    """Key/shape inventory: the reference's 963 keys, or (backbone='hrnet_w32') the HRNet extension's."""
+    with open(_KEYS_JSON if backbone == "resnet50" else _KEYS_JSON_HRNET) as f:
         return json.load(f)
 
 
@@ -80,7 +82,7 @@ class DIR(nn.Module):
     BASELINE.json configs[0]; outs_list then holds two stage dicts; needs aux_outputs=False)."""
 
     def __init__(self, joint_num, mano_path, root_joint=0, precision="fp32", aux_outputs=True, max_batch=128,
-                 use_cuda_graph=False, refine_stages=2):
+                 use_cuda_graph=False, refine_stages=2, backbone="resnet50"):
         super().__init__()
         if joint_num != 21:
             raise ValueError("DIR is defined for the 21-joint hand skeleton (models/dir.py:25-26)")
@@ -93,11 +95,15 @@ class DIR(nn.Module):
         self.max_batch = int(max_batch)
         self.use_cuda_graph = bool(use_cuda_graph)
         self.refine_stages = int(refine_stages)
+        if backbone not in capi.BACKBONE:
+            raise ValueError(f"backbone must be one of {sorted(capi.BACKBONE)} (the reference has ResNet-50 only; "
+                             "'hrnet_w32' is an extension with a self-authored oracle)")
+        self.backbone_name = backbone
         if self.refine_stages not in (1, 2):
             raise ValueError("the reference defines two refinement stages (models/dir.py:437-471): refine_stages is 1 or 2")
         if self.refine_stages == 1 and self.aux_outputs:
             raise ValueError("refine_stages=1 needs aux_outputs=False (seg/dense/proj_feat hang off the second stage)")
-        for name, shape in reference_key_shapes().items():
+        for name, shape in reference_key_shapes(backbone).items():
             parts = name.split(".")
             m = self
             for p in parts[:-1]:
@@ -136,7 +142,7 @@ class DIR(nn.Module):
     def load_checkpoint(self, path, strict=False):
         """apps/eval.py:107-108 in one call: torch.load(path)['net'] (DataParallel prefixes stripped) -> load_state_dict.
         Returns the missing/unexpected key report."""
-        state, report = assets.read_checkpoint(path, expected_keys=reference_key_shapes().keys())
+        state, report = assets.read_checkpoint(path, expected_keys=reference_key_shapes(self.backbone_name).keys())
         self.load_state_dict(state, strict=strict)
         return report
 
@@ -149,7 +155,7 @@ class DIR(nn.Module):
         return super()._apply(fn, *a, **k)
 
     def _device(self):
-        return self.backbone.conv1.weight.device
+        return self.init_regressor.offset.weight.device
 
     def _ensure_handle(self):
         dev = self._device()
@@ -162,7 +168,8 @@ class DIR(nn.Module):
             self._packed = False
             self._workspace = {}
         if self._handle is None:
-            self._handle = capi.Handle(self.precision, self.max_batch, self.aux_outputs, index, self.refine_stages)
+            self._handle = capi.Handle(self.precision, self.max_batch, self.aux_outputs, index, self.refine_stages,
+                                       self.backbone_name)
         return self._handle
 
     def required_keys(self):

@@ -201,6 +201,10 @@ def make_tensor(name: str, shape, keys, seed: int = 0) -> torch.Tensor:
         w = _uniform(shape, 0.8, 1.2, g)
         if name.startswith("backbone") and ".bn3." in name:
             w = w * 0.3  # damp the residual branch
+        if name.startswith("backbone") and ".branches." in name and ".bn2." in name:
+            w = w * 0.2  # HRNet BasicBlock: damp the residual branch (32 blocks per branch in sequence)
+        if name.startswith("backbone") and ".fuse_layers." in name:
+            w = w * 0.2  # HRNet fuse layers sum up to four branches per module, eight modules in sequence
         return w
     if leaf == "bias":
         return _normal(shape, 0.1, g)
@@ -217,9 +221,17 @@ def make_tensor(name: str, shape, keys, seed: int = 0) -> torch.Tensor:
     raise KeyError(f"no synthetic rule for {name} {shape}")
 
 
-def make_state_dict(seed: int = 0, prefix: str = "", key_shapes: dict = None) -> dict:
-    """Full (or prefix-filtered) synthetic state_dict with the reference's 963 keys."""
-    ks = key_shapes or load_key_shapes()
+def hrnet_key_shapes(width: int = 32) -> dict:
+    """Key/shape inventory of the HRNet extension (oracle/hrnet_oracle.py; parity unpinned)."""
+    from .hrnet_oracle import dir_key_shapes
+
+    return dir_key_shapes(width, load_key_shapes())
+
+
+def make_state_dict(seed: int = 0, prefix: str = "", key_shapes: dict = None, backbone: str = "resnet50") -> dict:
+    """Full (or prefix-filtered) synthetic state_dict with the reference's 963 keys (backbone='hrnet_w32'|'hrnet_w48': the
+    HRNet extension's inventory instead)."""
+    ks = key_shapes or (load_key_shapes() if backbone == "resnet50" else hrnet_key_shapes(int(backbone.split("_w")[1])))
     out = {}
     for name, shape in ks.items():
         if prefix and not name.startswith(prefix):

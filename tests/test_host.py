@@ -48,7 +48,7 @@ def test_create_fails_loudly_without_b200(lib):
 
     if torch.cuda.is_available():
         pytest.skip("GPU present")
-    cfg = capi.Config(0, 8, 1, 0, 2)
+    cfg = capi.Config(0, 8, 1, 0, 2, 0)
     h = ctypes.c_void_p()
     rc = lib.dirb200_create(ctypes.byref(cfg), ctypes.byref(h))
     assert rc == -3 and not h.value
@@ -56,7 +56,7 @@ def test_create_fails_loudly_without_b200(lib):
     m = dir_b200.DIR(21, "./misc/mano")
     with pytest.raises(dir_b200.DirB200Error):
         m({"img": torch.zeros(1, 3, 256, 256)}, None, None)
-    bad = capi.Config(7, 8, 1, 0, 2)
+    bad = capi.Config(7, 8, 1, 0, 2, 0)
     assert lib.dirb200_create(ctypes.byref(bad), ctypes.byref(h)) == -1  # unknown precision
 
 
@@ -179,3 +179,18 @@ def test_sharded_gather_world2_gloo(n):
         p.join(120)
     res = sorted(q.get(timeout=10) for _ in range(2))
     assert res == [(0, True), (1, True)]
+
+
+def test_hrnet_key_inventory_is_the_generators():
+    """The shipped inventory of the HRNet extension equals what oracle/hrnet_oracle.py derives (python -m oracle.hrnet_oracle)."""
+    import dir_b200
+    from dir_b200.module import reference_key_shapes
+    from oracle.synth import hrnet_key_shapes
+
+    shipped = reference_key_shapes("hrnet_w32")
+    assert shipped == hrnet_key_shapes(32)
+    m = dir_b200.DIR(21, "./misc/mano", backbone="hrnet_w32")
+    assert set(m.state_dict()) == set(shipped)
+    assert tuple(m.state_dict()["init_regressor.mano_left.weight"].shape) == (64, 256)
+    with pytest.raises(ValueError):
+        dir_b200.DIR(21, "./misc/mano", backbone="hrnet_w48")
