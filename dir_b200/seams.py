@@ -67,10 +67,12 @@ def backbone(model, img):
     B, _, H, W = img.shape
     h, ws = _prep(model, B)
     dev = img.device
-    c1 = torch.empty(B, 256, H // 4, W // 4, device=dev)
-    c2 = torch.empty(B, 512, H // 8, W // 8, device=dev)
-    c3 = torch.empty(B, 1024, H // 16, W // 16, device=dev)
-    c4 = torch.empty(B, 2048, H // 32, W // 32, device=dev)
+    # packed channel counts: ResNet-50, or HRNet-W32 (whose 32-channel branch is stored in 64, the upper half zero)
+    ch = (64, 64, 128, 256) if getattr(model, "backbone_name", "resnet50") == "hrnet_w32" else (256, 512, 1024, 2048)
+    c1 = torch.empty(B, ch[0], H // 4, W // 4, device=dev)
+    c2 = torch.empty(B, ch[1], H // 8, W // 8, device=dev)
+    c3 = torch.empty(B, ch[2], H // 16, W // 16, device=dev)
+    c4 = torch.empty(B, ch[3], H // 32, W // 32, device=dev)
     h.check(h.lib.dirb200_backbone(h.h, _ptr(img), B, H, W, _ptr(c1), _ptr(c2), _ptr(c3), _ptr(c4), _ptr(ws),
                                    ws.numel(), _stream()), "backbone")
     return [c1, c2, c3, c4]
