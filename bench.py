@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip eager-GPU baseline, parity, no-aux and fp32-config legs")
     ap.add_argument("--cuda-graph", action="store_true")
+    ap.add_argument("--backbone", default="resnet50", choices=["resnet50", "hrnet_w32"],
+                    help="resnet50 = the reference's network; hrnet_w32 = extension, parity unpinned (BASELINE configs 3-5)")
     return ap.parse_args()
 
 
@@ -245,10 +247,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
 
-    def make_net(precision, aux, max_batch=B):
+    def make_net(precision, aux, max_batch=B, backbone=None):
+        backbone = backbone or args.backbone
         n = dir_b200.DIR(21, "./misc/mano", precision=precision, aux_outputs=aux, max_batch=max_batch,
-                         use_cuda_graph=args.cuda_graph).to(dev)
-        n.load_state_dict(make_state_dict(0), strict=False)
+                         use_cuda_graph=args.cuda_graph, backbone=backbone).to(dev)
+        n.load_state_dict(make_state_dict(0, backbone=backbone), strict=False)
         n.eval()
         return n
 
@@ -393,7 +396,9 @@ def main():
         h2d_gbs = 8 * B * 3 * 256 * 256 * 4 / (float(t.item()) / 1000.0) / 1e9
 
     extras = world == 1 and not args.no_extras
-    no_aux = parity = parity32 = fp32_cfg = eager = None
+    no_aux = parity = parity32 = fp32_cfg = eager = hrnet_cfg = None
+    if extras and args.backbone != "resnet50":
+        extras = False  # the extra legs (oracle parity, eager baseline) are defined for the reference's network
     if extras:
         net_na = make_net(args.precision, False)
         ms_na = timed(step_of(net_na), K, W)
@@ -411,6 +416,16 @@ def main():
             parity32 = parity_check(net32, "fp32", host[0])
             del net32
         eager = gpu_eager_baseline(dev, B if B <= 128 else 128)
+        # BASELINE.json configs[2] names HRNet-W32 as the headline network; the reference has none. The
+        # extension (self-authored oracle, parity UNPINNED) is timed here so that the config has a number, labelled as such
+        net_h = make_net(args.precision, True, B, "hrnet_w32")
+        ms_h = timed(step_of(net_h), max(5, K // 2), W)
+        hh = net_h._handle
+        hrnet_cfg = {"value": B * max(5, K // 2) / (ms_h / 1000.0), "unit": "images/s", "batch": B,
+                     "ms_per_step": ms_h / max(5, K // 2), "gpu_launches_per_step": hh.lib.dirb200_forward_launches(hh.h, B),
+                     "what": f"backbone='hrnet_w32', precision='{args.precision}': EXTENSION, not in the reference; parity "
+                             "unpinned (tests/test_gpu_hrnet.py checks it against the self-authored oracle/hrnet_oracle.py)"}
+        del net_h
 
     if rank != 0:
         if world > 1:
@@ -479,7 +494,8 @@ def main():
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"bf16": "bf16", "fp32": "f32", "tf32": "tf32"}[args.precision], "data": "synthetic",
         "config": {"workload": f"DIR eval forward (ResNet-50 backbone, init regression, 2 refinement stages, "
-                               f"seg/dense/proj_feat heads), 256x256, B={B} per GPU, random-init weights + synthetic MANO",
+                               f"seg/dense/proj_feat heads), 256x256, B={B} per GPU, random-init weights + synthetic MANO"
+                               + ("" if args.backbone == "resnet50" else " [--backbone hrnet_w32: extension, ResNet-50 replaced]"),
                    "global_batch": B * world, "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": f"{NBUF} rotating resident input batches (4x100 MB > 126 MB L2); activations ~GBs per step",
                    "collective": "ncclAllGather of (B,14661) fp32 records per step" if world > 1 else None,
@@ -489,7 +505,7 @@ def main():
         "gpu_launches": launches_per_step * K,
         "roofline": roof, "roofline_top": roof_top, "roofline_step": step_roof,
         "cpu_baseline": cpu, "gpu_eager_baseline": eager, "parity": parity, "no_aux": no_aux,
-        "fp32_config": fp32_cfg, "parity_fp32": parity32,
+        "fp32_config": fp32_cfg, "parity_fp32": parity32, "hrnet_w32_extension": hrnet_cfg,
     }
     print(json.dumps(line))
     if world > 1:
