@@ -75,6 +75,8 @@ extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
   {
     const char* dis = getenv("DIRB200_DISABLE_TC");
     h->e.disable_tc = dis && dis[0] == '1';
+    const char* nh = getenv("DIRB200_NO_HALO");
+    h->e.no_halo = nh && nh[0] == '1';
     const char* f32s = getenv("DIRB200_FP32_SIMT");
     h->e.fp32_simt = f32s && f32s[0] == '1';
     const char* nopair = getenv("DIRB200_NO_PAIR_FUSION");

@@ -681,6 +681,18 @@ void Engine::conv(const ConvLayer& L, const T* x, T* y, const T* resid, int B, i
     if (pr) cudaEventRecord(pr->b, st);
     return;
   }
+  if (sizeof(T) == 2 && !in_nchw && !disable_tc && !no_halo && conv_tc_supported(L, B, H, W_) &&
+      conv_halo_supported(L, B, H, W_)) {
+    int rc = launch_conv_halo(L, reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
+                              reinterpret_cast<const __nv_bfloat16*>(resid), B, H, W_, st);
+    if (rc && !sticky_rc) {
+      sticky_rc = rc;
+      err = "halo conv launch failed for " + L.name;
+    }
+    ++tc_launches;
+    if (pr) cudaEventRecord(pr->b, st);
+    return;
+  }
   if (sizeof(T) == 2 && !in_nchw && !disable_tc && conv_tc_supported(L, B, H, W_)) {
     int rc = launch_conv_tc(L, reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
                             reinterpret_cast<const __nv_bfloat16*>(resid), B, H, W_, st);

@@ -124,6 +124,7 @@ struct Engine {
   bool dense_fusion = false;  // DIRB200_DENSE_FUSION=1: materialise bone_proj and run the dense 2560-ch conv
   bool disable_pair_fusion = false;  // DIRB200_NO_PAIR_FUSION=1: keep conv3 and skip/downsample as separate launches
   bool disable_tc = false;  // DIRB200_DISABLE_TC=1: force the CUDA-core conv in bf16 mode (debug A/B)
+  bool no_halo = false;     // DIRB200_NO_HALO=1: 64-channel 3x3 convs on the per-tap kernel (conv_tc.cu) instead of conv_halo.cu
   bool fp32_simt = false;   // DIRB200_FP32_SIMT=1: fp32 configuration on the CUDA-core conv (the round-1 path; debug A/B)
   const ConvLayer* find_conv(const std::string& weight_key) const;
   void* nccl_comm = nullptr;
@@ -243,6 +244,10 @@ int conv_tf32_prepare_stem(ConvLayer& L, const float* w_raw, float* buf, cudaStr
 bool conv_tf32_stem_supported(const ConvLayer& L, int H, int W);
 int launch_conv_tf32_stem(const ConvLayer& L, const float* img, float* scratch, float* y, int B, int H, int W, int nsplit,
                           cudaStream_t st);
+// halo-tile 3x3 conv for the 64 -> 64 channel layers (conv_halo.cu): one input fetch per tile instead of one per tap
+bool conv_halo_supported(const ConvLayer& L, int B, int H, int W);
+int launch_conv_halo(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bfloat16* res, int B, int H,
+                     int W, cudaStream_t st);
 // tensor-core conv (conv_tc.cu). Returns false if the shape is not supported (caller falls back to CUDA cores).
 bool conv_tc_supported(const ConvLayer& L, int B, int H, int W);
 int conv_tc_prepare_weights(ConvLayer& L);  // builds L.wmap

@@ -42,6 +42,22 @@ __device__ __forceinline__ void tma_load_2d(const void* map, uint64_t* bar, void
       ::"r"(s32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(s32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const void* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(s32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// no-swizzle K-major operand descriptor: core matrices of 8 rows x 16 B; lbo = byte step between the two 16-byte K-chunks
+// of one MMA, sbo = byte step between 8-row groups (cute::UMMA::make_umma_desc<Major::K>, LayoutType::INTERLEAVE)
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

@@ -198,3 +198,30 @@ def test_backbone_bf16_tensor_core_stem(m16, synth_sd):
         mean = float((a.cpu() - b).abs().mean() / b.abs().mean())
         print(f"c{i + 1}: max-rel {err:.3e} mean-rel {mean:.3e}")
         assert err < 6e-2 and mean < 2e-2, (i, err, mean)
+
+
+@pytest.mark.parametrize("B,H,W,with_res", [(2, 64, 64, False), (3, 32, 32, True), (5, 16, 16, True), (1, 16, 16, False)])
+def test_halo_conv_vs_per_tap_kernel_and_reference(synth_sd, monkeypatch, B, H, W, with_res):
+    """conv_halo.cu (one input fetch per tile, chunk-major no-swizzle A operand, three column-masked copies for the
+    horizontal padding) against the per-tap TMA kernel it replaces (DIRB200_NO_HALO=1) and against the exact bf16-operand
+    model: 64 -> 64 channels, 3x3, maps of 64 / 32 / 16 pixels (2 / 4 / 8 image rows per tile), with and without the
+    residual + ReLU epilogue HRNet's BasicBlocks use. Same products, same fp32 accumulation: the two kernels may differ
+    by summation order only."""
+    from dir_b200 import seams
+
+    key = "backbone.layer1.0.conv2.weight"
+    halo = _model(synth_sd, "bf16")
+    monkeypatch.setenv("DIRB200_NO_HALO", "1")
+    taps = _model(synth_sd, "bf16")
+    taps._ensure_handle()  # the handle reads the switch at creation
+    monkeypatch.delenv("DIRB200_NO_HALO")
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    x = torch.relu(torch.randn(B, 64, H, W, generator=g)) * 1.5
+    res = torch.randn(B, 64, H, W, generator=g) if with_res else None
+    want = expected(synth_sd, key, x, res, round_bf16=True)
+    a, ua = seams.conv_layer(halo, key, x.cuda(), None if res is None else res.cuda())
+    b, ub = seams.conv_layer(taps, key, x.cuda(), None if res is None else res.cuda())
+    assert ua == 1 and ub == 1
+    scale = float(want.abs().max())
+    assert float((a.cpu() - want).abs().max()) / scale < 6e-3
+    assert float((a - b).abs().max()) / scale < 4e-3  # one bf16 ulp of the output at most, from the summation order
