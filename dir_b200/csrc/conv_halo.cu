@@ -12,9 +12,9 @@
 // Horizontal zero padding without a padded pitch: three copies of the planes -- kx = 0 reads a copy whose last image
 // column is zero (row x = 0 would otherwise wrap to the previous row's last pixel), kx = 2 a copy whose first column is
 // zero, kx = 1 the plain copy; one slack pixel of zeros before and after each plane catches the two corner reads.
-// Roles (320 threads, persistent): warp 0 TMA producer (weights once: 9 x [64 n][64 k] swizzled tiles = 72 KB resident;
-// one raw halo box per tile), warp 1 MMA issuer (36 x M128 N64 K16 per tile, two TMEM accumulators), warps 2-5 re-layout,
-// warps 6-9 epilogue (scale/shift (+residual) (+ReLU) -> bf16 -> swizzled staging -> TMA store).
+// Roles (448 threads, persistent): warp 0 TMA producer (weights once: 9 x [64 n][64 k] swizzled tiles = 72 KB resident;
+// one raw halo box per tile), warp 1 MMA issuer (36 x M128 N64 K16 per tile, two TMEM accumulators), warps 2-9 re-layout,
+// warps 10-13 epilogue (scale/shift (+residual) (+ReLU) -> bf16 -> swizzled staging -> TMA store).
 #include <cuda.h>
 
 #include <cstdio>
@@ -32,7 +32,8 @@ namespace {
 
 using namespace tc;
 
-constexpr int HALO_THREADS = 320;
+constexpr int HALO_THREADS = 448;  // producer, MMA issuer, 8 re-layout warps, 4 epilogue warps
+constexpr int RELAYOUT_THREADS = 256;
 constexpr int W_BYTES = 9 * 64 * 128;       // resident weights: 9 taps x [64 n][64 k] bf16
 constexpr int RAW_BYTES = 4 * 64 * 128;     // largest halo: (2+2) rows x 64 px x 128 B
 constexpr int LBO = 265 * 16;               // chunk-plane stride: (256 + 2 slack + 7 pad) pixels; 265 % 8 == 1 keeps the
@@ -84,8 +85,8 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     tma_prefetch_desc(&tmY);
     mbar_init(&bars->wbar, 1);
     mbar_init(&bars->raw_full, 1);
-    mbar_init(&bars->raw_empty, 128);
-    mbar_init(&bars->planes_full, 128);
+    mbar_init(&bars->raw_empty, RELAYOUT_THREADS);
+    mbar_init(&bars->planes_full, RELAYOUT_THREADS);
     mbar_init(&bars->planes_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tfull[i], 1);
@@ -153,7 +154,7 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         umma_commit(&bars->tfull[buf]);
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // ===================== re-layout: raw [pixel][8 chunks x 16 B] -> three chunk-major planes
     const int t = threadIdx.x - 64;
     uint32_t i = 0;
@@ -162,7 +163,7 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       mbar_wait(&bars->planes_empty, (i & 1) ^ 1);  // previous tile's MMAs are done with the planes
       const uint4* src = reinterpret_cast<const uint4*>(sRaw);
       const uint4 zero = make_uint4(0, 0, 0, 0);
-      for (int idx = t; idx < Np * 8; idx += 128) {
+      for (int idx = t; idx < Np * 8; idx += RELAYOUT_THREADS) {
         const int p = idx >> 3, c = idx & 7;
         const uint4 v = src[idx];
         const int x = p & (W - 1);  // W is a power of two
@@ -177,7 +178,7 @@ conv3x3_c64_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     }
   } else {
     // ===================== epilogue
-    const int et = threadIdx.x - 192;  // 0..127
+    const int et = threadIdx.x - 320;  // 0..127
     const int lane_base = (warp & 3) * 32;
     const int row = lane_base + lane;
     const uint32_t swz = (uint32_t)(row & 7);
