@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const Program prog, float
 }
 
 // issue rate: `n` MMAs (M=128, N=256, one 32-byte k-step) back to back into one accumulator
-__global__ void __launch_bounds__(128, 1) rate_kernel(int bf16, int n, long long* cycles) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int bf16, int n, long long* cycles, int N = 256) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int bf16, int n, long long
   fence_after();
   const uint32_t tmem = tmem_slot;
   if (threadIdx.x == 0) {
-    const uint32_t id = idesc(256, bf16 ? 1u : 2u);
+    const uint32_t id = idesc(N, bf16 ? 1u : 2u);
     const uint64_t da = desc128(s32(sA)), db = desc128(s32(sB));
     const long long t0 = clock64();
     for (int r = 0; r < n; ++r) {
@@ -272,6 +272,12 @@ int main() {
       printf("rate %s: %d MMAs (M128 N256) in %lld clk = %.1f clk/MMA = %.0f flop/clk/SM (x148 SMs x 1.965 GHz = %.0f "
              "TFLOP/s)\n", bf16 ? "bf16" : "tf32", n, h, (double)h / n, flop / h, flop / h * 148 * 1.965e9 / 1e12);
     }
+  }
+  for (int N : {64, 128, 256}) {  // does the instruction time scale with N? (conv_tc<64,...>, conv_halo issue N = 64 MMAs)
+    rate_kernel<<<1, 128, (128 + 256) * 128 + 1024>>>(1, 4096, dc, N);
+    long long h = 0;
+    cudaMemcpy(&h, dc, 8, cudaMemcpyDeviceToHost);
+    printf("rate bf16 N=%d: %.1f clk/MMA (M128 K16) = %.0f flop/clk/SM\n", N, (double)h / 4096, 2.0 * 128 * N * 16 * 4096 / h);
   }
   cudaError_t e = cudaDeviceSynchronize();
   printf("final status: %s\n", cudaGetErrorString(e));
