@@ -8,16 +8,21 @@
 //  * kind::tf32 TRUNCATES its fp32 operands to 10 mantissa bits, so the hardware itself forms A_hi = trunc(A) from the
 //    raw activation tile; only A_lo = rn_tf32(A - trunc(A)) has to be produced in software (an elementwise pass over
 //    the 16 KB tile by four "splitter" warps, position for position, so the 128B swizzle never has to be decoded).
-//  * D += A_hi*W_hi is accumulated in one TMEM buffer, the 2^-11-sized cross terms A_lo*W_hi + A_hi*W_lo in another
-//    (their rounding is negligible); A_lo*W_lo (2^-22) is dropped.
+//  * D = A_hi*W_hi + (A_lo*W_hi + A_hi*W_lo); A_lo*W_lo (2^-22) is dropped. W_hi and W_lo tiles sit back to back in shared
+//    memory, so ONE N = 2*BN instruction computes A_hi*[W_hi | W_lo] (main term into columns 0..BN-1, first cross term into
+//    BN..2BN-1) and a second N = BN instruction adds A_lo*W_hi to the cross columns: 2 instructions per k-step instead
+//    of 3, A is read from shared memory once instead of twice, and the wide instruction is the efficient one (an M=128 MMA
+//    costs 107 cycles at N=128 but only 171 at N=256, profiles/mma_probe_r2.txt). The cross terms are 2^-11 of the main
+//    term and live in their own columns, so their rounding never touches the main sum.
 //  * the TMEM accumulator rounds TOWARD ZERO on every MMA: a biased 2^-24 relative loss per instruction, which over the
 //    2304 k-steps of the 18432-deep attention convolution would reach 1e-4. The main accumulator is therefore drained
-//    every CHUNK_KB k-blocks (8 MMAs) into fp32 registers of the epilogue warps with ordinary round-to-nearest adds
-//    while the MMA warp continues into the other TMEM buffer (ping-pong), bounding the bias at ~4e-7.
+//    every CHUNK_KB k-blocks (8 accumulating MMAs) into fp32 registers of the epilogue warps with ordinary round-to-nearest
+//    adds (main + cross columns together) while the MMA warp continues into the other TMEM buffer (ping-pong), bounding
+//    the bias at ~4e-7.
 // Roles per CTA (448 threads, persistent over tiles of 128 pixels x BN channels, k-block = 32 channels of one tap):
 //   warp 0    TMA producer: A box {32 ch, wbox*s, hbox*s, nbox} (im2col, padding and stride are TMA coordinates),
 //             W_hi and W_lo boxes {32 k, BN rows}; `stages`-deep mbarrier ring
-//   warp 1    TMEM allocation (4 x BN columns) + single-thread tcgen05.mma.kind::tf32 issue (12 MMAs per k-block)
+//   warp 1    TMEM allocation (4 x BN columns) + single-thread tcgen05.mma.kind::tf32 issue (4 wide + 4 narrow MMAs per k-block)
 //   warps 2-5 splitter: A_lo tile of each stage
 //   warps 6-13 accumulate/epilogue, two groups of four warps owning one half of the BN columns each: tcgen05.ld of each
 //             finished chunk -> += registers; at the end of the tile add the cross-term accumulator, apply scale/shift
@@ -71,7 +76,7 @@ template <int BN>
 struct Cfg32 {
   static constexpr int B_TILE = BN * 128;
   static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;  // A, A_lo, W_hi, W_lo
-  static constexpr uint32_t TMEM_COLS = 4 * BN;                // main[2] (ping-pong per chunk) + cross[2] (per tile)
+  static constexpr uint32_t TMEM_COLS = 4 * BN;                // 2 ping-pong buffers of [main BN | cross BN] columns
   static int stages() {
     int s = (192 * 1024) / STAGE_BYTES;
     return s > MAX_STAGES ? MAX_STAGES : s;
@@ -95,9 +100,8 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = bars + MAX_STAGES;        // the MMAs reading a stage have completed
   uint64_t* split_bar = bars + 2 * MAX_STAGES;    // A_lo of a stage is written (128 arrivals)
   uint64_t* main_full = bars + 3 * MAX_STAGES;    // [2] a chunk's accumulator is complete
-  uint64_t* main_empty = main_full + 2;           // [2] ... and has been drained (128 arrivals)
-  uint64_t* cross_empty = main_empty + 2;         // [2] the tile's cross-term accumulator has been drained
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(cross_empty + 2);
+  uint64_t* main_empty = main_full + 2;           // [2] ... and has been drained (256 arrivals)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(main_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = a.m_tiles * a.n_tiles;
@@ -117,7 +121,6 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&main_full[i], 1);
       mbar_init(&main_empty[i], EPI_THREADS);
-      mbar_init(&cross_empty[i], EPI_THREADS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -172,42 +175,38 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===================== MMA issuer
-      constexpr uint32_t ID = idesc(BN, 2u);
+      constexpr uint32_t ID = idesc(BN, 2u), ID_WIDE = idesc(2 * BN, 2u);
       int s = 0;
-      uint32_t ph = 0, g = 0, t = 0;  // g: running chunk counter (main ping-pong), t: running tile counter (cross)
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-        const uint32_t d_cross = tmem_base + (2 + (t & 1)) * BN;
-        if (comp) {
-          mbar_wait(&cross_empty[t & 1], ((t >> 1) & 1) ^ 1);
-          fence_after();
-        }
+      uint32_t ph = 0, g = 0;  // g: running chunk counter (ping-pong of the [main | cross] accumulator pair)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < nkb; ++kb) {
           const int kc = kb % CHUNK_KB;
           if (kc == 0) {  // a new chunk: its accumulator buffer must have been drained
             mbar_wait(&main_empty[g & 1], ((g >> 1) & 1) ^ 1);
             fence_after();
           }
-          const uint32_t d_main = tmem_base + (g & 1) * BN;
+          const uint32_t d_main = tmem_base + (g & 1) * 2 * BN, d_cross = d_main + BN;
           mbar_wait(&full_bar[s], ph);
           if (!comp) mbar_wait(&split_bar[s], ph);  // plain TF32: the splitter rounds the A tile in place first
           fence_after();
           const uint64_t dA = desc128(s32(stage_A(s))), dAlo = desc128(s32(stage_Alo(s)));
-          const uint64_t dBhi = desc128(s32(stage_Bhi(s))), dBlo = desc128(s32(stage_Blo(s)));
-          // the eight MMAs that only need the TMA data go first: they cover the splitter's latency
-#pragma unroll
-          for (int k = 0; k < 4; ++k)  // +32 B per K=8 step inside the swizzle atom
-            umma_tf32(d_main, dA + 2 * k, dBhi + 2 * k, ID, (kc | k) ? 1u : 0u);
+          const uint64_t dB = desc128(s32(stage_Bhi(s)));  // W_hi rows 0..BN-1, W_lo rows BN..2BN-1 (adjacent tiles)
           if (comp) {
+            // A_hi * [W_hi | W_lo]: needs only TMA data, so it goes first and covers the splitter's latency
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(d_cross, dA + 2 * k, dBlo + 2 * k, ID, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)  // +32 B per K=8 step inside the swizzle atom
+              umma_tf32(d_main, dA + 2 * k, dB + 2 * k, ID_WIDE, (kc | k) ? 1u : 0u);
             mbar_wait(&split_bar[s], ph);
             fence_after();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(d_cross, dAlo + 2 * k, dBhi + 2 * k, ID, 1u);
+            for (int k = 0; k < 4; ++k) umma_tf32(d_cross, dAlo + 2 * k, dB + 2 * k, ID, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(d_main, dA + 2 * k, dB + 2 * k, ID, (kc | k) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have consumed it
           if (kc == CHUNK_KB - 1 || kb == nkb - 1) {
-            umma_commit(&main_full[g & 1]);  // chunk complete (the tile's last one also covers the cross terms)
+            umma_commit(&main_full[g & 1]);
             ++g;
           }
           if (++s == stages) {
@@ -264,9 +263,9 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int lane_base = (warp & 3) * 32;
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
     const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
-    uint32_t g = 0, t = 0;
+    uint32_t g = 0;
     int cur_n0 = -1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = tile_m0(tile), n0 = tile_n0(tile);
       if (n0 != cur_n0) {  // (re)stage the per-channel affine of this n-tile
         if (cur_n0 >= 0) asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone is done with the previous one
@@ -283,7 +282,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c = 0; c < nchunks; ++c, ++g) {
         mbar_wait(&main_full[g & 1], (g >> 1) & 1);
         fence_after();
-        const uint32_t taddr = tmem_base + lane_addr + (g & 1) * BN + half * HN;
+        const uint32_t taddr = tmem_base + lane_addr + (g & 1) * 2 * BN + half * HN;
 #pragma unroll
         for (int j = 0; j < HN / 32; ++j) {
           float v[32];
@@ -291,22 +290,19 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+        }
+        if (comp) {  // the cross terms of the same chunk
+#pragma unroll
+          for (int j = 0; j < HN / 32; ++j) {
+            float v[32];
+            tmem_ld32(taddr + BN + j * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+          }
         }
         fence_before();
         mbar_arrive(&main_empty[g & 1]);
-      }
-      if (comp) {  // the last chunk's commit covered every MMA of the tile, cross terms included
-        const uint32_t taddr = tmem_base + lane_addr + (2 + (t & 1)) * BN + half * HN;
-#pragma unroll
-        for (int j = 0; j < HN / 32; ++j) {
-          float v[32];
-          tmem_ld32(taddr + j * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
-        }
-        fence_before();
-        mbar_arrive(&cross_empty[t & 1]);
       }
       // epilogue: 32 columns at a time through the group's 128B-swizzled staging buffer, written out by one TMA store
       // (whole 128-byte lines; rows beyond M are clipped by the tensor map)
