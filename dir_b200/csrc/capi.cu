@@ -77,6 +77,8 @@ extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
     h->e.disable_tc = dis && dis[0] == '1';
     const char* nh = getenv("DIRB200_NO_HALO");
     h->e.no_halo = nh && nh[0] == '1';
+    const char* npf = getenv("DIRB200_NO_PREACT_FOLD");
+    h->e.no_preact_fold = npf && npf[0] == '1';
     const char* f32s = getenv("DIRB200_FP32_SIMT");
     h->e.fp32_simt = f32s && f32s[0] == '1';
     const char* nopair = getenv("DIRB200_NO_PAIR_FUSION");
@@ -281,11 +283,12 @@ template <typename T>
 static int seam_residual(Engine& e, const ResidualBlock& r, const float* x, int B, int H, int W, float* y, Arena& ar,
                          cudaStream_t st) {
   const int64_t n = (int64_t)B * H * W * r.cin;
+  const bool fold = e.preact_fold_ok<T>(r, B, H, W, 0);  // same path as the forward: conv1 pre-activates its own operand
   T* raw = reinterpret_cast<T*>(ar.alloc(n * sizeof(T)));
-  T* act = reinterpret_cast<T*>(ar.alloc(n * sizeof(T)));
+  T* act = fold ? nullptr : reinterpret_cast<T*>(ar.alloc(n * sizeof(T)));
   if (ar.overflow) return DIRB200_E_WORKSPACE;
   launch_nchw_to_nhwc<T>(x, raw, B, r.cin, H, W, st);
-  launch_concat_preact<T>(raw, r.cin, 0, nullptr, 0, r.bn1s, r.bn1b, nullptr, act, B, H, W, st);
+  if (!fold) launch_concat_preact<T>(raw, r.cin, 0, nullptr, 0, r.bn1s, r.bn1b, nullptr, act, B, H, W, st);
   T* out = e.run_residual<T>(r, raw, act, B, H, W, ar, st);
   if (!out) return DIRB200_E_WORKSPACE;
   launch_nhwc_to_nchw<T>(out, y, B, r.cout, H, W, st);

@@ -44,6 +44,7 @@ constexpr int BM = 128;
 constexpr int NUM_THREADS = 320;  // producer warp + MMA warp + 2 epilogue groups of 4 warps
 constexpr int MAX_STAGES = 8;
 constexpr int CHUNK_BYTES = BM * 128;  // one 64-column bf16 epilogue box: 16 KB
+constexpr int PRE_WARPS = 6;           // transform warps of the PRE kernels (16 warps = 4 per scheduler: same 128-register cap as 14)
 constexpr int RES_BUFS = 4;            // residual ring: the producer prefetches residual chunks ~2 tiles ahead
 
 struct TcArgs {
@@ -58,6 +59,10 @@ struct TcArgs {
   int kb2, stride2;  // K-concatenated second operand: kb2 extra 1x1 k-blocks read from tmA2 at spatial stride2
   int kb2a;          // ... of which the first kb2a come from tmA2 and the rest from tmA3 (a channel concat never built)
   int b_resident;    // 1: the whole weight matrix (one n-tile, all k-blocks) is loaded once per CTA and stays in smem
+  // PRE kernels (1x1 conv with the consuming Residual's pre-activation folded into the A operand, hourglass.py:60-61):
+  const float* pre_scale;  // per INPUT channel: A <- relu(A * pre_scale + pre_shift) in shared memory, before the MMA
+  const float* pre_shift;
+  int pre_cb1;             // the first pre_cb1 channel blocks come from tmA, the rest from tmA2 (virtual channel concat)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,6 +121,24 @@ __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t
 }
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the leader CTA's copy of `bar`
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {  // {bf16(max(lo,0)), bf16(max(hi,0))}, RN
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -199,14 +222,18 @@ struct TcCfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN;
   static constexpr int NCH = BN / 64;
   // bslots = weight tiles held in smem: one per stage, or (resident mode) one per k-block
-  static int smem_bytes(int stages, int has_res, int bslots) {
+  static int smem_bytes(int stages, int has_res, int bslots, int pre = 0) {
     return 1024 + stages * A_STAGE + bslots * B_STAGE + 2 * CHUNK_BYTES + (has_res ? RES_BUFS * CHUNK_BYTES : 0) +
-           4 * BN * 4 + 256;
+           4 * BN * 4 + 256 + (pre ? 128 : 0);
   }
 };
 
-template <int BN, int SW, int CG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// PRE = 1 (1x1 convs only): PRE_WARPS more warps (10-15) apply relu(x * pre_scale[c] + pre_shift[c]) to every A tile in place
+// between its TMA arrival and the MMA: the pre-activated copy of the input never exists in HBM. A tiles then complete on
+// a CTA-local barrier (afull_bar) that the transform warps wait on; the MMA warp waits for the weights (full_bar) and for
+// the transform warps of BOTH CTAs of the pair (xf_bar on the leader, remote arrivals).
+template <int BN, int SW, int CG, int PRE = 0>
+__global__ void __launch_bounds__(NUM_THREADS + PRE * PRE_WARPS * 32, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3, const TcArgs a) {
@@ -234,6 +261,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* res_empty = res_full + RES_BUFS;
   uint64_t* bres_bar = res_empty + RES_BUFS;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  uint64_t* afull_bar = bres_bar + 2;           // PRE only (the extra 128 bytes of smem_bytes(.., pre = 1))
+  uint64_t* xf_bar = afull_bar + MAX_STAGES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_units = a.m_tiles / CG;  // scheduling unit = CG adjacent M tiles (one per CTA of the pair)
@@ -259,6 +288,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&res_empty[i], 1);
     }
     mbar_init(bres_bar, 1);
+    if constexpr (PRE) {
+      for (int s = 0; s < MAX_STAGES; ++s) {
+        mbar_init(&afull_bar[s], 1);
+        mbar_init(&xf_bar[s], CG);  // one arrival per CTA of the pair (the transform warp that owns the k-block)
+      }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: two accumulator buffers of BN fp32 columns x 128 lanes
@@ -306,7 +341,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          if constexpr (CG == 2) {  // both CTAs' bytes are counted on the leader's full barrier
+          if constexpr (PRE) {  // A -> this CTA's afull barrier (transform warps); weights -> the MMA warp's full barrier
+            mbar_expect_tx(&afull_bar[s], Cfg::A_STAGE);
+            const bool first = kb < a.pre_cb1;
+            tma_load_4d(first ? &tmA : &tmA2, &afull_bar[s], sA + s * Cfg::A_STAGE, (first ? kb : kb - a.pre_cb1) * 64,
+                        wo0, ho0, b0);
+            if constexpr (CG == 2) {
+              if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::B_STAGE);
+              tma_load_2d_2sm(&tmB, &full_bar[s], sB + s * Cfg::B_STAGE, kb * 64, nb0);
+            } else {
+              mbar_expect_tx(&full_bar[s], Cfg::B_STAGE);
+              tma_load_2d(&tmB, &full_bar[s], sB + s * Cfg::B_STAGE, kb * 64, n0);
+            }
+          } else if constexpr (CG == 2) {  // both CTAs' bytes are counted on the leader's full barrier
             if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
             if (kb >= nkb1) {
               const int k2 = kb - nkb1;
@@ -369,6 +416,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t d = tmem_base + buf * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[s], ph);
+          if constexpr (PRE) mbar_wait(&xf_bar[s], ph);  // A tiles of the pair transformed in place
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t da = umma_desc<SW>(smem_u32(sA + s * Cfg::A_STAGE));
           const uint64_t db = umma_desc<SW>(smem_u32(sB + (bres ? kb : s) * Cfg::B_STAGE));
@@ -389,6 +437,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if constexpr (CG == 2) umma_commit_2sm(&tmem_full[buf]);
         else umma_commit(&tmem_full[buf]);
       }
+    }
+  } else if (PRE && warp >= 10) {
+    // ===================== pre-activation of the A operand, in place in the 128B-swizzled stage. Warp w owns smem stage
+    // w (the host caps `stages` at PRE_WARPS), i.e. every stages-th k-block of this CTA's stream, so that many
+    // wait -> load -> store -> fence -> arrive chains run concurrently. (A warp must see EVERY phase of a barrier it
+    // waits on: handing k-blocks out round-robin over a different number of warps lets a warp reach a stage one phase
+    // early, where a parity wait passes at once.) lane = 16-byte chunk column q (8 channels: scale/shift in registers
+    // for the k-block) x rows rr + 4 j: one warp instruction touches 4 full 128-byte rows (conflict-free under the swizzle).
+    const int w = warp - 10;
+    const int q = lane & 7, rr = lane >> 3;
+    const uint32_t coff0 = (uint32_t)((q ^ rr) << 4), coff1 = (uint32_t)((q ^ (rr + 4)) << 4);  // row & 7 = rr + 4 (j & 1)
+    const int my_tiles = first_tile < total_tiles ? (total_tiles - first_tile + tile_step - 1) / tile_step : 0;
+    const int total_kb = my_tiles * nkb;
+    const int s = w;
+    int kb = w;
+    uint32_t ph = 0;
+    while (kb >= nkb) kb -= nkb;
+    for (int g = w; w < stages && g < total_kb; g += stages) {
+      const float4* ps = reinterpret_cast<const float4*>(a.pre_scale + kb * 64 + q * 8);
+      const float4* pb = reinterpret_cast<const float4*>(a.pre_shift + kb * 64 + q * 8);
+      const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), h0 = __ldg(pb), h1 = __ldg(pb + 1);
+      mbar_wait(&afull_bar[s], ph);
+      const uint32_t base = smem_u32(sA + s * Cfg::A_STAGE) + (uint32_t)rr * 128u;
+#pragma unroll 1
+      for (int jb = 0; jb < 32; jb += 8) {
+        uint4 u[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = lds128(base + (jb + j) * 512 + ((j & 1) ? coff1 : coff0));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u[j]);
+          const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+          const float2 f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+          uint4 o;
+          o.x = pack_relu_bf16x2(fmaf(f0.x, s0.x, h0.x), fmaf(f0.y, s0.y, h0.y));
+          o.y = pack_relu_bf16x2(fmaf(f1.x, s0.z, h0.z), fmaf(f1.y, s0.w, h0.w));
+          o.z = pack_relu_bf16x2(fmaf(f2.x, s1.x, h1.x), fmaf(f2.y, s1.y, h1.y));
+          o.w = pack_relu_bf16x2(fmaf(f3.x, s1.z, h1.z), fmaf(f3.y, s1.w, h1.w));
+          sts128(base + (jb + j) * 512 + ((j & 1) ? coff1 : coff0), o);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> the MMA's async proxy
+      __syncwarp();
+      if (lane == 0) {
+        // same publication pattern as the epilogue's tmem_empty hand-back: proxy fence, then a (remote) arrive.
+        // (An explicit .release.cluster here compiles to MEMBAR.ALL.GPU per k-block and tripled the kernel time.)
+        if constexpr (CG == 2) mbar_arrive_leader(&xf_bar[s]);
+        else mbar_arrive(&xf_bar[s]);
+      }
+      ph ^= 1;
+      kb += stages;
+      while (kb >= nkb) kb -= nkb;
     }
   } else {
     // ===================== epilogue: two groups of 4 warps take alternate 64-column chunks (global chunk parity),
@@ -427,21 +527,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld32(taddr, r);
         tmem_ld32(taddr + 32, r + 32);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const float* sc = s_scale + c * 64;
-        const float* sh = s_shift + c * 64;
+        const uint32_t sc = smem_u32(s_scale + c * 64);
+        const uint32_t sh = smem_u32(s_shift + c * 64);
         uint4 packed[8];
         if (a.has_res) {
           const uint32_t rb = rchunk % RES_BUFS;
           mbar_wait(&res_full[rb], (rchunk / RES_BUFS) & 1);
-          const uint8_t* rrow = sRes + rb * CHUNK_BYTES + row * 128;
+          const uint32_t rrow = smem_u32(sRes + rb * CHUNK_BYTES + row * 128);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const uint4 u = *reinterpret_cast<const uint4*>(rrow + ((q ^ swz) << 4));
+            const uint4 u = lds128(rrow + ((q ^ swz) << 4));
             const __nv_bfloat162* hres = reinterpret_cast<const __nv_bfloat162*>(&u);
-            const float4 s0 = *reinterpret_cast<const float4*>(sc + q * 8);
-            const float4 s1 = *reinterpret_cast<const float4*>(sc + q * 8 + 4);
-            const float4 h0 = *reinterpret_cast<const float4*>(sh + q * 8);
-            const float4 h1 = *reinterpret_cast<const float4*>(sh + q * 8 + 4);
+            const float4 s0 = lds_f4(sc + q * 32), s1 = lds_f4(sc + q * 32 + 16);
+            const float4 h0 = lds_f4(sh + q * 32), h1 = lds_f4(sh + q * 32 + 16);
             float v[8];
             v[0] = fmaf(__uint_as_float(r[q * 8 + 0]), s0.x, h0.x);
             v[1] = fmaf(__uint_as_float(r[q * 8 + 1]), s0.y, h0.y);
@@ -468,10 +566,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 s0 = *reinterpret_cast<const float4*>(sc + q * 8);
-            const float4 s1 = *reinterpret_cast<const float4*>(sc + q * 8 + 4);
-            const float4 h0 = *reinterpret_cast<const float4*>(sh + q * 8);
-            const float4 h1 = *reinterpret_cast<const float4*>(sh + q * 8 + 4);
+            const float4 s0 = lds_f4(sc + q * 32), s1 = lds_f4(sc + q * 32 + 16);
+            const float4 h0 = lds_f4(sh + q * 32), h1 = lds_f4(sh + q * 32 + 16);
             float v[8];
             v[0] = fmaf(__uint_as_float(r[q * 8 + 0]), s0.x, h0.x);
             v[1] = fmaf(__uint_as_float(r[q * 8 + 1]), s0.y, h0.y);
@@ -493,9 +589,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // (a) this group's previous TMA store must have finished reading its staging buffer
         if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         epi_barrier(eg);  // (b)
-        uint8_t* orow = sOutG + row * 128;
+        const uint32_t orow = smem_u32(sOutG + row * 128);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(orow + ((q ^ swz) << 4)) = packed[q];
+        for (int q = 0; q < 8; ++q) sts128(orow + ((q ^ swz) << 4), packed[q]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // (c) generic-proxy writes -> async proxy
         epi_barrier(eg);  // (d) staging complete; every thread of the group is also done reading its residual slot
         if (et == 0) {
@@ -676,27 +772,29 @@ bool resident_enabled() {
   return on;
 }
 
-template <int BN, int SW, int CG>
+template <int BN, int SW, int CG, int PRE = 0>
 int launch_tc_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                  const CUtensorMap& tmA2, const CUtensorMap& tmA3, TcArgs a, cudaStream_t st) {
   using Cfg = TcCfg<BN, SW, CG>;
   const int nkb = a.taps * a.cblocks + a.kb2;
   // resident weights: one n-tile whose whole K extent fits next to a useful A ring (layer1: <= 72 KB); the TMA engine
   // then only fetches activations (it retires ~one 128-byte box row per 3-5 cycles, the limit of these layers)
-  a.b_resident = (CG == 1 && SW == 128 && !a.stem && a.n_tiles == 1 && nkb * Cfg::B_STAGE <= 80 * 1024 && resident_enabled())
+  a.b_resident = (CG == 1 && SW == 128 && !PRE && !a.stem && a.n_tiles == 1 && nkb * Cfg::B_STAGE <= 80 * 1024 &&
+                  resident_enabled())
                      ? 1 : 0;
   int stages = MAX_STAGES;  // the ring runs ahead across tiles, so short K loops still want every stage that fits
-  while (stages > 1 && Cfg::smem_bytes(stages, a.has_res, a.b_resident ? nkb : stages) > 227 * 1024) --stages;
+  while (stages > 1 && Cfg::smem_bytes(stages, a.has_res, a.b_resident ? nkb : stages, PRE) > 227 * 1024) --stages;
+  if (PRE && stages > PRE_WARPS) stages = PRE_WARPS;  // one transform warp per stage
   a.stages = stages;
-  const int smem = Cfg::smem_bytes(stages, a.has_res, a.b_resident ? nkb : stages);
-  if (ensure_dynamic_smem(reinterpret_cast<const void*>(conv_tc_kernel<BN, SW, CG>), 227 * 1024) != cudaSuccess)
+  const int smem = Cfg::smem_bytes(stages, a.has_res, a.b_resident ? nkb : stages, PRE);
+  if (ensure_dynamic_smem(reinterpret_cast<const void*>(conv_tc_kernel<BN, SW, CG, PRE>), 227 * 1024) != cudaSuccess)
     return DIRB200_E_CUDA;
   const int units = (a.m_tiles / CG) * a.n_tiles;        // scheduling units (one per CTA, or per CTA pair)
   const int slots = num_sms() / CG;
   const int grid = (units < slots ? units : slots) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(NUM_THREADS + PRE * PRE_WARPS * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -716,7 +814,7 @@ int launch_tc_cg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   cfg.attrs = attr;
   cfg.numAttrs = na;
   if (a.kb2a == 0) a.kb2a = a.kb2;  // no third operand
-  if (cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SW, CG>, tmA, tmB, tmY, tmR, tmA2, tmA3, a) != cudaSuccess)
+  if (cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SW, CG, PRE>, tmA, tmB, tmY, tmR, tmA2, tmA3, a) != cudaSuccess)
     return DIRB200_E_CUDA;
   return DIRB200_OK;
 }
@@ -968,6 +1066,47 @@ int launch_conv_tc_dual(const ConvLayer& L, const __nv_bfloat16* x1, int C1, con
     case 128: return launch_tc<128, 128>(tmA, L.wmap, L.wmap2_ok ? &L.wmap2 : nullptr, tmY, tmY, tmA2, a, st, tmA3);
     default: return launch_tc<64, 128>(tmA, L.wmap, nullptr, tmY, tmY, tmA2, a, st, tmA3);
   }
+}
+
+bool conv_tc_pre_supported(const ConvLayer& L, int B, int H, int W, int C1, int C2) {
+  return L.kh == 1 && L.kw == 1 && L.stride == 1 && L.pad == 0 && L.wmap_bn == 128 &&
+         C1 % 64 == 0 && C2 % 64 == 0 && C1 + C2 == L.Cin && conv_tc_supported(L, B, H, W);
+}
+
+// 1x1 conv over relu(bn(x)) with x = [x1 (C1 channels) | x2 (C2 channels, may be null)]: the pre-activation of the
+// consuming Residual (models/backbone/hourglass.py:60-61) is applied to the A tiles in shared memory (PRE kernels), so
+// neither the pre-activated tensor nor the channel concat is ever written.
+int launch_conv_tc_pre(const ConvLayer& L, const __nv_bfloat16* x1, int C1, const __nv_bfloat16* x2, int C2,
+                       const float* pre_scale, const float* pre_shift, __nv_bfloat16* y, int B, int H, int W,
+                       cudaStream_t st) {
+  const Boxes bx = pick_boxes(H, W);
+  CUtensorMap tmA, tmA2, tmY;
+  const int M = B * H * W;
+  if (!act_map_cached(x1, B, H, W, C1, 1, bx, L.name.c_str(), &tmA) || !rowmajor_map_cached(y, M, L.Cout, &tmY))
+    return DIRB200_E_CUDA;
+  if (!x2 || C2 == 0) tmA2 = tmA;
+  else if (!act_map_cached(x2, B, H, W, C2, 1, bx, L.name.c_str(), &tmA2)) return DIRB200_E_CUDA;
+  TcArgs a{};
+  a.scale = L.scale;
+  a.shift = L.shift;
+  a.M = M;
+  a.Cout = L.Cout;
+  a.Ho = H;
+  a.Wo = W;
+  a.stride = 1;
+  a.pad = 0;
+  a.kw = 1;
+  a.taps = 1;
+  a.cblocks = L.Cin / 64;
+  a.relu = L.relu;
+  a.m_tiles = (M + BM - 1) / BM;
+  a.n_tiles = L.Cout / L.wmap_bn;
+  a.pre_scale = pre_scale;
+  a.pre_shift = pre_shift;
+  a.pre_cb1 = C1 / 64;
+  const bool cg2 = L.wmap2_ok && cg2_enabled() && a.m_tiles % 2 == 0;
+  return cg2 ? launch_tc_cg<128, 128, 2, 1>(tmA, L.wmap2, tmY, tmY, tmA2, tmA2, a, st)
+             : launch_tc_cg<128, 128, 1, 1>(tmA, L.wmap, tmY, tmY, tmA2, tmA2, a, st);
 }
 
 int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bfloat16* res, int B,

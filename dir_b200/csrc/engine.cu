@@ -875,6 +875,44 @@ bool Engine::virtual_concat_ok(const ResidualBlock& r, int B, int H, int W_) con
   return conv_tc_supported(probe, B, H, W_);
 }
 
+// true if conv1 of `r` can apply the block's pre-activation (bn1 + ReLU, hourglass.py:60-61) to its own A tiles, reading
+// the raw input from one source (c2 = 0) or from the two sources of a channel concat (c2 = channels of the second)
+template <typename T>
+bool Engine::preact_fold_ok(const ResidualBlock& r, int B, int H, int W_, int c2) const {
+  return sizeof(T) == 2 && !disable_tc && !no_preact_fold && conv_tc_pre_supported(r.c1, B, H, W_, r.c1.Cin - c2, c2);
+}
+
+// conv1 of a Residual with the pre-activation folded in (PRE variant of conv_tc_kernel)
+void Engine::conv_pre(const ResidualBlock& r, const __nv_bfloat16* x1, const __nv_bfloat16* x2, int c2, __nv_bfloat16* y,
+                      int B, int H, int W_, cudaStream_t st) {
+  const ConvLayer& L = r.c1;
+  ++launches;
+  ++tc_launches;
+  Engine::ProfRec* pr = nullptr;
+  if (prof_on && L.name.compare(0, prof_prefix.size(), prof_prefix) == 0) {
+    if (prof_used == prof.size()) {
+      ProfRec rec;
+      cudaEventCreate(&rec.a);
+      cudaEventCreate(&rec.b);
+      rec.flops = 0;
+      prof.push_back(rec);
+    }
+    pr = &prof[prof_used++];
+    pr->flops = 2.0 * B * H * W_ * (double)L.Cout * L.K;
+    pr->bytes = 2.0 * ((double)B * H * W_ * (L.Cin + L.Cout) + (double)L.Cout * L.K);
+    pr->layer = &L;
+    pr->tc = 1;
+    cudaEventRecord(pr->a, st);
+  }
+  int rc = launch_conv_tc_pre(L, x1, L.Cin - c2, x2, c2, r.bn1s, r.bn1b, y, B, H, W_, st);
+  if (pr) cudaEventRecord(pr->b, st);
+  if (rc && !sticky_rc) {
+    sticky_rc = rc;
+    err = "tcgen05 pre-activated conv launch failed for " + L.name;
+  }
+}
+
+// act == null: the caller checked preact_fold_ok(); conv1 reads the raw input and pre-activates it on the fly
 template <typename T>
 T* Engine::run_residual(const ResidualBlock& r, const T* rawx, const T* act, int B, int H, int W_, Arena& ar,
                         cudaStream_t st, const T* raw2, int c2) {
@@ -884,7 +922,15 @@ T* Engine::run_residual(const ResidualBlock& r, const T* rawx, const T* act, int
   T* sk = r.need_skip ? aalloc<T>(ar, px * r.cout) : nullptr;
   T* out = aalloc<T>(ar, px * r.cout);
   if (!ar.base || ar.overflow) return nullptr;
-  conv<T>(r.c1, act, t1, nullptr, B, H, W_, st);
+  if (act) {
+    conv<T>(r.c1, act, t1, nullptr, B, H, W_, st);
+  } else if (sizeof(T) == 2) {
+    conv_pre(r, reinterpret_cast<const __nv_bfloat16*>(rawx), reinterpret_cast<const __nv_bfloat16*>(raw2), raw2 ? c2 : 0,
+             reinterpret_cast<__nv_bfloat16*>(t1), B, H, W_, st);
+  } else if (!sticky_rc) {
+    sticky_rc = DIRB200_E_STATE;
+    err = "folded pre-activation needs the tensor-core conv";
+  }
   conv<T>(r.c2, t1, t2, nullptr, B, H, W_, st);
   if (r.need_skip && conv_pair<T>(r.c3skip, r.c3, r.skip, t2, rawx, out, B, H, W_, st, raw2, c2)) return out;
   if (raw2) {  // callers check virtual_concat_ok() first
@@ -1109,9 +1155,12 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   auto concat = [&](const T* s0, int C0, int up, const T* s1, int C1, const ResidualBlock& r, int S, T** rawo,
                     T** acto) {
     const int64_t n = (int64_t)B * S * S * (C0 + C1);
+    // bf16 configuration: the pre-activated copy is never written (conv1 of `r` pre-activates its A tiles, PRE kernels);
+    // what remains of this pass is the upsample + concat into `raw`, and nothing at all for a single full-size source
+    const bool fold = preact_fold_ok<T>(r, B, S, S, 0);
     *rawo = s1 ? aalloc<T>(ar, n) : nullptr;
-    *acto = aalloc<T>(ar, n);
-    if (plan || ar.overflow) return;
+    *acto = fold ? nullptr : aalloc<T>(ar, n);
+    if (plan || ar.overflow || (fold && !s1)) return;
     launch_concat_preact<T>(s0, C0, up, s1, C1, r.bn1s, r.bn1b, *rawo, *acto, B, S, S, st);
     ++launches;
   };
@@ -1147,7 +1196,7 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
     cudaStreamWaitEvent(side, ev_fork[0], 0);
   }
   T *raw3 = nullptr, *act3 = nullptr;
-  {
+  if (!preact_fold_ok<T>(skip3, B, 32, 32, 0)) {
     const int64_t n = (int64_t)B * 32 * 32 * c2ch;
     act3 = aalloc<T>(ar, n);
     if (!plan && !ar.overflow) {
@@ -1172,6 +1221,8 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   // enhance_layer{4,3}: the block input cat(fusion, img_feat) is only pre-activated (act); its raw copy is never
   // written: the skip half of the pair GEMM reads the two sources directly (third A operand of conv_tc_kernel)
   auto enhance = [&](const ResidualBlock& r, const T* a0, const T* a1, int S) -> T* {
+    if (virtual_concat_ok<T>(r, B, S, S) && preact_fold_ok<T>(r, B, S, S, 256))  // neither concat nor pre-activation
+      return run_residual<T>(r, a0, (const T*)nullptr, B, S, S, ar, st, a1, 256);  // is materialised
     if (virtual_concat_ok<T>(r, B, S, S)) {
       T* acto = aalloc<T>(ar, (int64_t)B * S * S * 512);
       if (!plan && !ar.overflow) {
@@ -1231,6 +1282,8 @@ template int Engine::run_backbone<float>(const float*, int, int, int, Arena&, fl
                                          cudaStream_t);
 template int Engine::run_backbone<__nv_bfloat16>(const float*, int, int, int, Arena&, __nv_bfloat16**,
                                                  __nv_bfloat16**, __nv_bfloat16**, __nv_bfloat16**, cudaStream_t);
+template bool Engine::preact_fold_ok<float>(const ResidualBlock&, int, int, int, int) const;
+template bool Engine::preact_fold_ok<__nv_bfloat16>(const ResidualBlock&, int, int, int, int) const;
 template float* Engine::run_residual<float>(const ResidualBlock&, const float*, const float*, int, int, int, Arena&,
                                             cudaStream_t, const float*, int);
 template __nv_bfloat16* Engine::run_residual<__nv_bfloat16>(const ResidualBlock&, const __nv_bfloat16*,

@@ -124,6 +124,7 @@ struct Engine {
   bool dense_fusion = false;  // DIRB200_DENSE_FUSION=1: materialise bone_proj and run the dense 2560-ch conv
   bool disable_pair_fusion = false;  // DIRB200_NO_PAIR_FUSION=1: keep conv3 and skip/downsample as separate launches
   bool disable_tc = false;  // DIRB200_DISABLE_TC=1: force the CUDA-core conv in bf16 mode (debug A/B)
+  bool no_preact_fold = false;  // DIRB200_NO_PREACT_FOLD=1: Residual pre-activations as a separate pass (concat_preact_kernel)
   bool no_halo = false;     // DIRB200_NO_HALO=1: 64-channel 3x3 convs on the per-tap kernel (conv_tc.cu) instead of conv_halo.cu
   bool fp32_simt = false;   // DIRB200_FP32_SIMT=1: fp32 configuration on the CUDA-core conv (the round-1 path; debug A/B)
   const ConvLayer* find_conv(const std::string& weight_key) const;
@@ -214,6 +215,10 @@ struct Engine {
   // raw2 != null: the block input is the channel concat [raw (cin - c2 channels) | raw2 (c2 channels)], never built
   T* run_residual(const ResidualBlock& r, const T* raw, const T* act, int B, int H, int W_, Arena& ar, cudaStream_t st,
                   const T* raw2 = nullptr, int c2 = 0);
+  template <typename T>
+  bool preact_fold_ok(const ResidualBlock& r, int B, int H, int W_, int c2) const;
+  void conv_pre(const ResidualBlock& r, const __nv_bfloat16* x1, const __nv_bfloat16* x2, int c2, __nv_bfloat16* y, int B,
+                int H, int W_, cudaStream_t st);
   // true if run_residual can take the skip operand of `r` from two sources (tensor-core pair GEMM available)
   template <typename T>
   bool virtual_concat_ok(const ResidualBlock& r, int B, int H, int W_) const;
@@ -255,6 +260,11 @@ int launch_conv_tc(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y,
                    int H, int W, cudaStream_t st);
 int conv_tc_prepare_dual(ConvLayer& F, const ConvLayer& main, const ConvLayer& second, __nv_bfloat16* w16, float* scale,
                          float* shift, cudaStream_t st);
+// 1x1 conv over relu(x * pre_scale + pre_shift), x = [x1 | x2] by channels, pre-activation applied in shared memory
+bool conv_tc_pre_supported(const ConvLayer& L, int B, int H, int W, int C1, int C2);
+int launch_conv_tc_pre(const ConvLayer& L, const __nv_bfloat16* x1, int C1, const __nv_bfloat16* x2, int C2,
+                       const float* pre_scale, const float* pre_shift, __nv_bfloat16* y, int B, int H, int W,
+                       cudaStream_t st);
 int launch_conv_tc_dual(const ConvLayer& L, const __nv_bfloat16* x1, int C1, const __nv_bfloat16* x2, int C2, int stride2,
                         __nv_bfloat16* y, int B, int Ho, int Wo, cudaStream_t st, const __nv_bfloat16* x2b = nullptr,
                         int C2b = 0);

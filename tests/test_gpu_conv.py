@@ -225,3 +225,57 @@ def test_halo_conv_vs_per_tap_kernel_and_reference(synth_sd, monkeypatch, B, H, 
     scale = float(want.abs().max())
     assert float((a.cpu() - want).abs().max()) / scale < 6e-3
     assert float((a - b).abs().max()) / scale < 4e-3  # one bf16 ulp of the output at most, from the summation order
+
+
+RESIDUALS = [("decoder.skip_layer4.", 1024, 16), ("decoder.fusion_layer4.", 2304, 16), ("decoder.enhance_layer4.", 512, 16),
+             ("decoder.skip_layer3.", 512, 32), ("decoder.fusion_layer3.", 512, 32), ("decoder.enhance_layer3.", 512, 32)]
+
+
+@pytest.mark.parametrize("B", [1, 3, 4])
+def test_residual_preactivation_folded_into_conv1_is_bit_identical(synth_sd, monkeypatch, B):
+    """hourglass.py:60-61 (bn1 + ReLU of a Residual) applied by conv1 to its own A tiles in shared memory (PRE variant of
+    conv_tc_kernel: transform warps between the TMA arrival and the MMA; 2-CTA pairs for even tile counts, single CTAs for
+    B = 1 and 3 at 16x16) against the separate pre-activation pass it replaces (DIRB200_NO_PREACT_FOLD=1). Same bf16
+    input, same fp32 fma + ReLU, same rounding, same MMA order: the block outputs must be bit-identical; and both must
+    sit at the bf16-operand distance from the fp32 oracle."""
+    from dir_b200 import seams
+    from oracle import dir_oracle as O
+
+    fold = _model(synth_sd, "bf16")
+    monkeypatch.setenv("DIRB200_NO_PREACT_FOLD", "1")
+    sep = _model(synth_sd, "bf16")
+    sep._ensure_handle()  # the handle reads the switch at creation
+    monkeypatch.delenv("DIRB200_NO_PREACT_FOLD")
+    for name, cin, S in RESIDUALS:
+        g = torch.Generator().manual_seed(B * 100 + cin + S)
+        x = torch.randn(B, cin, S, S, generator=g)
+        a = seams.residual(fold, name, x.cuda())
+        b = seams.residual(sep, name, x.cuda())
+        assert torch.equal(a, b), (name, float((a - b).abs().max()))
+        with torch.no_grad():
+            want = O.residual(synth_sd, name, x)
+        assert float((a.cpu() - want).abs().max() / want.abs().max()) < 3e-2, name
+
+
+def test_whole_forward_with_and_without_preact_fold_bit_identical(synth_sd, monkeypatch):
+    """The forward with every Residual pre-activation folded (4 of the 6 concat_preact launches gone, the other 2 reduced
+    to upsample + concat; both sources of enhance_layer{4,3}'s virtual concat pre-activated in flight) equals the forward
+    with the separate pass, bit for bit, at an even and an odd batch."""
+    fold = _model(synth_sd, "bf16")
+    monkeypatch.setenv("DIRB200_NO_PREACT_FOLD", "1")
+    sep = _model(synth_sd, "bf16")
+    sep._ensure_handle()
+    monkeypatch.delenv("DIRB200_NO_PREACT_FOLD")
+    for B in (4, 5):
+        img = torch.randn(B, 3, 256, 256, generator=torch.Generator().manual_seed(B)).cuda()
+        oa = {k: v.clone() for k, v in fold.run_raw(img).items()}
+        ob = sep.run_raw(img)
+        torch.cuda.synchronize()
+        for k in ("record", "mano_para", "seg", "dense", "proj_feat"):
+            assert torch.equal(oa[k], ob[k]), (B, k, float((oa[k] - ob[k]).abs().max()))
+        for _ in range(25):  # the transform warps race nobody: every repetition reproduces the same bits
+            oc = fold.run_raw(img)
+            assert torch.equal(oa["record"], oc["record"])
+        n_fold = fold._handle.lib.dirb200_forward_launches(fold._handle.h, B)
+        n_sep = sep._handle.lib.dirb200_forward_launches(sep._handle.h, B)
+        assert n_fold == n_sep - 4, (n_fold, n_sep)
