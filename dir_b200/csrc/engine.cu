@@ -1164,14 +1164,28 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
     launch_concat_preact<T>(s0, C0, up, s1, C1, r.bn1s, r.bn1b, *rawo, *acto, B, S, S, st);
     ++launches;
   };
+  // fusion_layer{4,3}: Residual over cat(upsample2x(s0), s1) (models/dir.py:443-444,460-461). With the pre-activation
+  // folded and the pair GEMM available only upsample2x(s0) is materialised; conv1 and the skip conv read s1 in place.
+  auto up_residual = [&](const ResidualBlock& r, const T* s0, int C0, const T* s1, int C1, int S) -> T* {
+    if (virtual_concat_ok<T>(r, B, S, S) && preact_fold_ok<T>(r, B, S, S, C1)) {
+      T* up = aalloc<T>(ar, (int64_t)B * S * S * C0);
+      if (!plan && !ar.overflow) {
+        launch_concat_preact<T>(s0, C0, 1, (const T*)nullptr, 0, r.bn1s, r.bn1b, up, (T*)nullptr, B, S, S, st);
+        ++launches;
+      }
+      return run_residual<T>(r, up, (const T*)nullptr, B, S, S, ar, st, s1, C1);
+    }
+    T *rw = nullptr, *ac = nullptr;
+    concat(s0, C0, 1, s1, C1, r, S, &rw, &ac);
+    return run_residual<T>(r, rw, ac, B, S, S, ar, st);
+  };
   // ---- stage 1 @16x16 (models/dir.py:442-456)
   T *raw = nullptr, *act = nullptr;
   const ResidualBlock& skip4 = res["decoder.skip_layer4."];
   concat(c3, c3ch, 0, nullptr, 0, skip4, 16, &raw, &act);
   T* c3_skip = run_residual<T>(skip4, c3, act, B, 16, 16, ar, st);
   const ResidualBlock& fus4 = res["decoder.fusion_layer4."];
-  concat(c4, c4ch, 1, c3_skip, 256, fus4, 16, &raw, &act);
-  T* fusion4 = run_residual<T>(fus4, raw, act, B, 16, 16, ar, st);
+  T* fusion4 = up_residual(fus4, c4, c4ch, c3_skip, 256, 16);
   if (cfg.refine_stages == 1) {  // "1 refine iter": init regression + projecter_4 only (truncation after models/dir.py:456)
     T* img_feat1 = nullptr;
     rc = run_stage<T>(0, fusion4, rec, RS, para, PS, B, plan ? nullptr : rec + DIRB200_STAGE_FLOATS, RS,
@@ -1240,8 +1254,7 @@ int Engine::forward(const float* img, int B, Arena& ar, const dirb200_outputs* o
   // ---- stage 2 @32x32 (models/dir.py:459-471)
   if (overlap) cudaStreamWaitEvent(st, ev_join[0], 0);
   const ResidualBlock& fus3 = res["decoder.fusion_layer3."];
-  concat(enhance4, 256, 1, c2_skip, 256, fus3, 32, &raw, &act);
-  T* fusion3 = run_residual<T>(fus3, raw, act, B, 32, 32, ar, st);
+  T* fusion3 = up_residual(fus3, enhance4, 256, c2_skip, 256, 32);
   T* img_feat2 = nullptr;
   const bool aux = cfg.aux_outputs != 0;
   rc = run_stage<T>(1, fusion3, plan ? nullptr : rec + DIRB200_STAGE_FLOATS, RS, plan ? nullptr : para + 128, PS, B,
