@@ -77,6 +77,8 @@ extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
     h->e.disable_tc = dis && dis[0] == '1';
     const char* nh = getenv("DIRB200_NO_HALO");
     h->e.no_halo = nh && nh[0] == '1';
+    const char* nb2b = getenv("DIRB200_NO_B2B");
+    h->e.no_b2b = nb2b && nb2b[0] == '1';
     const char* npf = getenv("DIRB200_NO_PREACT_FOLD");
     h->e.no_preact_fold = npf && npf[0] == '1';
     const char* f32s = getenv("DIRB200_FP32_SIMT");

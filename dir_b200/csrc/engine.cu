@@ -719,6 +719,47 @@ void Engine::conv(const ConvLayer& L, const T* x, T* y, const T* resid, int B, i
   if (pr) cudaEventRecord(pr->b, st);
 }
 
+// Bottleneck tail (conv3 + identity, or the conv3 + downsample pair) and conv1 of the next block in one kernel; returns
+// false if the shapes are not covered (then the caller runs them separately). t1_next receives conv1's output.
+template <typename T>
+bool Engine::conv_b2b(const Bottleneck& bk, const Bottleneck& nx, const T* t2, const T* x, T* out, T* t1_next, int B,
+                      int Ho, int Wo, cudaStream_t st) {
+  if (sizeof(T) != 2 || disable_tc || no_b2b) return false;
+  const bool pair = bk.has_ds;
+  if (pair && (disable_pair_fusion || bk.c3ds.wmap_bn == 0 || bk.ds.stride != 1)) return false;
+  const ConvLayer& first = pair ? bk.c3ds : bk.c3;
+  const int Ka = bk.c3.Cin, Kb = pair ? bk.ds.Cin : 0, M = B * Ho * Wo;
+  if (!conv_b2b_supported(first, Ka, Kb, nx.c1, M, !pair)) return false;
+  launches += 1;
+  tc_launches += 1;
+  Engine::ProfRec* pr = nullptr;
+  if (prof_on && first.name.compare(0, prof_prefix.size(), prof_prefix) == 0) {
+    if (prof_used == prof.size()) {
+      ProfRec r;
+      cudaEventCreate(&r.a);
+      cudaEventCreate(&r.b);
+      prof.push_back(r);
+    }
+    pr = &prof[prof_used++];
+    pr->flops = 2.0 * M * ((double)first.Cout * first.K + (double)nx.c1.Cout * nx.c1.K);
+    pr->bytes = 2.0 * ((double)M * (first.K + (pair ? 0 : first.Cout) + first.Cout + nx.c1.Cout) +
+                       (double)first.Cout * first.K + (double)nx.c1.Cout * nx.c1.K);
+    pr->layer = &first;
+    pr->tc = 1;
+    cudaEventRecord(pr->a, st);
+  }
+  int rc = launch_conv_b2b(first, reinterpret_cast<const __nv_bfloat16*>(t2), Ka,
+                           pair ? reinterpret_cast<const __nv_bfloat16*>(x) : nullptr, Kb,
+                           pair ? nullptr : reinterpret_cast<const __nv_bfloat16*>(x), nx.c1,
+                           reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<__nv_bfloat16*>(t1_next), M, st);
+  if (pr) cudaEventRecord(pr->b, st);
+  if (rc && !sticky_rc) {
+    sticky_rc = rc;
+    err = "back-to-back conv launch failed for " + first.name;
+  }
+  return true;
+}
+
 // conv3 + (downsample | skip) as one K-concatenated tensor-core GEMM; returns false if the pair must run separately
 template <typename T>
 bool Engine::conv_pair(const ConvLayer& F, const ConvLayer& main, const ConvLayer& second, const T* x1, const T* x2,
@@ -831,20 +872,27 @@ int Engine::run_backbone(const float* img, int B, int H, int W_, Arena& ar, T** 
   }
   const T* x = pool_out;
   int xi = -1;  // index of the rotating buffer holding x (-1: none)
+  int t1i = -1;  // index of the rotating buffer that already holds conv1's output of the coming block (-1: none)
   int h = H4, w = W4;
   for (int l = 0; l < 4; ++l) {
     for (size_t b = 0; b < layers[l].size(); ++b) {
       const Bottleneck& bk = layers[l][b];
       int idx[4], n = 0;
+      if (t1i >= 0) idx[n++] = t1i;
       for (int i = 0; i < 5 && n < 4; ++i)
-        if (i != xi) idx[n++] = i;
+        if (i != xi && i != t1i) idx[n++] = i;
       T *t1 = R[idx[0]], *t2 = R[idx[1]], *dsb = R[idx[2]], *out = R[idx[3]];
       const bool last = b + 1 == layers[l].size();
       if (last && keep[l]) out = keep[l];
       const int ho = h / bk.c2.stride, wo = w / bk.c2.stride;
-      conv<T>(bk.c1, x, t1, nullptr, B, h, w, st);
+      if (t1i < 0) conv<T>(bk.c1, x, t1, nullptr, B, h, w, st);  // else: written by the previous block's tail kernel
+      t1i = -1;
       conv<T>(bk.c2, t1, t2, nullptr, B, h, w, st);
-      if (!(bk.has_ds && conv_pair<T>(bk.c3ds, bk.c3, bk.ds, t2, x, out, B, ho, wo, st))) {
+      // tail of this block + conv1 of the next one as back-to-back GEMMs (conv_b2b.cu): `out` is not re-read
+      const Bottleneck* nx = !last ? &layers[l][b + 1] : (l + 1 < 4 ? &layers[l + 1][0] : nullptr);
+      if (nx && conv_b2b<T>(bk, *nx, t2, x, out, dsb, B, ho, wo, st)) {
+        t1i = idx[2];
+      } else if (!(bk.has_ds && conv_pair<T>(bk.c3ds, bk.c3, bk.ds, t2, x, out, B, ho, wo, st))) {
         const T* identity = x;
         if (bk.has_ds) {
           conv<T>(bk.ds, x, dsb, nullptr, B, h, w, st);

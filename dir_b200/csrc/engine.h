@@ -124,6 +124,7 @@ struct Engine {
   bool dense_fusion = false;  // DIRB200_DENSE_FUSION=1: materialise bone_proj and run the dense 2560-ch conv
   bool disable_pair_fusion = false;  // DIRB200_NO_PAIR_FUSION=1: keep conv3 and skip/downsample as separate launches
   bool disable_tc = false;  // DIRB200_DISABLE_TC=1: force the CUDA-core conv in bf16 mode (debug A/B)
+  bool no_b2b = false;          // DIRB200_NO_B2B=1: bottleneck tail and the next block's conv1 as separate launches
   bool no_preact_fold = false;  // DIRB200_NO_PREACT_FOLD=1: Residual pre-activations as a separate pass (concat_preact_kernel)
   bool no_halo = false;     // DIRB200_NO_HALO=1: 64-channel 3x3 convs on the per-tap kernel (conv_tc.cu) instead of conv_halo.cu
   bool fp32_simt = false;   // DIRB200_FP32_SIMT=1: fp32 configuration on the CUDA-core conv (the round-1 path; debug A/B)
@@ -207,6 +208,9 @@ struct Engine {
             bool in_nchw = false);
   void make_dual(ConvLayer& F, const ConvLayer& main, const ConvLayer& second);
   template <typename T>
+  bool conv_b2b(const Bottleneck& bk, const Bottleneck& nx, const T* t2, const T* x, T* out, T* t1_next, int B, int Ho,
+                int Wo, cudaStream_t st);
+  template <typename T>
   bool conv_pair(const ConvLayer& F, const ConvLayer& main, const ConvLayer& second, const T* x1, const T* x2, T* y,
                  int B, int Ho, int Wo, cudaStream_t st, const T* x2b = nullptr, int C2b = 0);
   template <typename T>
@@ -253,6 +257,11 @@ int launch_conv_tf32_stem(const ConvLayer& L, const float* img, float* scratch, 
 bool conv_halo_supported(const ConvLayer& L, int B, int H, int W);
 int launch_conv_halo(const ConvLayer& L, const __nv_bfloat16* x, __nv_bfloat16* y, const __nv_bfloat16* res, int B, int H,
                      int W, cudaStream_t st);
+// back-to-back 1x1 convs across a bottleneck boundary (conv_b2b.cu)
+bool conv_b2b_supported(const ConvLayer& first, int Ka, int Kb, const ConvLayer& next, int M, bool has_res);
+int launch_conv_b2b(const ConvLayer& first, const __nv_bfloat16* xa, int Ka, const __nv_bfloat16* xb, int Kb,
+                    const __nv_bfloat16* res, const ConvLayer& next, __nv_bfloat16* out, __nv_bfloat16* t1, int M,
+                    cudaStream_t st);
 // tensor-core conv (conv_tc.cu). Returns false if the shape is not supported (caller falls back to CUDA cores).
 bool conv_tc_supported(const ConvLayer& L, int B, int H, int W);
 int conv_tc_prepare_weights(ConvLayer& L);  // builds L.wmap

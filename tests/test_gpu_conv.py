@@ -279,3 +279,33 @@ def test_whole_forward_with_and_without_preact_fold_bit_identical(synth_sd, monk
         n_fold = fold._handle.lib.dirb200_forward_launches(fold._handle.h, B)
         n_sep = sep._handle.lib.dirb200_forward_launches(sep._handle.h, B)
         assert n_fold == n_sep - 4, (n_fold, n_sep)
+
+
+@pytest.mark.parametrize("B", [1, 2, 5])
+def test_bottleneck_tail_and_next_conv1_back_to_back_bit_identical(synth_sd, monkeypatch, B):
+    """conv_b2b.cu: conv3 (+identity, or the conv3+downsample pair of block 0) of a layer1 bottleneck and conv1 of the
+    next block (layer1.1, layer1.2, layer2.0) as back-to-back GEMMs, the 256-channel block output handed from the
+    first GEMM's store staging to the second GEMM as its A operand (models/backbone/resnet.py:120-140). Against the
+    separate launches (DIRB200_NO_B2B=1): same bf16 operands, same fp32 accumulation order over K, same epilogue
+    arithmetic, so c1..c4 must be bit-identical, and three launches disappear."""
+    from dir_b200 import seams
+
+    fused = _model(synth_sd, "bf16")
+    monkeypatch.setenv("DIRB200_NO_B2B", "1")
+    sep = _model(synth_sd, "bf16")
+    sep._ensure_handle()
+    monkeypatch.delenv("DIRB200_NO_B2B")
+    img = torch.randn(B, 3, 256, 256, generator=torch.Generator().manual_seed(40 + B)).cuda()
+    a = seams.backbone(fused, img)
+    b = seams.backbone(sep, img)
+    for i, (u, v) in enumerate(zip(a, b)):
+        assert torch.equal(u, v), (f"c{i + 1}", float((u - v).abs().max()), float(v.abs().max()))
+    for _ in range(10):  # no race between the store staging, the second GEMM and the next tile's epilogue
+        c = seams.backbone(fused, img)
+        assert all(torch.equal(u, v) for u, v in zip(a, c))
+    oa = fused.run_raw(img)["record"].clone()
+    ob = sep.run_raw(img)["record"]
+    assert torch.equal(oa, ob)
+    n_f = fused._handle.lib.dirb200_forward_launches(fused._handle.h, B)
+    n_s = sep._handle.lib.dirb200_forward_launches(sep._handle.h, B)
+    assert n_f == n_s - 3, (n_f, n_s)
