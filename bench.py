@@ -452,7 +452,7 @@ def main():
                 t = json.load(f)
             if t.get("batch") == B and t.get("precision") == args.precision:
                 traffic = t.get("family_dram_bytes_per_launch")
-        kname = "conv_tc_kernel<BN,128,CG> + conv3x3_c64_halo_kernel (tcgen05 bf16 implicit GEMM)" if args.precision == "bf16" else \
+        kname = "conv_tc_kernel<BN,128,CG,PRE> + conv3x3_c64_halo_kernel + conv1x1_b2b_kernel<N2> (tcgen05 bf16 implicit GEMM)" if args.precision == "bf16" else \
                 "conv_tf32_kernel<BN> (tcgen05 kind::tf32 implicit GEMM)"
         roof = {"bound": "tensor", "kernel": f"{kname}: all {n_launch // prof_steps} launches of a step "
                                              f"({fam_fl / n_launch / 1e9:.1f} GFLOP/launch executed, algorithmic 2*M*N*K)",

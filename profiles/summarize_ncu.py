@@ -34,7 +34,7 @@ def conv(path, per_forward):
           f"launch; L2->SM (xbar2l1tex) {l2sm / 1e9:.2f} GB")
     print(f"{'#':>3s} {'kernel':28s} {'grid':>6s} {'us':>8s} {'tensor%':>8s} {'dramR MB':>9s} {'dramW MB':>9s} {'L2->SM MB':>10s} {'DRAM GB/s':>10s}")
     for i, l in enumerate(launches):
-        k = re.search(r"(conv_\w+<[^>]*>|conv3x3_c64_halo_kernel)", l["name"])
+        k = re.search(r"(conv_\w+<[^>]*>|conv3x3_c64_halo_kernel|conv1x1_b2b_kernel<[^>]*>)", l["name"])
         ns = l["gpu__time_duration.sum"]
         rd, wr = l["dram__bytes_read.sum"], l["dram__bytes_write.sum"]
         print(f"{i:3d} {k.group(1) if k else l['name'][:28]:28s} {l['grid'].split(',')[0].strip('('):>6s} {ns / 1e3:8.1f} {l[T]:8.1f} "

@@ -8,10 +8,10 @@ $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/launches_r2_bf
 $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/launches_r2_fp32_b32.csv python scripts/one_forward.py --precision fp32 --batch 32 --iters 3 > gpurun_out/ncu_b.log 2>&1
 # per-launch tensor pipe / DRAM / L2->SM of every conv launch of the last forward (both configurations)
 M="gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes_equiv_l1sectormiss_pipe_lsu_mem_global_op_ld.sum,l1tex__m_xbar2l1tex_read_bytes.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed"
-$NCU --metrics $M -k "regex:conv_tc_kernel|conv3x3_c64_halo_kernel" --csv --log-file gpurun_out/conv_ncu_r2_bf16.csv python scripts/one_forward.py --precision bf16 --batch 128 --iters 2 > gpurun_out/ncu_c.log 2>&1
+$NCU --metrics $M -k "regex:conv_tc_kernel|conv3x3_c64_halo_kernel|conv1x1_b2b_kernel" --csv --log-file gpurun_out/conv_ncu_r2_bf16.csv python scripts/one_forward.py --precision bf16 --batch 128 --iters 2 > gpurun_out/ncu_c.log 2>&1
 $NCU --metrics $M -k regex:conv_tf32_kernel --csv --log-file gpurun_out/conv_ncu_r2_fp32.csv python scripts/one_forward.py --precision fp32 --batch 32 --iters 2 > gpurun_out/ncu_d.log 2>&1
 # --set full of the joint-space tensor-core kernels (bf16 configuration, B=128) and of the fp32 attention conv
-for k in gcn_gemm_tc_kernel bone_fusion_tc_kernel bone_coef_tc_kernel ste_tc_kernel regress_mano_kernel joint_embed_kernel conv3x3_c64_halo_kernel; do
+for k in gcn_gemm_tc_kernel bone_fusion_tc_kernel bone_coef_tc_kernel ste_tc_kernel regress_mano_kernel joint_embed_kernel conv3x3_c64_halo_kernel conv1x1_b2b_kernel; do
   $NCU --set full --import-source on -k regex:$k -s 2 -c 2 -o gpurun_out/full_r2_$k -f python scripts/one_forward.py --precision bf16 --batch 128 --iters 2 > gpurun_out/ncu_full_$k.log 2>&1
 done
 # the attention conv (3x3 2048->2048 @8x8, the largest launch) and its neighbours on the fp32 configuration's 3xTF32 kernel
