@@ -319,7 +319,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {  // ===================== TMA producer
       int s = 0;
-      uint32_t ph = 0, rchunk = 0;
+      uint32_t ph = 0;
       if (bres && first_tile < total_tiles) {  // weights: finalize-time data, one load per CTA for all its tiles
         mbar_expect_tx(bres_bar, (uint32_t)nkb * Cfg::B_STAGE);
         for (int kb = 0; kb < nkb; ++kb) tma_load_2d(&tmB, bres_bar, sB + kb * Cfg::B_STAGE, kb * 64, 0);
@@ -331,14 +331,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int wo0 = m0 % a.Wo;
         const int ho0 = (m0 / a.Wo) % a.Ho;
         const int b0 = m0 / (a.Wo * a.Ho);
-        if (a.has_res) {  // residual chunks of this tile, into the residual ring (freed by the epilogue)
-          for (int c = 0; c < Cfg::NCH; ++c, ++rchunk) {
-            const uint32_t rb = rchunk % RES_BUFS;
-            mbar_wait(&res_empty[rb], ((rchunk / RES_BUFS) & 1) ^ 1);
-            mbar_expect_tx(&res_full[rb], CHUNK_BYTES);
-            tma_load_2d(&tmR, &res_full[rb], sRes + rb * CHUNK_BYTES, n0 + c * 64, m0);
-          }
-        }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           if constexpr (PRE) {  // A -> this CTA's afull barrier (transform warps); weights -> the MMA warp's full barrier
@@ -504,6 +496,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* sOutG = sOut + eg * CHUNK_BYTES;
     int i = 0;
     int cur_n0 = -1;
+    // Residual chunks arrive by TMA in a ring of RES_BUFS slots, slot = chunk index % RES_BUFS. The ring is clocked by its
+    // consumer: the elected thread of the group that has finished with a slot issues the load of the chunk that uses it
+    // next (RES_BUFS chunks ahead, same chunk parity = same group). Issuing them from the producer warp instead blocked
+    // it on the epilogue's progress before it could fetch the next tile's operands (BN = 256: one tile fills the ring).
+    auto load_res = [&](uint32_t j) {  // chunk j of this CTA's chunk stream
+      const int tile_j = first_tile + (int)(j / Cfg::NCH) * tile_step;
+      if (tile_j >= total_tiles) return;
+      const int c_j = (int)(j % Cfg::NCH);
+      const int m0_j = ((a.raster_m ? tile_j % m_units : tile_j / a.n_tiles) * CG + (int)rank) * BM;
+      const int n0_j = (a.raster_m ? tile_j / m_units : tile_j % a.n_tiles) * BN;
+      const uint32_t rb = j % RES_BUFS;
+      mbar_expect_tx(&res_full[rb], CHUNK_BYTES);
+      tma_load_2d(&tmR, &res_full[rb], sRes + rb * CHUNK_BYTES, n0_j + c_j * 64, m0_j);
+    };
+    if (a.has_res && et == 0) {  // this group's first RES_BUFS / 2 chunks
+      for (uint32_t j = (uint32_t)eg; j < RES_BUFS; j += 2) load_res(j);
+    }
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++i) {
       const int m0 = ((a.raster_m ? tile % m_units : tile / a.n_tiles) * CG + (int)rank) * BM;
       const int n0 = (a.raster_m ? tile / m_units : tile % a.n_tiles) * BN;
@@ -597,7 +606,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (et == 0) {
           tma_store_2d(&tmY, sOutG, n0 + c * 64, m0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          if (a.has_res) mbar_arrive(&res_empty[rchunk % RES_BUFS]);  // every thread is past its residual reads
+          if (a.has_res) load_res(rchunk + RES_BUFS);  // every thread of the group is past its reads of this slot
         }
       }
       // this thread has read everything it needs from accumulator buffer `buf` (256 arrivals hand it back to the MMA warp)

@@ -30,17 +30,19 @@ def build():
 
 
 on = build()
-os.environ[args.env] = "1"
+name, _, value = args.env.partition("=")  # NAME or NAME=VALUE
+os.environ[name] = value or "1"
 off = build()
-del os.environ[args.env]
+del os.environ[name]
+args.env = name + "=" + (value or "1")
 imgs = [torch.randn(args.batch, 3, 256, 256, generator=torch.Generator().manual_seed(i)).cuda() for i in range(4)]
-res = {"default": [], args.env + "=1": []}
+res = {"default": [], args.env: []}
 for m in (on, off):
     for i in range(5):
         m.run_raw(imgs[i % 4])
 torch.cuda.synchronize()
 for rnd in range(5):
-    for name, m in (("default", on), (args.env + "=1", off)):
+    for name, m in (("default", on), (args.env, off)):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(20):
