@@ -41,7 +41,7 @@ for m in (on, off):
     for i in range(5):
         m.run_raw(imgs[i % 4])
 torch.cuda.synchronize()
-for rnd in range(5):
+for rnd in range(int(os.environ.get("AB_ROUNDS", "5"))):
     for name, m in (("default", on), (args.env, off)):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
