@@ -14,11 +14,14 @@
 //   and the A box is taken from an OVERLAPPING-stride view of that buffer (consecutive wo are 2 px = 16 B apart),
 //   so the 7x7 window gather is again pure TMA.
 // Persistent schedule (grid = min(tiles, SMs)), roles per CTA (320 threads):
-//   warp 0   : TMA producer over a `stages`-deep smem ring (runs ahead across tiles; also feeds the residual ring)
+//   warp 0   : TMA producer over a `stages`-deep smem ring (runs ahead across tiles)
 //   warp 1   : TMEM alloc (2 accumulator buffers of BN fp32 columns) + single-thread tcgen05.mma issue
 //   warps 2-9: two epilogue groups of 4 warps taking alternate 64-column chunks; the epilogue of tile i overlaps the
 //              main loop of tile i+1: tcgen05.ld -> affine/residual/ReLU -> bf16 -> 128B-swizzled smem staging ->
-//              TMA store (coalesced, asynchronous); residual tiles arrive by TMA.
+//              TMA store (coalesced, asynchronous); residual tiles arrive by TMA through a ring that the epilogue group
+//              clocks itself (whoever frees a slot issues the load of the chunk that uses it next).
+//   warps 10-15 (PRE kernels only): apply the consuming Residual's bn1 + ReLU to every A tile in place, between its
+//              TMA arrival and the MMA (one warp per smem stage).
 // Variants selected per layer at launch:
 //   CG = 2       : clusters of two CTAs share every MMA (tcgen05.mma.cta_group::2, M = 256); each CTA loads its own A
 //                  tile and half of the weight tile (every layer with BN >= 128 and an even number of M tiles)
@@ -26,6 +29,8 @@
 //   kb2 / kb2a   : K-concatenated second (and third) 1x1 operand: conv3 + downsample/skip as one GEMM, the skip operand
 //                  optionally read from the two sources of a channel concat that is never materialised
 //   stem         : legacy TMA stem (DIRB200_STEM_SPLIT=1); the default stem is stem_pool.cu
+//   PRE = 1      : 1x1 conv over relu(x * s[c] + h[c]) with x optionally the channel concat of two tensors (hourglass
+//                  Residual conv1: neither the pre-activated tensor nor the concat exists in HBM)
 #include <cuda.h>
 
 #include <cstdio>
@@ -45,7 +50,7 @@ constexpr int NUM_THREADS = 320;  // producer warp + MMA warp + 2 epilogue group
 constexpr int MAX_STAGES = 8;
 constexpr int CHUNK_BYTES = BM * 128;  // one 64-column bf16 epilogue box: 16 KB
 constexpr int PRE_WARPS = 6;           // transform warps of the PRE kernels (16 warps = 4 per scheduler: same 128-register cap as 14)
-constexpr int RES_BUFS = 4;            // residual ring: the producer prefetches residual chunks ~2 tiles ahead
+constexpr int RES_BUFS = 4;            // residual ring: chunks are fetched RES_BUFS chunks (1-2 tiles) ahead of their use
 
 struct TcArgs {
   const float* scale;
