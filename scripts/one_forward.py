@@ -17,9 +17,11 @@ ap.add_argument("--precision", default="bf16")
 ap.add_argument("--batch", type=int, default=128)
 ap.add_argument("--iters", type=int, default=4)
 ap.add_argument("--no-aux", action="store_true")
+ap.add_argument("--backbone", default="resnet50")
 a = ap.parse_args()
-net = dir_b200.DIR(21, "./misc/mano", precision=a.precision, aux_outputs=not a.no_aux, max_batch=a.batch).cuda()
-net.load_state_dict(make_state_dict(0), strict=False)
+net = dir_b200.DIR(21, "./misc/mano", precision=a.precision, aux_outputs=not a.no_aux, max_batch=a.batch,
+                   backbone=a.backbone).cuda()
+net.load_state_dict(make_state_dict(0, backbone=a.backbone) if a.backbone != "resnet50" else make_state_dict(0), strict=False)
 img = torch.randn(a.batch, 3, 256, 256, generator=torch.Generator().manual_seed(0)).cuda()
 for _ in range(a.iters):
     net.run_raw(img)
