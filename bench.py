@@ -49,8 +49,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip eager-GPU baseline, parity, no-aux and fp32-config legs")
     ap.add_argument("--cuda-graph", action="store_true")
-    ap.add_argument("--backbone", default="resnet50", choices=["resnet50", "hrnet_w32"],
-                    help="resnet50 = the reference's network; hrnet_w32 = extension, parity unpinned (BASELINE configs 3-5)")
+    ap.add_argument("--backbone", default="resnet50", choices=["resnet50", "hrnet_w32", "hrnet_w48"],
+                    help="resnet50 = the reference's network; hrnet_w32 / hrnet_w48 = extension, parity unpinned (BASELINE configs 3-5)")
     return ap.parse_args()
 
 
@@ -495,7 +495,7 @@ def main():
         "dtype": {"bf16": "bf16", "fp32": "f32", "tf32": "tf32"}[args.precision], "data": "synthetic",
         "config": {"workload": f"DIR eval forward (ResNet-50 backbone, init regression, 2 refinement stages, "
                                f"seg/dense/proj_feat heads), 256x256, B={B} per GPU, random-init weights + synthetic MANO"
-                               + ("" if args.backbone == "resnet50" else " [--backbone hrnet_w32: extension, ResNet-50 replaced]"),
+                               + ("" if args.backbone == "resnet50" else f" [--backbone {args.backbone}: extension, ResNet-50 replaced]"),
                    "global_batch": B * world, "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": f"{NBUF} rotating resident input batches (4x100 MB > 126 MB L2); activations ~GBs per step",
                    "collective": "ncclAllGather of (B,14661) fp32 records per step" if world > 1 else None,

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DIRB200_LIB") or os.path.join(_HERE, "libdirb200.so")  # override: A/B of builds
 
 PRECISION = {"fp32": 0, "bf16": 1, "tf32": 2}
-BACKBONE = {"resnet50": 0, "hrnet_w32": 32}
+BACKBONE = {"resnet50": 0, "hrnet_w32": 32, "hrnet_w48": 48}
 DTYPE_F32, DTYPE_I64 = 0, 1
 STAGE_FLOATS = 4887
 RECORD_FLOATS = 3 * STAGE_FLOATS

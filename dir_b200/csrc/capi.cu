@@ -40,8 +40,8 @@ extern "C" int dirb200_create(const dirb200_config* cfg, dirb200_handle** out) {
     g_create_err = "refine_stages must be 0 (= 2), 1 or 2: the reference defines two refinement stages (models/dir.py:437-471)";
     return DIRB200_E_INVALID;
   }
-  if (cfg->backbone != 0 && cfg->backbone != 32) {
-    g_create_err = "backbone must be 0 (ResNet-50, the reference) or 32 (HRNet-W32 extension)";
+  if (cfg->backbone != 0 && cfg->backbone != 32 && cfg->backbone != 48) {
+    g_create_err = "backbone must be 0 (ResNet-50, the reference) or 32 / 48 (HRNet-W32 / -W48 extension)";
     return DIRB200_E_INVALID;
   }
   if (cfg->refine_stages == 1 && cfg->aux_outputs) {

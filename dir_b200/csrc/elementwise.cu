@@ -625,7 +625,7 @@ void launch_attn_logits(const T* a, const float* w, const float* bias, float* at
 template <typename T>
 void launch_attn_pool(const T* f, const float* attn, float* pooled, int B, int P, int C, cudaStream_t st) {
   // C is a multiple of 256 and P of 4 for every caller (2048 channels, 8x8 map; models/dir.py:263-268; 256 for HRNet-W32)
-  const int chunk = C % 512 == 0 ? 512 : 256;
+  const int chunk = C % 512 == 0 ? 512 : (C % 256 == 0 ? 256 : (C <= 512 ? C : 128));  // 384 (HRNet-W48): one block per image
   launch_pdl(attn_pool_kernel<T>, dim3(B, C / chunk), dim3(256), (P * 2 + 4 * 3 * 512) * sizeof(float), st, f, attn, pooled,
              P, C, chunk);
 }

@@ -227,21 +227,25 @@ PointMlp Engine::make_mlp(const std::string& p, int cin, int cmid, int cout) {
   return m;
 }
 
-ResidualBlock Engine::make_residual(const std::string& p) {
+// cin_pad > 0: the block's input tensor carries zero-padded channels beyond the tensor's own (HRNet-W48: the 96-channel
+// c2 lives in 128); conv1 / skip weights and the pre-activation affine are padded with zeros to match
+ResidualBlock Engine::make_residual(const std::string& p, int cin_pad) {
   ResidualBlock r;
-  r.c1 = make_conv(p + "conv1.conv.weight", p + "conv1.conv.bias", p + "bn2.", 1, 0, 1);
+  r.c1 = make_conv(p + "conv1.conv.weight", p + "conv1.conv.bias", p + "bn2.", 1, 0, 1, cin_pad);
   r.c2 = make_conv(p + "conv2.conv.weight", p + "conv2.conv.bias", p + "bn3.", 1, 1, 1);
   r.c3 = make_conv(p + "conv3.conv.weight", p + "conv3.conv.bias", "", 1, 0, 0);
   if (!dry && bf16() && r.c3.w16) {
     r.c3.tc_bn_cap = 128;
     conv_tc_prepare_weights(r.c3);
   }
-  r.skip = make_conv(p + "skip_layer.conv.weight", p + "skip_layer.conv.bias", "", 1, 0, 0);
+  r.skip = make_conv(p + "skip_layer.conv.weight", p + "skip_layer.conv.bias", "", 1, 0, 0, cin_pad);
   r.cin = r.c1.Cin;
   r.cout = r.c3.Cout;
   r.need_skip = r.cin != r.cout;  // hourglass.py:49-52
   if (r.need_skip) make_dual(r.c3skip, r.c3, r.skip);
-  fold("", p + "bn1.", &r.bn1s, &r.bn1b, r.cin);  // pre-activation BN, applied by concat_preact
+  int cin_src = r.cin;  // pre-activation BN: padded channels keep scale = shift = 0 (relu(0) = 0)
+  if (!dry && raw.count(p + "bn1.weight") && !raw[p + "bn1.weight"].shape.empty()) cin_src = (int)raw[p + "bn1.weight"].shape[0];
+  fold("", p + "bn1.", &r.bn1s, &r.bn1b, cin_src, 0, r.cin);  // applied by conv1 (PRE kernels) or concat_preact
   return r;
 }
 
@@ -467,7 +471,8 @@ int Engine::build(cudaStream_t st) {
   for (const char* n : {"skip_layer4", "fusion_layer4", "enhance_layer4", "skip_layer3", "fusion_layer3",
                         "enhance_layer3"}) {
     std::string p = std::string("decoder.") + n + ".";
-    res[p] = make_residual(p);
+    // the only decoder input with padded channels: c2 of HRNet-W48 (96 -> 128), consumed by skip_layer3
+    res[p] = make_residual(p, (hrnet() && std::string(n) == "skip_layer3" && c2ch % 64 == 0) ? c2ch : 0);
   }
   build_stage(0, "decoder.projecter_4.");
   build_stage(1, "decoder.projecter_3.");
@@ -581,7 +586,9 @@ void Engine::build_hrnet(int width) {
   c2ch = pad64(C[1]);
   c3ch = pad64(C[2]);
   c4ch = pad64(C[3]);
-  if (!dry && err.empty() && (c2ch != C[1] || c3ch != C[2] || c4ch != C[3])) err = "HRNet width must make c2..c4 multiples of 64";
+  // c2 may be padded (W48: 96 -> 128; skip_layer3 is built with matching zero weights); c3 feeds skip_layer4 AND sits
+  // in the middle of fusion_layer4's concat, c4 is InitRegressor's feat_dim: those two must be exact
+  if (!dry && err.empty() && (c3ch != C[2] || c4ch != C[3])) err = "HRNet width must make c3 and c4 multiples of 64";
 }
 
 template <typename T>

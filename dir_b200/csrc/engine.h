@@ -198,7 +198,7 @@ struct Engine {
   void fuse_post_bn(ConvLayer& c, const std::string& conv_bias, const std::string& bn);
   void prepare_tf32(ConvLayer& L);
   PointMlp make_mlp(const std::string& prefix, int cin, int cmid, int cout);
-  ResidualBlock make_residual(const std::string& prefix);
+  ResidualBlock make_residual(const std::string& prefix, int cin_pad = 0);
   ManoWeights make_mano(const std::string& prefix, bool left);
   void build_stage(int s, const std::string& p);
 

@@ -22,7 +22,7 @@ from . import assets, capi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _KEYS_JSON = os.path.join(_HERE, "state_dict_keys.json")
-_KEYS_JSON_HRNET = os.path.join(_HERE, "state_dict_keys_hrnet_w32.json")
+_KEYS_JSON_HRNET = {w: os.path.join(_HERE, f"state_dict_keys_hrnet_w{w}.json") for w in (32, 48)}
 
 STAGE_KEYS = [  # (key in outs_list[i], offset name, trailing shape) — models/dir.py:521-535
     ("pd_joint_uv_left", "uv_l", (21, 2)), ("pd_joint_uv_right", "uv_r", (21, 2)),
@@ -66,8 +66,8 @@ def _default_init(name, shape):
 
 
 def reference_key_shapes(backbone="resnet50"):
-    """Key/shape inventory: the reference's 963 keys, or (backbone='hrnet_w32') the HRNet extension's."""
-    with open(_KEYS_JSON if backbone == "resnet50" else _KEYS_JSON_HRNET) as f:
+    """Key/shape inventory: the reference's 963 keys, or (backbone='hrnet_w32' | 'hrnet_w48') the HRNet extension's."""
+    with open(_KEYS_JSON if backbone == "resnet50" else _KEYS_JSON_HRNET[int(backbone.split("_w")[1])]) as f:
         return json.load(f)
 
 
@@ -97,7 +97,7 @@ class DIR(nn.Module):
         self.refine_stages = int(refine_stages)
         if backbone not in capi.BACKBONE:
             raise ValueError(f"backbone must be one of {sorted(capi.BACKBONE)} (the reference has ResNet-50 only; "
-                             "'hrnet_w32' is an extension with a self-authored oracle)")
+                             "'hrnet_w32' / 'hrnet_w48' are extensions with a self-authored oracle)")
         self.backbone_name = backbone
         if self.refine_stages not in (1, 2):
             raise ValueError("the reference defines two refinement stages (models/dir.py:437-471): refine_stages is 1 or 2")

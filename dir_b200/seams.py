@@ -67,8 +67,10 @@ def backbone(model, img):
     B, _, H, W = img.shape
     h, ws = _prep(model, B)
     dev = img.device
-    # packed channel counts: ResNet-50, or HRNet-W32 (whose 32-channel branch is stored in 64, the upper half zero)
-    ch = (64, 64, 128, 256) if getattr(model, "backbone_name", "resnet50") == "hrnet_w32" else (256, 512, 1024, 2048)
+    # packed channel counts: ResNet-50, or HRNet-W32 / -W48 (branch widths that are not multiples of 64 are stored zero-
+    # padded: W32's 32-channel branch in 64, W48's 48 in 64 and 96 in 128)
+    ch = {"hrnet_w32": (64, 64, 128, 256), "hrnet_w48": (64, 128, 192, 384)}.get(
+        getattr(model, "backbone_name", "resnet50"), (256, 512, 1024, 2048))
     c1 = torch.empty(B, ch[0], H // 4, W // 4, device=dev)
     c2 = torch.empty(B, ch[1], H // 8, W // 8, device=dev)
     c3 = torch.empty(B, ch[2], H // 16, W // 16, device=dev)

@@ -66,10 +66,10 @@ typedef struct dirb200_config {
                         1: stop after projecter_4 (init regression + one refinement, BASELINE.json configs[0] "1 refine
                         iter"; needs aux_outputs = 0, the stage-2 slice of the record is zero-filled). The reference has
                         no further stages, so larger values are rejected. */
-  int backbone;    /* 0: ResNet-50, the reference's only backbone (models/dir.py:492). 32: HRNet-W32 — an EXTENSION with no
-                      counterpart in the reference (BASELINE.json configs 3-5): the published HRNet backbone
-                      with the reference's decoder knobs inDim=[256,128,64,32], InitRegressor(feat_dim=256)
-                      (models/dir.py:390,501). Parity unpinned: tested against the self-authored oracle/hrnet_oracle.py. */
+  int backbone;    /* 0: ResNet-50, the reference's only backbone (models/dir.py:492). 32 / 48: HRNet-W32 / -W48 — an
+                      EXTENSION with no counterpart in the reference (BASELINE.json configs 3-5): the
+                      published HRNet backbone with the reference's decoder knobs inDim=[8w,4w,2w,w],
+                      InitRegressor(feat_dim=8w) (models/dir.py:390,501). Parity unpinned: tested against the self-authored oracle/hrnet_oracle.py. */
 } dirb200_config;
 
 /* Caller-owned output buffers of one forward (device pointers). */
@@ -127,8 +127,9 @@ int dirb200_profile_dump(dirb200_handle* h, char* buf, size_t buf_bytes);
 /* Per-seam entry points; used by the parity tests. All tensors fp32 device memory,
  * feature maps NCHW exactly as the reference module sees them; conversion to the internal NHWC /
  * bf16 layout happens inside, in `workspace`. */
-/* ResNet.forward (models/backbone/resnet.py:243-255): img (B,3,H,W) -> c1..c4 NCHW fp32. HRNet handles (backbone = 32):
- * 256x256 only; c1..c4 = (B,64,64,64) [32 channels + 32 zero-padded], (B,64,32,32), (B,128,16,16), (B,256,8,8). */
+/* ResNet.forward (models/backbone/resnet.py:243-255): img (B,3,H,W) -> c1..c4 NCHW fp32. HRNet handles:
+ * 256x256 only; backbone = 32: c1..c4 = (B,64,64,64) [32 channels + 32 zero-padded], (B,64,32,32), (B,128,16,16),
+ * (B,256,8,8); backbone = 48: (B,64,64,64) [48 + 16 zeros], (B,128,32,32) [96 + 32 zeros], (B,192,16,16), (B,384,8,8). */
 int dirb200_backbone(dirb200_handle* h, const float* img, int batch, int height, int width, float* c1, float* c2,
                      float* c3, float* c4, void* workspace, size_t workspace_bytes, void* stream);
 /* Residual.forward (models/backbone/hourglass.py:55-70); name = "decoder.enhance_layer4." etc. */

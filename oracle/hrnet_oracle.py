@@ -168,14 +168,15 @@ def dir_forward(sd, img, width=32):
         return outs
 
 
-if __name__ == "__main__":  # python -m oracle.hrnet_oracle  -> regenerates dir_b200/state_dict_keys_hrnet_w32.json
+if __name__ == "__main__":  # python -m oracle.hrnet_oracle  -> regenerates dir_b200/state_dict_keys_hrnet_w{32,48}.json
     import json
     import os
 
     from .synth import load_key_shapes
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    path = os.path.join(root, "dir_b200", "state_dict_keys_hrnet_w32.json")
-    with open(path, "w") as f:
-        json.dump(dir_key_shapes(32, load_key_shapes()), f, indent=0)
-    print("wrote", path)
+    for width in (32, 48):
+        path = os.path.join(root, "dir_b200", f"state_dict_keys_hrnet_w{width}.json")
+        with open(path, "w") as f:
+            json.dump(dir_key_shapes(width, load_key_shapes()), f, indent=0)
+        print("wrote", path)

@@ -111,3 +111,66 @@ def test_hrnet_u8_frames_and_batch_independence(m16):
     big = m16.run_raw(frames)["record"]
     small = m16.run_raw(frames[[1, 4]])["record"]
     assert torch.equal(small, big[[1, 4]]) and bool(torch.isfinite(big).all())
+
+
+# ---------------------------------------------------------------------------------------------- HRNet-W48 (configs[4])
+@pytest.fixture(scope="module")
+def sd48():
+    from oracle.synth import make_state_dict
+
+    return make_state_dict(0, backbone="hrnet_w48")
+
+
+def _make48(sd48, precision):
+    import dir_b200
+
+    m = dir_b200.DIR(21, "./misc/mano", precision=precision, backbone="hrnet_w48", max_batch=8).cuda()
+    m.load_state_dict(sd48, strict=False)
+    m.eval()
+    return m
+
+
+def test_hrnet_w48_fp32_backbone_and_forward_vs_oracle(sd48):
+    """Widths 48 / 96 / 192 / 384: the 48- and 96-channel branches are stored zero-padded in 64 and 128 channels (padding
+    exactly zero everywhere), the decoder's skip_layer3 consumes the padded c2 with zero-padded weights and pre-activation,
+    InitRegressor runs with feat_dim 384. Against the width-generic self-authored oracle (parity unpinned)."""
+    from dir_b200 import seams
+    from oracle import dir_oracle as O
+    from oracle import hrnet_oracle as H
+
+    m = _make48(sd48, "fp32")
+    img = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(11))
+    want = H.hrnet(sd48, img, 48)
+    got = seams.backbone(m, img.cuda())
+    assert [tuple(t.shape[1:]) for t in got] == [(64, 64, 64), (128, 32, 32), (192, 16, 16), (384, 8, 8)]
+    assert float(got[0][:, 48:].abs().max()) == 0.0 and float(got[1][:, 96:].abs().max()) == 0.0
+    for i, n in enumerate((48, 96, 192, 384)):
+        assert rel(got[i][:, :n], want[i]) < 1e-4, i
+    wf = H.dir_forward(sd48, img, 48)
+    outs, _ = m({"img": img}, None, None)
+    worst = max(rel(outs[i][k], wf[i][k]) for i in range(3) for k in O.OUT_KEYS)
+    print(f"hrnet_w48 fp32 whole forward: worst relative error vs the self-authored oracle {worst:.2e}")
+    assert worst < 1e-4
+    assert rel(outs[3]["seg"], wf[3]["seg"]) < 1e-4 and rel(outs[3]["dense"], wf[3]["dense"]) < 1e-4
+
+
+def test_hrnet_w48_bf16_vs_oracle_and_autocast(sd48):
+    from oracle import hrnet_oracle as H
+
+    m = _make48(sd48, "bf16")
+    img = torch.randn(4, 3, 256, 256, generator=torch.Generator().manual_seed(12))
+    want = H.dir_forward(sd48, img, 48)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        auto = H.dir_forward(sd48, img, 48)
+    outs, _ = m({"img": img}, None, None)
+
+    def drift(o, i):
+        d = torch.cat([(o[i][k].float().cpu() - want[i][k]).norm(dim=-1).flatten()
+                       for k in ("pd_mesh_xyz_left", "pd_mesh_xyz_right")]) * 1000
+        return float(d.mean())
+
+    for i in range(3):
+        ours, ref = drift(outs, i), drift(auto, i)
+        print(f"hrnet_w48 bf16 stage {i}: mean per-vertex drift {ours:.3f} mm (same oracle under bf16 autocast: {ref:.3f} mm)")
+        assert ours <= 1.25 * ref + 0.05, (i, ours, ref)
+    assert bool(torch.isfinite(outs[2]["pd_mesh_xyz_left"]).all())

@@ -192,5 +192,9 @@ def test_hrnet_key_inventory_is_the_generators():
     m = dir_b200.DIR(21, "./misc/mano", backbone="hrnet_w32")
     assert set(m.state_dict()) == set(shipped)
     assert tuple(m.state_dict()["init_regressor.mano_left.weight"].shape) == (64, 256)
+    assert reference_key_shapes("hrnet_w48") == hrnet_key_shapes(48)
+    m48 = dir_b200.DIR(21, "./misc/mano", backbone="hrnet_w48")
+    assert tuple(m48.state_dict()["init_regressor.mano_left.weight"].shape) == (64, 384)
+    assert tuple(m48.state_dict()["decoder.skip_layer3.conv1.conv.weight"].shape) == (128, 96, 1, 1)
     with pytest.raises(ValueError):
-        dir_b200.DIR(21, "./misc/mano", backbone="hrnet_w48")
+        dir_b200.DIR(21, "./misc/mano", backbone="hrnet_w64")
