@@ -396,7 +396,7 @@ def main():
         h2d_gbs = 8 * B * 3 * 256 * 256 * 4 / (float(t.item()) / 1000.0) / 1e9
 
     extras = world == 1 and not args.no_extras
-    no_aux = parity = parity32 = fp32_cfg = eager = hrnet_cfg = None
+    no_aux = parity = parity32 = fp32_cfg = eager = hrnet_cfg = hrnet48_cfg = None
     if extras and args.backbone != "resnet50":
         extras = False  # the extra legs (oracle parity, eager baseline) are defined for the reference's network
     if extras:
@@ -418,14 +418,19 @@ def main():
         eager = gpu_eager_baseline(dev, B if B <= 128 else 128)
         # BASELINE.json configs[2] names HRNet-W32 as the headline network; the reference has none. The
         # extension (self-authored oracle, parity UNPINNED) is timed here so that the config has a number, labelled as such
-        net_h = make_net(args.precision, True, B, "hrnet_w32")
-        ms_h = timed(step_of(net_h), max(5, K // 2), W)
-        hh = net_h._handle
-        hrnet_cfg = {"value": B * max(5, K // 2) / (ms_h / 1000.0), "unit": "images/s", "batch": B,
-                     "ms_per_step": ms_h / max(5, K // 2), "gpu_launches_per_step": hh.lib.dirb200_forward_launches(hh.h, B),
-                     "what": f"backbone='hrnet_w32', precision='{args.precision}': EXTENSION, not in the reference; parity "
-                             "unpinned (tests/test_gpu_hrnet.py checks it against the self-authored oracle/hrnet_oracle.py)"}
-        del net_h
+        hrnet_legs = {}
+        for bb in ("hrnet_w32", "hrnet_w48"):
+            net_h = make_net(args.precision, True, B, bb)
+            ms_h = timed(step_of(net_h), max(5, K // 2), W)
+            hh = net_h._handle
+            hrnet_legs[bb] = {"value": B * max(5, K // 2) / (ms_h / 1000.0), "unit": "images/s", "batch": B,
+                              "ms_per_step": ms_h / max(5, K // 2),
+                              "gpu_launches_per_step": hh.lib.dirb200_forward_launches(hh.h, B),
+                              "what": f"backbone='{bb}', precision='{args.precision}': EXTENSION, not in the reference; parity "
+                                      "unpinned (tests/test_gpu_hrnet.py checks it against the self-authored "
+                                      "oracle/hrnet_oracle.py)"}
+            del net_h
+        hrnet_cfg, hrnet48_cfg = hrnet_legs["hrnet_w32"], hrnet_legs["hrnet_w48"]
 
     if rank != 0:
         if world > 1:
@@ -505,7 +510,7 @@ def main():
         "gpu_launches": launches_per_step * K,
         "roofline": roof, "roofline_top": roof_top, "roofline_step": step_roof,
         "cpu_baseline": cpu, "gpu_eager_baseline": eager, "parity": parity, "no_aux": no_aux,
-        "fp32_config": fp32_cfg, "parity_fp32": parity32, "hrnet_w32_extension": hrnet_cfg,
+        "fp32_config": fp32_cfg, "parity_fp32": parity32, "hrnet_w32_extension": hrnet_cfg, "hrnet_w48_extension": hrnet48_cfg,
     }
     print(json.dumps(line))
     if world > 1:
