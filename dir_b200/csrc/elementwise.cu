@@ -559,31 +559,30 @@ struct FuseArgs {
 template <typename T>
 __global__ void __launch_bounds__(256) fuse_sum_relu_kernel(FuseArgs a) {
   pdl_wait();
-  const int c4n = a.C >> 2;
-  const int64_t total = (int64_t)a.B * a.H * a.W * c4n;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // one 8-channel vector (16 bytes of bf16) per thread, 32-bit index arithmetic: the first version (4 channels, 64-bit
+  // div/mod per thread) ran the 64x64 fuse of HRNet's first branch at 1.4 TB/s
+  const unsigned c8n = (unsigned)a.C >> 3;
+  const unsigned total = (unsigned)a.B * a.H * a.W * c8n;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int c = (int)(idx % c4n) * 4;
-  int64_t t = idx / c4n;
-  const int w = (int)(t % a.W);
-  t /= a.W;
-  const int h = (int)(t % a.H), b = (int)(t / a.H);
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = 0; k < a.nterm; ++k) {
+  const unsigned c = (idx % c8n) * 8, pix = idx / c8n;
+  const unsigned w = pix % (unsigned)a.W, t = pix / (unsigned)a.W;
+  const unsigned h = t % (unsigned)a.H, b = t / (unsigned)a.H;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  for (int k = 0; k < a.nterm; ++k) {  // same term order as before: the sums are bit-identical
     const int sh = a.shift[k];
-    const int Hk = a.H >> sh, Wk = a.W >> sh;
-    const T* p = reinterpret_cast<const T*>(a.term[k]) + (((int64_t)b * Hk + (h >> sh)) * Wk + (w >> sh)) * a.C + c;
-    const float4 v = ActIO<T>::ld4(p);
-    s.x += v.x;
-    s.y += v.y;
-    s.z += v.z;
-    s.w += v.w;
+    const unsigned Hk = (unsigned)a.H >> sh, Wk = (unsigned)a.W >> sh;
+    const T* p = reinterpret_cast<const T*>(a.term[k]) + ((size_t)(b * Hk + (h >> sh)) * Wk + (w >> sh)) * a.C + c;
+    float v[8];
+    Vec8<T>::ld(p, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += v[i];
   }
-  s.x = fmaxf(s.x, 0.f);
-  s.y = fmaxf(s.y, 0.f);
-  s.z = fmaxf(s.z, 0.f);
-  s.w = fmaxf(s.w, 0.f);
-  ActIO<T>::st4(reinterpret_cast<T*>(a.out) + idx * 4, s);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = fmaxf(s[i], 0.f);
+  Vec8<T>::st(reinterpret_cast<T*>(a.out) + (size_t)idx * 8, s);
 }
 
 template <typename T>
@@ -597,7 +596,7 @@ void launch_fuse_sum_relu(const T* const* terms, const int* shifts, int nterm, T
   a.nterm = nterm;
   a.out = out;
   a.B = B; a.H = H; a.W = W; a.C = C;
-  const int64_t total = (int64_t)B * H * W * (C / 4);
+  const int64_t total = (int64_t)B * H * W * (C / 8);
   launch_pdl(fuse_sum_relu_kernel<T>, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, st, a);
 }
 template void launch_fuse_sum_relu<float>(const float* const*, const int*, int, float*, int, int, int, int, cudaStream_t);
