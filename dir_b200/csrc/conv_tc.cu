@@ -378,7 +378,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           if (a.stem) {  // k-block = kernel row ky; overlapped view: {32 elems, wo (16 B apart), h, n}
-            tma_load_4d(&tmA, &full_bar[s], sA + s * Cfg::A_STAGE, 0, wo0, ho0 * 2 + kb - 3, b0);
+            tma_load_4d(&tmA, &full_bar[s], sA + s * Cfg::A_STAGE, 0, wo0, ho0 * 2 + kb - a.pad, b0);
             tma_load_2d(&tmB, &full_bar[s], sB + s * Cfg::B_STAGE, kb * 32, n0);
           } else if (kb >= nkb1) {  // second operand of a K-concatenated pair (1x1, own stride): skip / downsample conv
             const int k2 = kb - nkb1;
@@ -686,13 +686,14 @@ __global__ void stem_pack_u8_kernel(const unsigned char* __restrict__ img, __nv_
   *reinterpret_cast<uint2*>(out + idx * 4) = u;
 }
 
-// stem weights [64][3][7][7] fp32 -> [64][7*32] bf16 with k = ky*32 + kx*4 + c (zero elsewhere)
-__global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+// stem weights [64][3][ks][ks] fp32 -> [64][ks*32] bf16 with k = ky*32 + kx*4 + c (zero elsewhere); ks = 7 or 3
+__global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int ks) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 64 * 224) return;
-  int k = idx % 224, n = idx / 224;
+  const int kk = ks * 32;
+  if (idx >= 64 * kk) return;
+  int k = idx % kk, n = idx / kk;
   int ky = k / 32, r = k % 32, kx = r / 4, c = r % 4;
-  float v = (kx < 7 && c < 3) ? w[((n * 3 + c) * 7 + ky) * 7 + kx] : 0.f;
+  float v = (kx < ks && c < 3) ? w[((n * 3 + c) * ks + ky) * ks + kx] : 0.f;
   out[idx] = __float2bfloat16_rn(v);
 }
 
@@ -939,10 +940,13 @@ int conv_tc_prepare_dual(ConvLayer& F, const ConvLayer& main, const ConvLayer& s
 int conv_tc_prepare_stem(ConvLayer& L, const float* w_raw, __nv_bfloat16* w_packed, cudaStream_t st) {
   L.tc_stem = false;
   EncodeTiledFn enc = get_encode();
-  if (!enc || L.Cin != 3 || L.Cout != 64 || L.kh != 7 || L.kw != 7 || L.stride != 2 || L.pad != 3) return 0;
-  stem_pack_weight_kernel<<<(64 * 224 + 255) / 256, 256, 0, st>>>(w_raw, w_packed);
-  cuuint64_t dims[2] = {224, 64};
-  cuuint64_t strides[1] = {224 * 2};
+  // 7x7 / pad 3 (ResNet, resnet.py:176) or 3x3 / pad 1 (HRNet's first stem conv): one k-block per kernel row
+  const bool k7 = L.kh == 7 && L.kw == 7 && L.pad == 3, k3 = L.kh == 3 && L.kw == 3 && L.pad == 1;
+  if (!enc || L.Cin != 3 || L.Cout != 64 || !(k7 || k3) || L.stride != 2) return 0;
+  const int kk = L.kh * 32;
+  stem_pack_weight_kernel<<<(64 * kk + 255) / 256, 256, 0, st>>>(w_raw, w_packed, L.kh);
+  cuuint64_t dims[2] = {(cuuint64_t)kk, 64};
+  cuuint64_t strides[1] = {(cuuint64_t)kk * 2};
   cuuint32_t box[2] = {32, 64};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(&L.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, dims, strides, box, es,
@@ -971,17 +975,18 @@ int launch_conv_tc_stem(const ConvLayer& L, const float* img, const unsigned cha
                         __nv_bfloat16* y, int B, int H, int W, cudaStream_t st) {
   const int Wp = W + 8, Ho = H / 2, Wo = W / 2;
   launch_stem_pack(img, img_u8, scratch, B, H, W, st);
-  typedef std::tuple<const void*, int, int, int> Key;
+  typedef std::tuple<const void*, int, int, int, int> Key;
   static thread_local MapCache<Key> cache;
-  Key key(scratch, B, H, W);
+  Key key(scratch, B, H, W, L.pad);
   CUtensorMap tm;
   if (!cache.find(key, &tm)) {
-    // overlapping view of the padded NHWC4 buffer: window wo starts at padded pixel 2*wo (= pixel 2*wo-3)
+    // overlapping view of the padded NHWC4 buffer (pixel w at index w + 3): the 8-pixel window of output column wo starts
+    // at pixel 2*wo - pad, i.e. the view's base is (3 - pad) pixels into the buffer (0 for the 7x7, 16 bytes for the 3x3)
     cuuint64_t dims[4] = {32, (cuuint64_t)Wo, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {16, (cuuint64_t)Wp * 8, (cuuint64_t)H * Wp * 8};
     cuuint32_t box[4] = {32, (cuuint32_t)BM, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, scratch, dims, strides, box, es,
+    CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, scratch + (3 - L.pad) * 4, dims, strides, box, es,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1001,9 +1006,9 @@ int launch_conv_tc_stem(const ConvLayer& L, const float* img, const unsigned cha
   a.Ho = Ho;
   a.Wo = Wo;
   a.stride = 2;
-  a.pad = 3;
-  a.kw = 7;
-  a.taps = 7;
+  a.pad = L.pad;
+  a.kw = L.kw;
+  a.taps = L.kh;  // k-blocks = kernel rows
   a.cblocks = 1;
   a.relu = L.relu;
   a.has_res = 0;

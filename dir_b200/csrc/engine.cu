@@ -512,6 +512,10 @@ void Engine::build_hrnet(int width) {
     const int padn = (k - 1) / 2;
     const int H = in < 0 ? 256 : hr_bufs[in].H, W_ = in < 0 ? 256 : hr_bufs[in].W;
     ConvLayer L = make_conv(p + w + ".weight", "", p + bn + ".", stride, padn, relu, in < 0 ? 0 : hr_bufs[in].C, pad64(cout));
+    if (!dry && bf16() && in < 0 && err.empty() && L.w32) {  // 3 -> 64, 3x3 / s2 on the image: the TMA stem variant of conv_tc.cu
+      __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(dalloc(64 * 3 * 32 / 2));
+      if (wp) conv_tc_prepare_stem(L, W(p + w + ".weight"), wp, fin_stream);
+    }
     if (!dry && bf16() && L.w16 && res >= 0) {
       L.tc_bn_cap = 128;  // residual-adding layer (see the ResNet bottlenecks)
       conv_tc_prepare_weights(L);
@@ -597,9 +601,14 @@ int Engine::run_backbone_hrnet(const float* img, int B, Arena& ar, T** c1, T** c
   for (size_t i = 0; i < hr_bufs.size(); ++i)
     ptr[i] = reinterpret_cast<T*>(ar.alloc((size_t)B * hr_bufs[i].H * hr_bufs[i].W * hr_bufs[i].C * sizeof(T)));
   float* u8_scratch = reinterpret_cast<float*>(ar.alloc((size_t)B * 3 * 256 * 256 * sizeof(float)));
+  // first stem conv on the tensor cores (bf16): image -> padded NHWC4 operand (uint8 preprocessing fused in) -> TMA stem
+  const bool tc_stem = sizeof(T) == 2 && !disable_tc && !hr_ops.empty() && hr_ops[0].kind == 0 && hr_ops[0].in < 0 &&
+                       hr_convs[hr_ops[0].layer].tc_stem && conv_tc_supported(hr_convs[hr_ops[0].layer], B, 256, 256);
+  __nv_bfloat16* stem_scratch =
+      tc_stem ? reinterpret_cast<__nv_bfloat16*>(ar.alloc(conv_tc_stem_scratch_bytes(B, 256, 256))) : nullptr;
   if (!ar.base) return DIRB200_OK;
   if (ar.overflow) return DIRB200_E_WORKSPACE;
-  if (img_u8) {  // input pipeline (apps/eval.py:56-61) as its own pass
+  if (img_u8 && !tc_stem) {  // input pipeline (apps/eval.py:56-61) as its own pass
     launch_preprocess_u8(img_u8, u8_scratch, B, 256, 256, st);
     ++launches;
     img = u8_scratch;
@@ -607,7 +616,16 @@ int Engine::run_backbone_hrnet(const float* img, int B, Arena& ar, T** c1, T** c
   for (const HrOp& op : hr_ops) {
     if (op.kind == 0) {
       const ConvLayer& L = hr_convs[op.layer];
-      if (op.in < 0)
+      if (op.in < 0 && tc_stem) {
+        int rc = launch_conv_tc_stem(L, img, img_u8, stem_scratch, reinterpret_cast<__nv_bfloat16*>(ptr[op.out]), B, 256, 256,
+                                     st);
+        if (rc && !sticky_rc) {
+          sticky_rc = rc;
+          err = "tcgen05 stem launch failed";
+        }
+        launches += 2;
+        tc_launches += 1;
+      } else if (op.in < 0)
         conv<T>(L, reinterpret_cast<const T*>(img), ptr[op.out], nullptr, B, 256, 256, st, /*in_nchw=*/true);
       else
         conv<T>(L, ptr[op.in], ptr[op.out], op.res >= 0 ? ptr[op.res] : nullptr, B, hr_bufs[op.in].H, hr_bufs[op.in].W, st);
