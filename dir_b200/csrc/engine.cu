@@ -425,7 +425,10 @@ int Engine::build(cudaStream_t st) {
         bk.c3 = make_conv(p + "conv3.weight", "", p + "bn3.", 1, 0, 1);
         if (!dry && bf16() && bk.c3.w16) {  // residual-adding layer: smaller n-tile leaves room for the residual ring
           bk.c3.tc_bn_cap = 128;  // (256 measured: -4 % images/s)
-          if (const char* e = getenv("DIRB200_C3_BN")) bk.c3.tc_bn_cap = atoi(e);  // experiment switch
+          if (const char* e = getenv("DIRB200_C3_BN")) {  // experiment switch: 64 / 128 / 256 only
+            const int v = atoi(e);
+            if (v == 64 || v == 128 || v == 256) bk.c3.tc_bn_cap = v;
+          }
           conv_tc_prepare_weights(bk.c3);
         }
         bk.has_ds = (b == 0);
